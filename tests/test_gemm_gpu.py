@@ -1,0 +1,85 @@
+"""GPU parity of fd_gemm (tcgen05 GEMM / implicit-GEMM conv) against plain torch fp32 math."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+@pytest.fixture(scope="module")
+def raw():
+    from flash.b200 import raw as r
+    return r
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (4096, 640, 640), (308, 1280, 2048),
+                                   (1024, 320, 1280), (16384, 1920, 640), (4, 1280, 320), (200, 72, 200)])
+@pytest.mark.parametrize("bn", [0, 64, 128, 256])
+def test_gemm_plain(raw, M, N, K, bn):
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    b = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+    ref = a.float() @ b.float().t()
+    out = raw.gemm(a, b, force_bn=bn)
+    torch.cuda.synchronize()
+    assert _rel(out, ref) < 6e-3, _rel(out, ref)
+    out32 = raw.gemm(a, b, out_fp32=True, force_bn=bn)
+    assert _rel(out32, ref) < 1e-5, _rel(out32, ref)
+
+
+def test_gemm_epilogue_and_lora(raw):
+    torch.manual_seed(0)
+    M, N, K, r = 1024, 640, 640, 64
+    x = torch.randn(M, K, device="cuda").bfloat16()
+    w = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+    t = torch.randn(M, r, device="cuda").bfloat16()
+    lb = (torch.randn(N, r, device="cuda") * 0.05).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda").bfloat16()
+    rowvec = torch.randn(4, N, device="cuda")
+    ref = x.float() @ w.float().t() + t.float() @ lb.float().t() + bias + res.float() \
+        + rowvec.repeat_interleave(M // 4, dim=0)
+    out = raw.gemm(x, w, a2=t, b2=lb, bias=bias, residual=res, rowvec=rowvec, rows_per_group=M // 4,
+                   out_fp32=True)
+    assert _rel(out, ref) < 1e-5, _rel(out, ref)
+
+
+def test_gemm_geglu(raw):
+    torch.manual_seed(1)
+    M, C = 512, 320
+    x = torch.randn(M, C, device="cuda").bfloat16()
+    w = (torch.randn(8 * C, C, device="cuda") / C ** 0.5).bfloat16()   # diffusers GEGLU.proj: [value | gate]
+    b = torch.randn(8 * C, device="cuda")
+    res = torch.randn(M, 4 * C, device="cuda").bfloat16()
+    h = x.float() @ w.float().t() + b
+    val, gate = h.chunk(2, dim=-1)
+    ref = val * torch.nn.functional.gelu(gate) + res.float()
+    # interleave 16 value rows / 16 gate rows
+    wv, wg = w[:4 * C].view(-1, 16, C), w[4 * C:].view(-1, 16, C)
+    wi = torch.stack([wv, wg], dim=1).reshape(8 * C, C).contiguous()
+    bi = torch.stack([b[:4 * C].view(-1, 16), b[4 * C:].view(-1, 16)], dim=1).reshape(-1).contiguous()
+    out = raw.gemm(x, wi, bias=bi, geglu=True, residual=res, out_fp32=True)
+    assert _rel(out, ref) < 1e-5, _rel(out, ref)
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout", [(2, 32, 32, 64, 64), (1, 64, 64, 320, 320), (2, 128, 128, 64, 128),
+                                             (4, 8, 8, 128, 192), (1, 16, 16, 1920, 640), (2, 32, 32, 8, 320)])
+def test_conv3x3(raw, NB, H, W, Cin, Cout):
+    torch.manual_seed(NB + H + Cin)
+    x = torch.randn(NB, Cin, H, W, device="cuda").bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, device="cuda") / (9 * Cin) ** 0.5).bfloat16()
+    bias = torch.randn(Cout, device="cuda")
+    torch.backends.cudnn.allow_tf32 = False
+    ref = torch.nn.functional.conv2d(x.float(), w.float(), bias, padding=1)     # NCHW
+    ref = ref.permute(0, 2, 3, 1).reshape(NB * H * W, Cout)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    cpad = (Cin + 63) // 64 * 64
+    wp = torch.zeros(Cout, 3, 3, cpad, device="cuda", dtype=torch.bfloat16)
+    wp[..., :Cin] = w.permute(0, 2, 3, 1)
+    wp = wp.reshape(Cout, 9 * cpad).contiguous()
+    out = raw.gemm(x_nhwc, wp, bias=bias, out_fp32=True, M=NB * H * W,
+                   conv=dict(NB_in=NB, H=H, W=W, C=Cin, taps=raw.TAPS_3X3))
+    assert _rel(out, ref) < 3e-5, _rel(out, ref)
