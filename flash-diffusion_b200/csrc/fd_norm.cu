@@ -1,0 +1,369 @@
+// fd_norm.cu — HBM-bound normalisation kernels (GroupNorm / LayerNorm, forward + backward) on
+// channels-last bf16 activations.  Vectorised 16-byte accesses, fp32 statistics, warp-shuffle
+// reductions.  UPSTREAM math: torch.nn.GroupNorm / LayerNorm as used by diffusers ResnetBlock2D,
+// Transformer2DModel and BasicTransformerBlock.
+#include "fd_common.cuh"
+#include "fd_host.h"
+
+namespace fd {
+
+__device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    float2 t;
+    t = unpack_bf16x2(u.x); f[0] = t.x; f[1] = t.y;
+    t = unpack_bf16x2(u.y); f[2] = t.x; f[3] = t.y;
+    t = unpack_bf16x2(u.z); f[4] = t.x; f[5] = t.y;
+    t = unpack_bf16x2(u.w); f[6] = t.x; f[7] = t.y;
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                              pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+// ---------------------------------------------------------------------------- GroupNorm
+// raw[n, g, 0..1] += (sum, sum of squares) over this block's rows.  blockDim = (nvec, rpi).
+// Optionally a second input (dy) turns this into the backward reduction:
+//   MODE 0: (sum x, sum x^2)
+//   MODE 1: (sum dyg, sum dyg * xhat) with dyg = dy * act'(pre) * gamma
+template <int MODE>
+__global__ void gn_reduce_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                 const float* __restrict__ stats, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float* __restrict__ raw, int HW,
+                                 int C, int G, int rows_per_block, int silu_act) {
+    extern __shared__ float sm[];  // [2*G]
+    const int n = blockIdx.y;
+    const int cpg = C / G;
+    const int vec = threadIdx.x;
+    const int c0 = vec * 8;
+    float a0[8], a1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
+    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 2 * G; i += blockDim.x * blockDim.y) sm[i] = 0.f;
+    __syncthreads();
+
+    float sc[8], sh[8], mu[8], rs[8];
+    if (MODE == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int g = (c0 + j) / cpg;
+            mu[j] = stats[(n * G + g) * 2 + 0];
+            rs[j] = stats[(n * G + g) * 2 + 1];
+            sc[j] = gamma[c0 + j];
+            sh[j] = beta[c0 + j];
+        }
+    }
+    const int r_begin = blockIdx.x * rows_per_block;
+    const int r_end = min(HW, r_begin + rows_per_block);
+    for (int r = r_begin + threadIdx.y; r < r_end; r += blockDim.y) {
+        const long long off = ((long long)n * HW + r) * C + c0;
+        float xv[8];
+        load8(x + off, xv);
+        if (MODE == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                a0[j] += xv[j];
+                a1[j] += xv[j] * xv[j];
+            }
+        } else {
+            float dv[8];
+            load8(dy + off, dv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xh = (xv[j] - mu[j]) * rs[j];
+                float d = dv[j];
+                if (silu_act) d *= silu_grad(xh * sc[j] + sh[j]);
+                d *= sc[j];
+                a0[j] += d;
+                a1[j] += d * xh;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int g = (c0 + j) / cpg;
+        atomicAdd(&sm[2 * g], a0[j]);
+        atomicAdd(&sm[2 * g + 1], a1[j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.y * blockDim.x + threadIdx.x; i < 2 * G; i += blockDim.x * blockDim.y)
+        atomicAdd(&raw[(long long)n * G * 2 + i], sm[i]);
+}
+
+__global__ void gn_finalize_kernel(const float* __restrict__ raw, float* __restrict__ stats, int total,
+                                   float inv_count, float eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float mean = raw[2 * i] * inv_count;
+    float var = raw[2 * i + 1] * inv_count - mean * mean;
+    var = fmaxf(var, 0.f);
+    stats[2 * i] = mean;
+    stats[2 * i + 1] = rsqrtf(var + eps);
+}
+
+// y = act((x - mean) * rstd * gamma + beta).  grid (row chunks, NB), block (nvec, rpi)
+__global__ void gn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ stats,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                bf16* __restrict__ y, int HW, int C, int G, int rows_per_block,
+                                int silu_act) {
+    const int n = blockIdx.y;
+    const int cpg = C / G;
+    const int c0 = threadIdx.x * 8;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int g = (c0 + j) / cpg;
+        const float mean = stats[(n * G + g) * 2 + 0];
+        const float rstd = stats[(n * G + g) * 2 + 1];
+        sc[j] = rstd * gamma[c0 + j];
+        sh[j] = beta[c0 + j] - mean * sc[j];
+    }
+    const int r_begin = blockIdx.x * rows_per_block;
+    const int r_end = min(HW, r_begin + rows_per_block);
+    for (int r = r_begin + threadIdx.y; r < r_end; r += blockDim.y) {
+        const long long off = ((long long)n * HW + r) * C + c0;
+        float v[8];
+        load8(x + off, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float t = v[j] * sc[j] + sh[j];
+            v[j] = silu_act ? silu(t) : t;
+        }
+        store8(y + off, v);
+    }
+}
+
+// dx = rstd * (dyg - (s1 + xhat * s2) / m)
+__global__ void gn_bwd_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                    const float* __restrict__ stats, const float* __restrict__ gamma,
+                                    const float* __restrict__ beta, const float* __restrict__ raw,
+                                    bf16* __restrict__ dx, int HW, int C, int G, int rows_per_block,
+                                    int silu_act, float inv_m) {
+    const int n = blockIdx.y;
+    const int cpg = C / G;
+    const int c0 = threadIdx.x * 8;
+    float sc[8], sh[8], mu[8], rs[8], s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int g = (c0 + j) / cpg;
+        mu[j] = stats[(n * G + g) * 2 + 0];
+        rs[j] = stats[(n * G + g) * 2 + 1];
+        s1[j] = raw[(n * G + g) * 2 + 0] * inv_m;
+        s2[j] = raw[(n * G + g) * 2 + 1] * inv_m;
+        sc[j] = gamma[c0 + j];
+        sh[j] = beta[c0 + j];
+    }
+    const int r_begin = blockIdx.x * rows_per_block;
+    const int r_end = min(HW, r_begin + rows_per_block);
+    for (int r = r_begin + threadIdx.y; r < r_end; r += blockDim.y) {
+        const long long off = ((long long)n * HW + r) * C + c0;
+        float xv[8], dv[8];
+        load8(x + off, xv);
+        load8(dy + off, dv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float xh = (xv[j] - mu[j]) * rs[j];
+            float d = dv[j];
+            if (silu_act) d *= silu_grad(xh * sc[j] + sh[j]);
+            d *= sc[j];
+            dv[j] = rs[j] * (d - s1[j] - xh * s2[j]);
+        }
+        store8(dx + off, dv);
+    }
+}
+
+static void gn_geometry(int HW, int C, int NB, dim3& grid, dim3& block, int& rows_per_block) {
+    const int nvec = C / 8;
+    int rpi = 256 / nvec;
+    if (rpi < 1) rpi = 1;
+    if (rpi > HW) rpi = HW;
+    block = dim3(nvec, rpi);
+    int target_blocks = (4 * num_sms() + NB - 1) / NB;  // per image
+    int max_chunks = (HW + rpi * 4 - 1) / (rpi * 4);    // at least 4 rows per thread
+    if (max_chunks < 1) max_chunks = 1;
+    int chunks = target_blocks < max_chunks ? target_blocks : max_chunks;
+    if (chunks < 1) chunks = 1;
+    rows_per_block = (HW + chunks - 1) / chunks;
+    chunks = (HW + rows_per_block - 1) / rows_per_block;
+    grid = dim3(chunks, NB);
+}
+
+// ---------------------------------------------------------------------------- LayerNorm
+// one warp per row; C % 8 == 0, C <= 2048
+constexpr int LN_MAXV = 8;  // vectors of 8 per lane -> C <= 2048
+
+__global__ void ln_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, bf16* __restrict__ y,
+                              float* __restrict__ stats, int rows, int C, float eps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const int nvec = C >> 3;
+    const bf16* xr = x + (long long)warp * C;
+    float v[LN_MAXV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nvec) {
+            load8(xr + vi * 8, v[i]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += v[i][j];
+        }
+    }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nvec) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float d = v[i][j] - mean;
+                q += d * d;
+            }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + eps);
+    if (stats != nullptr && lane == 0) {
+        stats[2 * warp] = mean;
+        stats[2 * warp + 1] = rstd;
+    }
+    bf16* yr = y + (long long)warp * C;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nvec) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float t = (v[i][j] - mean) * rstd;
+                if (gamma != nullptr) t = t * gamma[vi * 8 + j] + (beta != nullptr ? beta[vi * 8 + j] : 0.f);
+                o[j] = t;
+            }
+            store8(yr + vi * 8, o);
+        }
+    }
+}
+
+__global__ void ln_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ stats,
+                              const float* __restrict__ gamma, const bf16* __restrict__ dy,
+                              bf16* __restrict__ dx, int rows, int C) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const int nvec = C >> 3;
+    const bf16* xr = x + (long long)warp * C;
+    const bf16* dr = dy + (long long)warp * C;
+    const float mean = stats[2 * warp], rstd = stats[2 * warp + 1];
+    float xh[LN_MAXV][8], dg[LN_MAXV][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nvec) {
+            load8(xr + vi * 8, xh[i]);
+            load8(dr + vi * 8, dg[i]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                xh[i][j] = (xh[i][j] - mean) * rstd;
+                if (gamma != nullptr) dg[i][j] *= gamma[vi * 8 + j];
+                s1 += dg[i][j];
+                s2 += dg[i][j] * xh[i][j];
+            }
+        }
+    }
+    s1 = warp_sum(s1) / C;
+    s2 = warp_sum(s2) / C;
+    bf16* dxr = dx + (long long)warp * C;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nvec) {
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = rstd * (dg[i][j] - s1 - xh[i][j] * s2);
+            store8(dxr + vi * 8, o);
+        }
+    }
+}
+
+}  // namespace fd
+
+using namespace fd;
+
+extern "C" int fd_groupnorm_stats(const void* x, float* stats, int32_t NB, int32_t HW, int32_t C,
+                                  int32_t G, float eps, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FD_CHECK_ARG(C % 8 == 0 && C % G == 0 && C / 8 <= 1024, "fd_groupnorm_stats: bad C=%d G=%d", C, G);
+    // stats doubles as the raw accumulation buffer (sum, sumsq) before finalisation
+    FD_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * NB * G, stream));
+    dim3 grid, block;
+    int rpb;
+    gn_geometry(HW, C, NB, grid, block, rpb);
+    gn_reduce_kernel<0><<<grid, block, 2 * G * sizeof(float), stream>>>(
+        (const bf16*)x, nullptr, nullptr, nullptr, nullptr, stats, HW, C, G, rpb, 0);
+    FD_CHECK_LAUNCH();
+    const int total = NB * G;
+    gn_finalize_kernel<<<(total + 127) / 128, 128, 0, stream>>>(stats, stats, total,
+                                                                1.0f / ((float)HW * (C / G)), eps);
+    FD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int fd_groupnorm_apply(const void* x, const float* stats, const float* gamma,
+                                  const float* beta, void* y, int32_t NB, int32_t HW, int32_t C,
+                                  int32_t G, int32_t silu_act, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FD_CHECK_ARG(C % 8 == 0 && C % G == 0 && C / 8 <= 1024, "fd_groupnorm_apply: bad C=%d G=%d", C, G);
+    dim3 grid, block;
+    int rpb;
+    gn_geometry(HW, C, NB, grid, block, rpb);
+    gn_apply_kernel<<<grid, block, 0, stream>>>((const bf16*)x, stats, gamma, beta, (bf16*)y, HW, C, G,
+                                                rpb, silu_act);
+    FD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int fd_groupnorm_bwd(const void* x, const float* stats, const float* gamma,
+                                const float* beta, const void* dy, void* dx, float* scratch,
+                                int32_t NB, int32_t HW, int32_t C, int32_t G, int32_t silu_act,
+                                void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FD_CHECK_ARG(C % 8 == 0 && C % G == 0 && C / 8 <= 1024, "fd_groupnorm_bwd: bad C=%d G=%d", C, G);
+    FD_CHECK_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float) * 2 * NB * G, stream));
+    dim3 grid, block;
+    int rpb;
+    gn_geometry(HW, C, NB, grid, block, rpb);
+    gn_reduce_kernel<1><<<grid, block, 2 * G * sizeof(float), stream>>>(
+        (const bf16*)x, (const bf16*)dy, stats, gamma, beta, scratch, HW, C, G, rpb, silu_act);
+    FD_CHECK_LAUNCH();
+    gn_bwd_apply_kernel<<<grid, block, 0, stream>>>((const bf16*)x, (const bf16*)dy, stats, gamma, beta,
+                                                    scratch, (bf16*)dx, HW, C, G, rpb, silu_act,
+                                                    1.0f / ((float)HW * (C / G)));
+    FD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int fd_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y,
+                                float* stats, int32_t rows, int32_t C, float eps, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FD_CHECK_ARG(C % 8 == 0 && C <= 8 * 32 * LN_MAXV, "fd_layernorm_fwd: bad C=%d", C);
+    const int warps_per_block = 8;
+    const int blocks = (rows + warps_per_block - 1) / warps_per_block;
+    ln_fwd_kernel<<<blocks, warps_per_block * 32, 0, stream>>>((const bf16*)x, gamma, beta, (bf16*)y,
+                                                               stats, rows, C, eps);
+    FD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int fd_layernorm_bwd(const void* x, const float* stats, const float* gamma,
+                                const void* dy, void* dx, int32_t rows, int32_t C, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FD_CHECK_ARG(C % 8 == 0 && C <= 8 * 32 * LN_MAXV, "fd_layernorm_bwd: bad C=%d", C);
+    const int warps_per_block = 8;
+    const int blocks = (rows + warps_per_block - 1) / warps_per_block;
+    ln_bwd_kernel<<<blocks, warps_per_block * 32, 0, stream>>>((const bf16*)x, stats, gamma,
+                                                               (const bf16*)dy, (bf16*)dx, rows, C);
+    FD_CHECK_LAUNCH();
+    return 0;
+}

@@ -76,3 +76,215 @@ def gemm(a1, b1, *, a2=None, b2=None, bias=None, rowvec=None, rows_per_group=0, 
     args.force_bn = force_bn
     check(lib.fd_gemm(byref(args), stream_ptr()), "fd_gemm")
     return out
+
+
+# ------------------------------------------------------------------ normalisation
+def groupnorm_stats(x, NB, HW, C, G, eps):
+    lib = load(); _req(x, BF16, "x")
+    stats = torch.empty((NB, G, 2), device=x.device, dtype=torch.float32)
+    check(lib.fd_groupnorm_stats(ptr(x), ptr(stats), c_int32(NB), c_int32(HW), c_int32(C), c_int32(G),
+                                 c_float(eps), stream_ptr()), "fd_groupnorm_stats")
+    return stats
+
+
+def groupnorm_apply(x, stats, gamma, beta, NB, HW, C, G, silu):
+    lib = load(); _req(x, BF16, "x"); _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")
+    y = torch.empty_like(x)
+    check(lib.fd_groupnorm_apply(ptr(x), ptr(stats), ptr(gamma), ptr(beta), ptr(y), c_int32(NB), c_int32(HW),
+                                 c_int32(C), c_int32(G), c_int32(1 if silu else 0), stream_ptr()),
+          "fd_groupnorm_apply")
+    return y
+
+
+def groupnorm_bwd(x, stats, gamma, beta, dy, NB, HW, C, G, silu):
+    lib = load(); _req(x, BF16, "x"); _req(dy, BF16, "dy")
+    dx = torch.empty_like(x)
+    scratch = torch.empty((NB, G, 2), device=x.device, dtype=torch.float32)
+    check(lib.fd_groupnorm_bwd(ptr(x), ptr(stats), ptr(gamma), ptr(beta), ptr(dy), ptr(dx), ptr(scratch),
+                               c_int32(NB), c_int32(HW), c_int32(C), c_int32(G), c_int32(1 if silu else 0),
+                               stream_ptr()), "fd_groupnorm_bwd")
+    return dx
+
+
+def layernorm_fwd(x, gamma, beta, eps, save_stats=False):
+    lib = load(); _req(x, BF16, "x")
+    rows, C = x.shape
+    assert x.is_contiguous()
+    y = torch.empty_like(x)
+    stats = torch.empty((rows, 2), device=x.device, dtype=torch.float32) if save_stats else None
+    check(lib.fd_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(stats), c_int32(rows), c_int32(C),
+                               c_float(eps), stream_ptr()), "fd_layernorm_fwd")
+    return (y, stats) if save_stats else y
+
+
+def layernorm_bwd(x, stats, gamma, dy):
+    lib = load(); _req(x, BF16, "x"); _req(dy, BF16, "dy")
+    rows, C = x.shape
+    assert x.is_contiguous() and dy.is_contiguous()
+    dx = torch.empty_like(x)
+    check(lib.fd_layernorm_bwd(ptr(x), ptr(stats), ptr(gamma), ptr(dy), ptr(dx), c_int32(rows), c_int32(C),
+                               stream_ptr()), "fd_layernorm_bwd")
+    return dx
+
+
+# ------------------------------------------------------------------ attention
+def attention_fwd(q, k, v, H, scale=None, need_lse=False):
+    """q [B,Nq,H*64] view (last-dim stride 1), k/v [B,Nkv,H*64] views -> o [B,Nq,H*64] bf16."""
+    lib = load(); _req(q, BF16, "q"); _req(k, BF16, "k"); _req(v, BF16, "v")
+    B, Nq, HD = q.shape
+    Nkv = k.shape[1]
+    assert HD == H * 64 and q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1
+    o = torch.empty((B, Nq, HD), device=q.device, dtype=BF16)
+    lse = torch.empty((B, H, Nq), device=q.device, dtype=torch.float32) if need_lse else None
+    a = _l.FdAttnArgs()
+    a.q, a.ldq, a.q_batch_stride = ptr(q), q.stride(1), q.stride(0)
+    a.k, a.ldk, a.k_batch_stride = ptr(k), k.stride(1), k.stride(0)
+    a.v, a.ldv, a.v_batch_stride = ptr(v), v.stride(1), v.stride(0)
+    a.o, a.ldo, a.o_batch_stride = ptr(o), o.stride(1), o.stride(0)
+    a.lse = ptr(lse)
+    a.B, a.H, a.Nq, a.Nkv = B, H, Nq, Nkv
+    a.scale = scale if scale is not None else 64 ** -0.5
+    check(lib.fd_attn_fwd(byref(a), stream_ptr()), "fd_attn_fwd")
+    return (o, lse) if need_lse else o
+
+
+# ------------------------------------------------------------------ layout / elementwise
+def nchw_to_nhwc(x, Cpad):
+    lib = load(); _req(x, torch.float32, "x")
+    NB, C, H, W = x.shape
+    x = x.contiguous()
+    y = torch.empty((NB, H, W, Cpad), device=x.device, dtype=BF16)
+    check(lib.fd_nchw_to_nhwc(ptr(x), ptr(y), c_int32(NB), c_int32(C), c_int32(H), c_int32(W), c_int32(Cpad),
+                              stream_ptr()), "fd_nchw_to_nhwc")
+    return y
+
+
+def nhwc_to_nchw(x, NB, C, H, W):
+    """x: [NB*H*W, ld] fp32 or bf16 (first C columns valid) -> [NB,C,H,W] fp32."""
+    lib = load()
+    y = torch.empty((NB, C, H, W), device=x.device, dtype=torch.float32)
+    check(lib.fd_nhwc_to_nchw(ptr(x), c_int32(1 if x.dtype == torch.float32 else 0), c_int64(x.stride(0)),
+                              ptr(y), c_int32(NB), c_int32(C), c_int32(H), c_int32(W), stream_ptr()),
+          "fd_nhwc_to_nchw")
+    return y
+
+
+def upsample2x(x, NB, H, W, C):
+    lib = load(); _req(x, BF16, "x")
+    y = torch.empty((NB * 4 * H * W, C), device=x.device, dtype=BF16)
+    check(lib.fd_upsample2x(ptr(x), ptr(y), c_int32(NB), c_int32(H), c_int32(W), c_int32(C), stream_ptr()),
+          "fd_upsample2x")
+    return y
+
+
+def upsample2x_bwd(dy, NB, H, W, C):
+    lib = load(); _req(dy, BF16, "dy")
+    dx = torch.empty((NB * H * W, C), device=dy.device, dtype=BF16)
+    check(lib.fd_upsample2x_bwd(ptr(dy), ptr(dx), c_int32(NB), c_int32(H), c_int32(W), c_int32(C),
+                                stream_ptr()), "fd_upsample2x_bwd")
+    return dx
+
+
+def space_to_depth(x, NB, H, W, C):
+    lib = load(); _req(x, BF16, "x")
+    y = torch.empty((4 * NB * (H // 2) * (W // 2), C), device=x.device, dtype=BF16)
+    check(lib.fd_space_to_depth(ptr(x), ptr(y), c_int32(NB), c_int32(H), c_int32(W), c_int32(C), stream_ptr()),
+          "fd_space_to_depth")
+    return y
+
+
+def depth_to_space(x, NB, H, W, C):
+    lib = load(); _req(x, BF16, "x")
+    y = torch.empty((NB * H * W, C), device=x.device, dtype=BF16)
+    check(lib.fd_depth_to_space(ptr(x), ptr(y), c_int32(NB), c_int32(H), c_int32(W), c_int32(C), stream_ptr()),
+          "fd_depth_to_space")
+    return y
+
+
+def concat_channels(a, b):
+    lib = load(); _req(a, BF16, "a"); _req(b, BF16, "b")
+    rows = a.shape[0]
+    assert a.is_contiguous() and b.is_contiguous() and b.shape[0] == rows
+    y = torch.empty((rows, a.shape[1] + b.shape[1]), device=a.device, dtype=BF16)
+    check(lib.fd_concat_channels(ptr(a), c_int32(a.shape[1]), ptr(b), c_int32(b.shape[1]), ptr(y), c_int64(rows),
+                                 stream_ptr()), "fd_concat_channels")
+    return y
+
+
+def add(a, b):
+    lib = load(); _req(a, BF16, "a"); _req(b, BF16, "b")
+    assert a.shape == b.shape and a.is_contiguous() and b.is_contiguous()
+    y = torch.empty_like(a)
+    check(lib.fd_add(ptr(a), ptr(b), ptr(y), c_int64(a.numel()), stream_ptr()), "fd_add")
+    return y
+
+
+def transpose(x):
+    lib = load(); _req(x, BF16, "x")
+    rows, cols = x.shape
+    assert x.is_contiguous()
+    y = torch.empty((cols, rows), device=x.device, dtype=BF16)
+    check(lib.fd_transpose(ptr(x), ptr(y), c_int32(rows), c_int32(cols), stream_ptr()), "fd_transpose")
+    return y
+
+
+def cast_scale(x, scale=1.0):
+    lib = load(); _req(x, torch.float32, "x")
+    x = x.contiguous()
+    y = torch.empty(x.shape, device=x.device, dtype=BF16)
+    check(lib.fd_cast_scale(ptr(x), ptr(y), c_int64(x.numel()), c_float(scale), stream_ptr()), "fd_cast_scale")
+    return y
+
+
+def silu_f32_to_bf16(x):
+    lib = load(); _req(x, torch.float32, "x")
+    x = x.contiguous()
+    y = torch.empty(x.shape, device=x.device, dtype=BF16)
+    check(lib.fd_silu_f32_to_bf16(ptr(x), ptr(y), c_int64(x.numel()), stream_ptr()), "fd_silu_f32_to_bf16")
+    return y
+
+
+def timestep_embedding(t, dim):
+    lib = load(); _req(t, torch.float32, "t")
+    y = torch.empty((t.numel(), dim), device=t.device, dtype=BF16)
+    check(lib.fd_timestep_embedding(ptr(t), ptr(y), c_int32(t.numel()), c_int32(dim), stream_ptr()),
+          "fd_timestep_embedding")
+    return y
+
+
+def geglu_bwd(acc, dout):
+    lib = load(); _req(acc, BF16, "acc"); _req(dout, BF16, "dout")
+    M, N = acc.shape
+    assert acc.is_contiguous() and dout.is_contiguous() and dout.shape == (M, N // 2)
+    dacc = torch.empty_like(acc)
+    check(lib.fd_geglu_bwd(ptr(acc), ptr(dout), ptr(dacc), c_int64(M), c_int32(N), stream_ptr()), "fd_geglu_bwd")
+    return dacc
+
+
+# ------------------------------------------------------------------ distillation-step kernels (fp32)
+def step_add_noise(z, noise, sa, sg):
+    lib = load(); _req(z, torch.float32, "z")
+    B = z.shape[0]
+    out = torch.empty_like(z)
+    check(lib.fd_step_add_noise(ptr(z.contiguous()), ptr(noise.contiguous()), ptr(sa), ptr(sg), ptr(out),
+                                c_int32(B), c_int64(z.numel() // B), stream_ptr()), "fd_step_add_noise")
+    return out
+
+
+def step_cfg_dpm(eps_c, eps_u, x, x0_prev, coef6):
+    """in-place on x and x0_prev (fp32, contiguous)."""
+    lib = load()
+    arr = (c_float * 6)(*[float(c) for c in coef6])
+    check(lib.fd_step_cfg_dpm(ptr(eps_c), ptr(eps_u), ptr(x), ptr(x0_prev), arr, c_int64(x.numel()),
+                              stream_ptr()), "fd_step_cfg_dpm")
+    return x
+
+
+def step_student_output(x_t, eps, sa, sg, c_skip, c_out):
+    lib = load()
+    B = x_t.shape[0]
+    out = torch.empty_like(x_t)
+    check(lib.fd_step_student_output(ptr(x_t), ptr(eps), ptr(sa), ptr(sg), ptr(c_skip), ptr(c_out), ptr(out),
+                                     c_int32(B), c_int64(x_t.numel() // B), stream_ptr()),
+          "fd_step_student_output")
+    return out

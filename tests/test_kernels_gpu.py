@@ -1,0 +1,157 @@
+"""GPU parity of the attention / normalisation / elementwise kernels against torch fp32 math."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+@pytest.fixture(scope="module")
+def raw():
+    from flash.b200 import raw as r
+    return r
+
+
+@pytest.mark.parametrize("B,H,Nq,Nkv", [(1, 1, 128, 128), (2, 3, 256, 384), (2, 10, 1024, 1024), (1, 5, 4096, 4096),
+                                        (2, 4, 1024, 77), (1, 2, 200, 333), (3, 2, 64, 77)])
+def test_attention_fwd(raw, B, H, Nq, Nkv):
+    torch.manual_seed(B * 100 + H + Nq + Nkv)
+    q = torch.randn(B, Nq, H * 64, device="cuda").bfloat16()
+    k = torch.randn(B, Nkv, H * 64, device="cuda").bfloat16()
+    v = torch.randn(B, Nkv, H * 64, device="cuda").bfloat16()
+    o, lse = raw.attention_fwd(q, k, v, H, need_lse=True)
+    qf = q.float().view(B, Nq, H, 64).transpose(1, 2)
+    kf = k.float().view(B, Nkv, H, 64).transpose(1, 2)
+    vf = v.float().view(B, Nkv, H, 64).transpose(1, 2)
+    s = qf @ kf.transpose(-1, -2) / 8.0
+    ref = (torch.softmax(s, dim=-1) @ vf).transpose(1, 2).reshape(B, Nq, H * 64)
+    assert _rel(o, ref) < 1e-2, _rel(o, ref)
+    assert _rel(lse, torch.logsumexp(s, dim=-1)) < 1e-4
+
+
+def test_attention_fused_qkv_views(raw):
+    torch.manual_seed(5)
+    B, N, H = 2, 512, 5
+    qkv = torch.randn(B, N, 3 * H * 64, device="cuda").bfloat16()
+    q, k, v = qkv[..., :H * 64], qkv[..., H * 64:2 * H * 64], qkv[..., 2 * H * 64:]
+    o = raw.attention_fwd(q, k, v, H)
+    ref = F.scaled_dot_product_attention(q.float().view(B, N, H, 64).transpose(1, 2), k.float().view(B, N, H, 64).transpose(1, 2),
+                                         v.float().view(B, N, H, 64).transpose(1, 2)).transpose(1, 2).reshape(B, N, H * 64)
+    assert _rel(o, ref) < 1e-2
+
+
+@pytest.mark.parametrize("NB,HW,C,silu", [(2, 1024, 320, True), (4, 16384, 320, True), (1, 4096, 640, False),
+                                          (2, 1024, 1920, True), (3, 64, 2560, True), (2, 256, 960, False)])
+def test_groupnorm(raw, NB, HW, C, silu):
+    torch.manual_seed(C + HW)
+    G = 32
+    x = (torch.randn(NB, HW, C, device="cuda") * 2 + 0.5).bfloat16()
+    gamma = torch.randn(C, device="cuda")
+    beta = torch.randn(C, device="cuda")
+    stats = raw.groupnorm_stats(x, NB, HW, C, G, 1e-5)
+    y = raw.groupnorm_apply(x, stats, gamma, beta, NB, HW, C, G, silu)
+    xf = x.float().transpose(1, 2).requires_grad_(True)           # [NB, C, HW]
+    ref = F.group_norm(xf, G, gamma, beta, 1e-5)
+    if silu:
+        ref = F.silu(ref)
+    assert _rel(y, ref.transpose(1, 2)) < 6e-3
+    dy = torch.randn(NB, HW, C, device="cuda").bfloat16()
+    ref.backward(dy.float().transpose(1, 2))
+    dx = raw.groupnorm_bwd(x, stats, gamma, beta, dy, NB, HW, C, G, silu)
+    assert _rel(dx, xf.grad.transpose(1, 2)) < 8e-3, _rel(dx, xf.grad.transpose(1, 2))
+
+
+@pytest.mark.parametrize("rows,C", [(4096, 640), (1000, 1280), (308, 320), (77, 2048), (64, 1152)])
+def test_layernorm(raw, rows, C):
+    torch.manual_seed(rows + C)
+    x = (torch.randn(rows, C, device="cuda") * 1.5 + 0.3).bfloat16()
+    gamma = torch.randn(C, device="cuda")
+    beta = torch.randn(C, device="cuda")
+    y, stats = raw.layernorm_fwd(x, gamma, beta, 1e-5, save_stats=True)
+    xf = x.float().requires_grad_(True)
+    ref = F.layer_norm(xf, (C,), gamma, beta, 1e-5)
+    assert _rel(y, ref) < 6e-3
+    dy = torch.randn(rows, C, device="cuda").bfloat16()
+    ref.backward(dy.float())
+    dx = raw.layernorm_bwd(x, stats, gamma, dy)
+    assert _rel(dx, xf.grad) < 8e-3
+    y2 = raw.layernorm_fwd(x, None, None, 1e-6)
+    assert _rel(y2, F.layer_norm(x.float(), (C,), None, None, 1e-6)) < 6e-3
+
+
+def test_layout_and_elementwise(raw):
+    torch.manual_seed(0)
+    NB, C, H, W = 2, 4, 16, 16
+    x = torch.randn(NB, C, H, W, device="cuda")
+    y = raw.nchw_to_nhwc(x, 8)
+    assert torch.equal(y[..., :4], x.permute(0, 2, 3, 1).bfloat16()) and (y[..., 4:] == 0).all()
+    back = raw.nhwc_to_nchw(y.view(NB * H * W, 8), NB, C, H, W)
+    assert torch.equal(back, x.bfloat16().float())
+    o32 = torch.randn(NB * H * W, 4, device="cuda")
+    assert torch.equal(raw.nhwc_to_nchw(o32, NB, 4, H, W), o32.view(NB, H, W, 4).permute(0, 3, 1, 2))
+
+    C = 64
+    a = torch.randn(NB, H, W, C, device="cuda").bfloat16()
+    up = raw.upsample2x(a, NB, H, W, C).view(NB, 2 * H, 2 * W, C)
+    ref = F.interpolate(a.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(up.float(), ref)
+    g = torch.randn(NB, 2 * H, 2 * W, C, device="cuda").bfloat16()
+    gd = raw.upsample2x_bwd(g, NB, H, W, C).view(NB, H, W, C)
+    refg = g.float().view(NB, H, 2, W, 2, C).sum(dim=(2, 4))
+    assert _rel(gd, refg) < 5e-3
+    s2d = raw.space_to_depth(a, NB, H, W, C).view(2, 2, NB, H // 2, W // 2, C)
+    assert torch.equal(s2d[1, 0], a[:, 1::2, 0::2]) and torch.equal(s2d[0, 1], a[:, 0::2, 1::2])
+    assert torch.equal(raw.depth_to_space(s2d.reshape(-1, C), NB, H, W, C).view(NB, H, W, C), a)
+    b = torch.randn(NB * H * W, 128, device="cuda").bfloat16()
+    cat = raw.concat_channels(a.view(-1, C), b)
+    assert torch.equal(cat, torch.cat([a.view(-1, C), b], dim=1))
+    assert torch.equal(raw.add(b, b), (b.float() * 2).bfloat16())
+    assert torch.equal(raw.transpose(b), b.t().contiguous())
+    w = torch.randn(33, 70, device="cuda")
+    assert torch.equal(raw.cast_scale(w, 0.5), (w * 0.5).bfloat16())
+    assert _rel(raw.silu_f32_to_bf16(w), F.silu(w)) < 4e-3
+    t = torch.tensor([999.0, 500.0, 3.0], device="cuda")
+    emb = raw.timestep_embedding(t, 320)
+    half = 160
+    f = torch.exp(-math.log(10000.0) * torch.arange(half, device="cuda") / half)
+    ref = torch.cat([torch.cos(t[:, None] * f), torch.sin(t[:, None] * f)], dim=-1)
+    assert (emb.float() - ref).abs().max() < 1e-2
+
+
+def test_geglu_bwd(raw):
+    torch.manual_seed(3)
+    M, N = 256, 640
+    acc = torch.randn(M, N, device="cuda").bfloat16()
+    dout = torch.randn(M, N // 2, device="cuda").bfloat16()
+    a = acc.float().view(M, N // 32, 2, 16).requires_grad_(True)
+    out = (a[:, :, 0] * F.gelu(a[:, :, 1])).reshape(M, N // 2)
+    out.backward(dout.float())
+    d = raw.geglu_bwd(acc, dout)
+    assert _rel(d, a.grad.reshape(M, N)) < 6e-3
+
+
+def test_step_kernels(raw):
+    torch.manual_seed(4)
+    B, n = 3, 4 * 32 * 32
+    z, noise, eps_c, eps_u = (torch.randn(B, 4, 32, 32, device="cuda") for _ in range(4))
+    sa, sg = torch.rand(B, device="cuda") + 0.1, torch.rand(B, device="cuda")
+    out = raw.step_add_noise(z, noise, sa, sg)
+    assert torch.allclose(out, sa.view(-1, 1, 1, 1) * z + sg.view(-1, 1, 1, 1) * noise, atol=1e-6)
+    x = z.clone(); x0p = noise.clone()
+    coef = [7.5, 0.8, 0.6, 0.9, -0.3, 0.2]
+    w, al, si, cx, cd0, cd1 = coef
+    eps = w * eps_c + (1 - w) * eps_u
+    x0 = (z - si * eps) / al
+    ref = cx * z - cd0 * x0 - cd1 * (x0 - noise)
+    raw.step_cfg_dpm(eps_c, eps_u, x, x0p, coef)
+    assert torch.allclose(x, ref, atol=1e-4, rtol=1e-5) and torch.allclose(x0p, x0, atol=1e-5, rtol=1e-5)
+    cs, co = torch.rand(B, device="cuda"), torch.rand(B, device="cuda")
+    so = raw.step_student_output(z, eps_c, sa, sg, cs, co)
+    v = lambda t: t.view(-1, 1, 1, 1)
+    assert torch.allclose(so, v(cs) * z + v(co) * (z - v(sg) * eps_c) / v(sa), atol=1e-5, rtol=1e-5)
