@@ -130,6 +130,16 @@ __global__ void concat_kernel(const uint4* __restrict__ a, int V1, const uint4* 
     }
 }
 
+__global__ void slice_kernel(const uint4* __restrict__ x, int Vtot, int v0, int V, uint4* __restrict__ y,
+                             long long rows) {
+    const long long total = rows * V;
+    FD_GRID_STRIDE(i, total) {
+        const int v = (int)(i % V);
+        const long long r = i / V;
+        y[i] = x[r * Vtot + v0 + v];
+    }
+}
+
 __global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ b, bf16* __restrict__ y,
                            long long nvec) {
     FD_GRID_STRIDE(i, nvec) {
@@ -310,6 +320,14 @@ extern "C" int fd_concat_channels(const void* a, int32_t C1, const void* b, int3
     FD_CHECK_ARG(C1 % 8 == 0 && C2 % 8 == 0, "fd_concat_channels: C %% 8");
     const long long total = rows * ((C1 + C2) / 8);
     concat_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>((const uint4*)a, C1 / 8, (const uint4*)b, C2 / 8, (uint4*)y, rows);
+    FD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int fd_slice_channels(const void* x, int32_t Ctot, int32_t c0, int32_t C, void* y, int64_t rows,
+                                 void* stream) {
+    FD_CHECK_ARG(Ctot % 8 == 0 && c0 % 8 == 0 && C % 8 == 0, "fd_slice_channels: C %% 8");
+    slice_kernel<<<grid_for(rows * (C / 8)), 256, 0, (cudaStream_t)stream>>>((const uint4*)x, Ctot / 8, c0 / 8, C / 8, (uint4*)y, rows);
     FD_CHECK_LAUNCH();
     return 0;
 }

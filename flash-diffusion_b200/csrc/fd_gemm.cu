@@ -29,6 +29,7 @@ struct GemmKParams {
     const float* bias;
     const float* rowvec;
     int rows_per_group;
+    long long ldrv;
     int geglu;
     const bf16* residual;
     long long ldr;
@@ -75,8 +76,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int row, in
         }
     }
     if (p.rowvec != nullptr && row_ok) {
-        const float* rv = p.rowvec + (long long)(row / p.rows_per_group) * N + col0;
-        if (full) {
+        const float* rv = p.rowvec + (long long)(row / p.rows_per_group) * p.ldrv + col0;
+        if (full && (p.ldrv & 3) == 0) {
             const float4* b4 = reinterpret_cast<const float4*>(rv);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -393,6 +394,7 @@ extern "C" int fd_gemm(const FdGemmArgs* a, void* stream_) {
     p.bias = a->bias;
     p.rowvec = a->rowvec;
     p.rows_per_group = a->rows_per_group;
+    p.ldrv = a->ldrv > 0 ? a->ldrv : a->N;
     p.geglu = a->geglu;
     p.residual = (const bf16*)a->residual;
     p.ldr = a->ldr;

@@ -27,7 +27,7 @@ class FdGemmArgs(Structure):
         ("tap_dn", c_int32 * FD_MAX_TAPS), ("tap_dh", c_int32 * FD_MAX_TAPS),
         ("tap_dw", c_int32 * FD_MAX_TAPS),
         ("bias", c_void_p),
-        ("rowvec", c_void_p), ("rows_per_group", c_int32),
+        ("rowvec", c_void_p), ("rows_per_group", c_int32), ("ldrv", c_int64),
         ("geglu", c_int32),
         ("residual", c_void_p), ("ldr", c_int64),
         ("out", c_void_p), ("ldo", c_int64), ("out_fp32", c_int32),

@@ -1,0 +1,575 @@
+"""Autograd-aware operators over the raw C-ABI kernels.
+
+Every operator here runs hand-written sm_100a kernels (flash.b200.raw) in both directions.  Under
+`torch.no_grad()` (frozen teacher, ~85% of the step) the raw kernel is called directly; when a
+gradient is required a `torch.autograd.Function` records the tensors its hand-written backward needs.
+
+Only activation gradients (dX) and LoRA A/B gradients exist: every other weight is frozen in the
+Flash-Diffusion step (reference: examples/train_flash_sdxl.py:206-219, src/flash/trainer/trainer.py:115-124).
+
+Activations are channels-last bf16 matrices [NB*H*W, C]; `geom` = (NB, H, W).
+"""
+import torch
+
+from . import raw
+
+BF16 = torch.bfloat16
+
+
+def _grad_on(*tensors):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
+
+
+def _version(p):
+    return (p.data_ptr(), p._version, p.device)
+
+
+class PackCache:
+    """Per-module cache of kernel-ready (bf16, re-laid-out) copies of fp32 parameters, keyed on the
+    parameters' version counters so that optimizer updates (LoRA) invalidate them."""
+
+    def __init__(self):
+        self.store = {}
+
+    def get(self, key, params, build):
+        sig = tuple(_version(p) for p in params)
+        hit = self.store.get(key)
+        if hit is not None and hit[0] == sig:
+            return hit[1]
+        with torch.no_grad():
+            val = build()
+        self.store[key] = (sig, val)
+        return val
+
+
+def cache_of(module) -> PackCache:
+    c = module.__dict__.get("_fd_cache")
+    if c is None:
+        c = PackCache()
+        module.__dict__["_fd_cache"] = c
+    return c
+
+
+# ------------------------------------------------------------------------------------------------
+# weight packing
+# ------------------------------------------------------------------------------------------------
+def pack_matrix(w, scale=1.0):
+    """fp32 [N, K] -> bf16 [N, K] (K padded to a multiple of 8 is the caller's business)."""
+    return raw.cast_scale(w.detach().reshape(w.shape[0], -1).float().contiguous(), scale)
+
+
+def pack_conv3x3(w):
+    """[Cout, Cin, kh, kw] -> bf16 [Cout, taps * ceil64(Cin)], K ordered (tap, channel)."""
+    Cout, Cin, kh, kw = w.shape
+    cpad = (Cin + 63) // 64 * 64
+    buf = torch.zeros((Cout, kh * kw, cpad), device=w.device, dtype=torch.float32)
+    buf[:, :, :Cin] = w.detach().float().permute(0, 2, 3, 1).reshape(Cout, kh * kw, Cin)
+    return raw.cast_scale(buf.reshape(Cout, kh * kw * cpad), 1.0)
+
+
+def pack_conv3x3_dgrad(w):
+    """weights of the data-gradient convolution: Wd[ci, (kh',kw'), co] = W[co, ci, 2-kh', 2-kw']."""
+    wd = w.detach().float().flip(2, 3).permute(1, 0, 2, 3).contiguous()   # [Cin, Cout, kh', kw']
+    return pack_conv3x3(wd)
+
+
+def pack_geglu(w, b):
+    """diffusers GEGLU.proj [2*inner, C] = [value | gate] -> 16-row interleaved blocks (fd_gemm geglu)."""
+    two_inner, C = w.shape
+    inner = two_inner // 2
+    wv, wg = w.detach().float()[:inner].reshape(-1, 16, C), w.detach().float()[inner:].reshape(-1, 16, C)
+    wi = torch.stack([wv, wg], dim=1).reshape(two_inner, C).contiguous()
+    bi = torch.stack([b.detach().float()[:inner].reshape(-1, 16), b.detach().float()[inner:].reshape(-1, 16)],
+                     dim=1).reshape(-1).contiguous()
+    return raw.cast_scale(wi, 1.0), bi
+
+
+def _f32(p):
+    return None if p is None else p.detach().float().contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# convolution (implicit GEMM)
+# ------------------------------------------------------------------------------------------------
+# taps of the stride-2 3x3 conv (pad 1) over the space-to-depth input [4*NB, H/2, W/2, C]:
+# input row 2*ho + kh - 1 -> phase (kh-1)&1, row offset -1 for kh = 0 else 0
+def _s2_taps(NB):
+    taps = []
+    for kh in range(3):
+        for kw in range(3):
+            ph, pw = (kh - 1) & 1, (kw - 1) & 1
+            dh, dw = (-1 if kh == 0 else 0), (-1 if kw == 0 else 0)
+            taps.append(((ph * 2 + pw) * NB, dh, dw))
+    return taps
+
+
+def _conv_fwd_raw(x, geom, wpack, bias, rowvec, residual, shortcut, stride, Cin, out_fp32=False):
+    NB, H, W = geom
+    if stride == 1:
+        conv = dict(NB_in=NB, H=H, W=W, C=Cin, taps=raw.TAPS_3X3)
+        a1, M, rpg = x, NB * H * W, H * W
+    else:
+        a1 = raw.space_to_depth(x, NB, H, W, Cin)
+        conv = dict(NB_in=4 * NB, H=H // 2, W=W // 2, C=Cin, taps=_s2_taps(NB))
+        M, rpg = NB * (H // 2) * (W // 2), (H // 2) * (W // 2)
+    a2 = b2 = None
+    if shortcut is not None:
+        a2, b2 = shortcut
+    return raw.gemm(a1, wpack, a2=a2, b2=b2, bias=bias, rowvec=rowvec, rows_per_group=rpg, residual=residual,
+                    conv=conv, M=M, out_fp32=out_fp32)
+
+
+class _ConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, x2, mod, geom, stride, rowvec, out_fp32):
+        p = mod.pack()
+        shortcut = None
+        if x2 is not None:
+            shortcut = (x2, mod.pack_shortcut())
+        y = _conv_fwd_raw(x, geom, p["w"], p["b"], rowvec, residual, shortcut, stride, mod.cin, out_fp32)
+        ctx.mod, ctx.geom, ctx.stride = mod, geom, stride
+        ctx.has_res, ctx.has_x2 = residual is not None, x2 is not None
+        ctx.out_fp32 = out_fp32
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        mod, (NB, H, W), stride = ctx.mod, ctx.geom, ctx.stride
+        if dy.dtype != BF16:
+            dy = raw.cast_scale(dy.contiguous().float(), 1.0)
+        dy = dy.contiguous()
+        dx = dres = dx2 = None
+        if ctx.needs_input_grad[0]:
+            dx = conv_dgrad(dy, (NB, H, W), mod, stride)
+        if ctx.has_res and ctx.needs_input_grad[1]:
+            dres = dy
+        if ctx.has_x2 and ctx.needs_input_grad[2]:
+            dx2 = raw.gemm(dy, mod.pack_shortcut_t())
+        return dx, dres, dx2, None, None, None, None, None
+
+
+def conv_dgrad(dy, geom, mod, stride):
+    """dX of a 3x3 conv.  geom is the INPUT geometry (NB, H, W)."""
+    NB, H, W = geom
+    cout = mod.cout
+    if stride == 1:
+        wd = mod.pack_dgrad()
+        return raw.gemm(dy, wd, conv=dict(NB_in=NB, H=H, W=W, C=cout, taps=raw.TAPS_3X3), M=NB * H * W)
+    # stride 2: per input phase (p, q) a small conv over dy (grid H/2 x W/2); results are written
+    # phase-major and scattered back with depth_to_space.
+    Ho, Wo = H // 2, W // 2
+    Mo = NB * Ho * Wo
+    out = torch.empty((4 * Mo, mod.cin), device=dy.device, dtype=BF16)
+    packs = mod.pack_dgrad_s2()
+    for ph in range(4):
+        taps, wd = packs[ph]
+        raw.gemm(dy, wd, conv=dict(NB_in=NB, H=Ho, W=Wo, C=cout, taps=taps), M=Mo, out=out[ph * Mo:(ph + 1) * Mo])
+    return raw.depth_to_space(out, NB, H, W, mod.cin)
+
+
+def conv3x3(x, geom, mod, *, rowvec=None, residual=None, x2=None, stride=1, out_fp32=False):
+    """y = conv3x3(x) + bias (+ rowvec per image) (+ residual) (+ x2 @ W_shortcut^T).  `mod` is a ConvPack."""
+    if _grad_on(x, residual, x2):
+        return _ConvFn.apply(x, residual, x2, mod, geom, stride, rowvec, out_fp32)
+    p = mod.pack()
+    shortcut = (x2, mod.pack_shortcut()) if x2 is not None else None
+    return _conv_fwd_raw(x, geom, p["w"], p["b"], rowvec, residual, shortcut, stride, mod.cin, out_fp32)
+
+
+class ConvPack:
+    """Kernel-side view of a 3x3 nn.Conv2d (+ optional 1x1 shortcut conv accumulated as K-segment 2)."""
+
+    def __init__(self, conv, shortcut=None):
+        self.conv, self.shortcut = conv, shortcut
+        self.cout_true, self.cin_true = conv.weight.shape[0], conv.weight.shape[1]
+        self.cin = (self.cin_true + 7) // 8 * 8          # channel padding of the NHWC input (conv_in)
+        self.cout = (self.cout_true + 7) // 8 * 8        # and of the output (conv_out): zero rows
+        self.cache = cache_of(conv)
+
+    def _w(self):
+        w = self.conv.weight.detach()
+        if self.cin != self.cin_true or self.cout != self.cout_true:
+            w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, self.cin - self.cin_true, 0, self.cout - self.cout_true))
+        return w
+
+    def pack(self):
+        def build():
+            b = _f32(self.conv.bias)
+            if self.shortcut is not None and self.shortcut.bias is not None:
+                b = b + _f32(self.shortcut.bias)
+            if b is not None and self.cout != self.cout_true:
+                b = torch.nn.functional.pad(b, (0, self.cout - self.cout_true))
+            return {"w": pack_conv3x3(self._w()), "b": b}
+        params = [self.conv.weight, self.conv.bias] + ([self.shortcut.bias] if self.shortcut is not None else [])
+        return self.cache.get("fwd", params, build)
+
+    def pack_shortcut(self):
+        return self.cache.get("sc", [self.shortcut.weight], lambda: pack_matrix(self.shortcut.weight))
+
+    def pack_shortcut_t(self):
+        return self.cache.get("sc_t", [self.shortcut.weight],
+                              lambda: pack_matrix(self.shortcut.weight.detach().reshape(self.cout, -1).t()))
+
+    def pack_dgrad(self):
+        return self.cache.get("dgrad", [self.conv.weight], lambda: pack_conv3x3_dgrad(self._w()))
+
+    def pack_dgrad_s2(self):
+        """per input phase: (taps over dy, packed weights [Cin, ntaps*ceil64(Cout)])."""
+        def build():
+            w = self._w().detach().float()                     # [Cout, Cin, 3, 3]
+            cpad = (self.cout + 63) // 64 * 64
+            packs = []
+            for p in range(2):
+                for q in range(2):
+                    khs = [1] if p == 0 else [0, 2]            # input row 2a+p = 2*ho + kh - 1
+                    kws = [1] if q == 0 else [0, 2]
+                    taps, mats = [], []
+                    for kh in khs:
+                        for kw in kws:
+                            dh = (p + 1 - kh) // 2             # ho = a + dh
+                            dw = (q + 1 - kw) // 2
+                            taps.append((0, dh, dw))
+                            m = torch.zeros((self.cin, cpad), device=w.device)
+                            m[:, :self.cout] = w[:, :, kh, kw].t()
+                            mats.append(m)
+                    wd = torch.stack(mats, dim=1).reshape(self.cin, len(taps) * cpad)
+                    packs.append((taps, raw.cast_scale(wd.contiguous(), 1.0)))
+            return packs
+        return self.cache.get("dgrad_s2", [self.conv.weight], build)
+
+
+# ------------------------------------------------------------------------------------------------
+# GroupNorm (+SiLU) and LayerNorm
+# ------------------------------------------------------------------------------------------------
+class _GroupNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, geom, G, eps, silu):
+        NB, H, W = geom
+        C = x.shape[1]
+        stats = raw.groupnorm_stats(x, NB, H * W, C, G, eps)
+        y = raw.groupnorm_apply(x, stats, gamma, beta, NB, H * W, C, G, silu)
+        ctx.save_for_backward(x, stats, gamma, beta)
+        ctx.meta = (NB, H * W, C, G, silu)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, stats, gamma, beta = ctx.saved_tensors
+        NB, HW, C, G, silu = ctx.meta
+        dx = raw.groupnorm_bwd(x, stats, gamma, beta, dy.contiguous(), NB, HW, C, G, silu)
+        return dx, None, None, None, None, None, None
+
+
+def group_norm(x, geom, norm, silu):
+    """torch.nn.GroupNorm parameters `norm`; x [NB*H*W, C] bf16."""
+    cache = cache_of(norm)
+    gamma, beta = cache.get("gb", [norm.weight, norm.bias], lambda: (_f32(norm.weight), _f32(norm.bias)))
+    if _grad_on(x):
+        return _GroupNormFn.apply(x, gamma, beta, geom, norm.num_groups, norm.eps, silu)
+    NB, H, W = geom
+    C = x.shape[1]
+    stats = raw.groupnorm_stats(x, NB, H * W, C, norm.num_groups, norm.eps)
+    return raw.groupnorm_apply(x, stats, gamma, beta, NB, H * W, C, norm.num_groups, silu)
+
+
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        y, stats = raw.layernorm_fwd(x, gamma, beta, eps, save_stats=True)
+        ctx.save_for_backward(x, stats, gamma)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, stats, gamma = ctx.saved_tensors
+        return raw.layernorm_bwd(x, stats, gamma, dy.contiguous()), None, None, None
+
+
+def layer_norm(x, norm):
+    cache = cache_of(norm)
+    gamma, beta = cache.get("gb", [norm.weight, norm.bias], lambda: (_f32(norm.weight), _f32(norm.bias)))
+    if _grad_on(x):
+        return _LayerNormFn.apply(x, gamma, beta, norm.eps)
+    return raw.layernorm_fwd(x, gamma, beta, norm.eps)
+
+
+# ------------------------------------------------------------------------------------------------
+# Linear (+LoRA, +GEGLU, +residual)
+# ------------------------------------------------------------------------------------------------
+class LinearPack:
+    """Kernel-side view of one or several nn.Linear (or LoRA-wrapped Linear) sharing an input; several
+    are fused along N (self-attention q/k/v, cross-attention k/v)."""
+
+    def __init__(self, layers, geglu=False):
+        self.layers = layers if isinstance(layers, (list, tuple)) else [layers]
+        self.geglu = geglu
+        self.bases = [getattr(l, "base_layer", l) for l in self.layers]
+        self.loras = [l if hasattr(l, "base_layer") else None for l in self.layers]
+        self.has_lora = any(l is not None for l in self.loras)
+        self.cache = cache_of(self.bases[0])
+        self.N = sum(b.weight.shape[0] for b in self.bases)
+        self.K = self.bases[0].weight.shape[1]
+
+    def _w2d(self, b):
+        return b.weight.detach().reshape(b.weight.shape[0], -1)       # Linear or 1x1 Conv2d
+
+    def pack(self):
+        def build():
+            ws = [self._w2d(b).float() for b in self.bases]
+            bs = [b.bias for b in self.bases]
+            bias = None
+            if any(x is not None for x in bs):
+                bias = torch.cat([x.detach().float() if x is not None else
+                                  torch.zeros(w.shape[0], device=w.device) for x, w in zip(bs, ws)]).contiguous()
+            w = torch.cat(ws, dim=0)
+            if self.geglu:
+                wp, bp = pack_geglu(w, bias)
+                return {"w": wp, "b": bp}
+            return {"w": raw.cast_scale(w.contiguous(), 1.0), "b": bias}
+        params = [b.weight for b in self.bases] + [b.bias for b in self.bases if b.bias is not None]
+        return self.cache.get(("fwd", len(self.bases), self.geglu), params, build)
+
+    def pack_t(self):
+        """W^T [K, N] for the data gradient."""
+        def build():
+            w = torch.cat([self._w2d(b).float() for b in self.bases], dim=0)
+            if self.geglu:
+                w = pack_geglu(w, torch.zeros(w.shape[0], device=w.device))[0].float()
+            return raw.cast_scale(w.t().contiguous(), 1.0)
+        return self.cache.get(("t", len(self.bases), self.geglu), [b.weight for b in self.bases], build)
+
+    # LoRA: T = x [A_1;..;A_n]^T  (M x n*r);  y += T @ blockdiag(s B_i)^T
+    def lora_params(self):
+        ps = []
+        for l in self.loras:
+            if l is not None:
+                ps += [l.lora_A["default"].weight, l.lora_B["default"].weight]
+        return ps
+
+    def pack_lora(self):
+        def build():
+            r = next(l.r for l in self.loras if l is not None)
+            dev = self.bases[0].weight.device
+            n = len(self.layers)
+            a_cat = torch.zeros((n * r, self.K), device=dev)
+            b_blk = torch.zeros((self.N, n * r), device=dev)
+            row = 0
+            for i, (l, b) in enumerate(zip(self.loras, self.bases)):
+                nout = b.weight.shape[0]
+                if l is not None:
+                    a_cat[i * r:(i + 1) * r] = l.lora_A["default"].weight.detach().float()
+                    b_blk[row:row + nout, i * r:(i + 1) * r] = l.lora_B["default"].weight.detach().float() * l.scaling
+                row += nout
+            return {"a": raw.cast_scale(a_cat, 1.0), "b": raw.cast_scale(b_blk, 1.0),
+                    "a_t": raw.cast_scale(a_cat.t().contiguous(), 1.0),
+                    "b_t": raw.cast_scale(b_blk.t().contiguous(), 1.0), "r": r}
+        return self.cache.get("lora", self.lora_params(), build)
+
+
+def _linear_fwd_raw(x, pack: LinearPack, residual, out=None):
+    p = pack.pack()
+    a2 = b2 = None
+    t = None
+    if pack.has_lora:
+        lp = pack.pack_lora()
+        t = raw.gemm(x, lp["a"])
+        a2, b2 = t, lp["b"]
+    y = raw.gemm(x, p["w"], a2=a2, b2=b2, bias=p["b"], geglu=pack.geglu, residual=residual, out=out)
+    return y, t
+
+
+class _LinearFn(torch.autograd.Function):
+    """y = x W^T + b (+ LoRA) (+ residual); GEGLU handled by _GegluFn."""
+
+    @staticmethod
+    def forward(ctx, x, residual, pack, *lora_params):
+        y, t = _linear_fwd_raw(x, pack, residual)
+        ctx.pack = pack
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(x, t)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        pack = ctx.pack
+        x, t = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dres = None
+        grads = [None] * len(pack.lora_params())
+        if pack.has_lora:
+            lp = pack.pack_lora()
+            dt = raw.gemm(dy, lp["b_t"])                                  # [M, n*r] = dy @ (sB)
+            if ctx.needs_input_grad[0]:
+                dx = raw.gemm(dy, pack.pack_t(), a2=dt, b2=lp["a_t"])     # dy W + dt A
+            grads = _lora_weight_grads(pack, lp, x, t, dy, dt)
+        elif ctx.needs_input_grad[0]:
+            dx = raw.gemm(dy, pack.pack_t())
+        if ctx.has_res and ctx.needs_input_grad[1]:
+            dres = dy
+        return (dx, dres, None, *grads)
+
+
+def _lora_weight_grads(pack, lp, x, t, dy, dt):
+    """dA_i = dt_i^T x ; dB_i = s * dy_i^T t_i   (fp32, in the parameters' layout)."""
+    r = lp["r"]
+    x_t = raw.transpose(x)                      # [K, M]
+    dy_t = raw.transpose(dy)                    # [N, M]
+    t_t = raw.transpose(t)                      # [n*r, M]
+    dt_t = raw.transpose(dt)                    # [n*r, M]
+    d_a = raw.gemm(dt_t, x_t, out_fp32=True)    # [n*r, K]
+    d_b = raw.gemm(dy_t, t_t, out_fp32=True)    # [N, n*r]  (block-diagonal part is what we keep)
+    grads = []
+    row = 0
+    for i, (l, b) in enumerate(zip(pack.loras, pack.bases)):
+        nout = b.weight.shape[0]
+        if l is not None:
+            grads.append(d_a[i * r:(i + 1) * r])
+            grads.append(d_b[row:row + nout, i * r:(i + 1) * r] * l.scaling)
+        row += nout
+    return grads
+
+
+def linear(x, pack: LinearPack, residual=None):
+    lora_params = pack.lora_params() if pack.has_lora else []
+    if _grad_on(x, residual, *lora_params):
+        return _LinearFn.apply(x, residual, pack, *lora_params)
+    return _linear_fwd_raw(x, pack, residual)[0]
+
+
+class _GegluFn(torch.autograd.Function):
+    """out = value * gelu(gate) with [value|gate] = x W^T + b; backward recomputes the pre-activation."""
+
+    @staticmethod
+    def forward(ctx, x, pack):
+        p = pack.pack()
+        ctx.pack = pack
+        ctx.save_for_backward(x)
+        return raw.gemm(x, p["w"], bias=p["b"], geglu=True)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (x,) = ctx.saved_tensors
+        p = ctx.pack.pack()
+        acc = raw.gemm(x, p["w"], bias=p["b"])                 # recompute (interleaved layout)
+        dacc = raw.geglu_bwd(acc, dout.contiguous())
+        return raw.gemm(dacc, ctx.pack.pack_t()), None
+
+
+def geglu(x, pack: LinearPack):
+    if _grad_on(x):
+        return _GegluFn.apply(x, pack)
+    p = pack.pack()
+    return raw.gemm(x, p["w"], bias=p["b"], geglu=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+class _AttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, H):
+        o, lse = raw.attention_fwd(q, k, v, H, need_lse=True)
+        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.H = H
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, o, lse = ctx.saved_tensors
+        dq, dk, dv = raw.attention_bwd(q, k, v, o, lse, do.contiguous(), ctx.H)
+        return dq, dk, dv, None
+
+
+def attention(q, k, v, H):
+    """q [B,Nq,H*64], k/v [B,Nkv,H*64] (last-dim stride 1 views allowed) -> [B,Nq,H*64]."""
+    if _grad_on(q, k, v):
+        return _AttnFn.apply(q, k, v, H)
+    return raw.attention_fwd(q, k, v, H)
+
+
+# ------------------------------------------------------------------------------------------------
+# layout ops
+# ------------------------------------------------------------------------------------------------
+class _ConcatFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.c1, ctx.c2 = a.shape[1], b.shape[1]
+        return raw.concat_channels(a, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        return raw.slice_channels(dy, 0, ctx.c1), raw.slice_channels(dy, ctx.c1, ctx.c2)
+
+
+def concat(a, b):
+    if _grad_on(a, b):
+        return _ConcatFn.apply(a, b)
+    return raw.concat_channels(a, b)
+
+
+class _UpsampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, geom):
+        ctx.geom = geom
+        NB, H, W = geom
+        return raw.upsample2x(x, NB, H, W, x.shape[1])
+
+    @staticmethod
+    def backward(ctx, dy):
+        NB, H, W = ctx.geom
+        return raw.upsample2x_bwd(dy.contiguous(), NB, H, W, dy.shape[1]), None
+
+
+def upsample2x(x, geom):
+    if _grad_on(x):
+        return _UpsampleFn.apply(x, geom)
+    NB, H, W = geom
+    return raw.upsample2x(x, NB, H, W, x.shape[1])
+
+
+class _ToNHWCFn(torch.autograd.Function):
+    """NCHW fp32 -> NHWC bf16 (channel-padded); backward returns NCHW fp32."""
+
+    @staticmethod
+    def forward(ctx, x, cpad):
+        ctx.shape = x.shape
+        NB, C, H, W = x.shape
+        return raw.nchw_to_nhwc(x, cpad).view(NB * H * W, cpad)
+
+    @staticmethod
+    def backward(ctx, dy):
+        NB, C, H, W = ctx.shape
+        return raw.nhwc_to_nchw(dy.contiguous(), NB, C, H, W), None
+
+
+def to_nhwc(x, cpad):
+    if _grad_on(x):
+        return _ToNHWCFn.apply(x.float(), cpad)
+    NB, C, H, W = x.shape
+    return raw.nchw_to_nhwc(x.float(), cpad).view(NB * H * W, cpad)
+
+
+class _ToNCHWFn(torch.autograd.Function):
+    """NHWC rows [M, ld] (fp32 or bf16, first C valid) -> NCHW fp32."""
+
+    @staticmethod
+    def forward(ctx, x, geom, C):
+        NB, H, W = geom
+        ctx.meta = (geom, C, x.shape[1], x.dtype)
+        return raw.nhwc_to_nchw(x, NB, C, H, W)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (NB, H, W), C, ld, dtype = ctx.meta
+        g = raw.nchw_to_nhwc(dy.contiguous().float(), ld).view(NB * H * W, ld)
+        if dtype == torch.float32:
+            g = g.float()
+        return g, None, None
+
+
+def to_nchw(x, geom, C):
+    if _grad_on(x):
+        return _ToNCHWFn.apply(x, geom, C)
+    NB, H, W = geom
+    return raw.nhwc_to_nchw(x, NB, C, H, W)

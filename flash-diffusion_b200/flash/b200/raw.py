@@ -66,8 +66,8 @@ def gemm(a1, b1, *, a2=None, b2=None, bias=None, rowvec=None, rows_per_group=0, 
         assert bias.numel() == N and bias.is_contiguous()
         args.bias = ptr(bias)
     if rowvec is not None:
-        assert rowvec.is_contiguous() and rowvec.shape[-1] == N
-        args.rowvec, args.rows_per_group = ptr(rowvec), rows_per_group
+        assert rowvec.dim() == 2 and rowvec.stride(1) == 1 and rowvec.shape[1] == N
+        args.rowvec, args.rows_per_group, args.ldrv = ptr(rowvec), rows_per_group, rowvec.stride(0)
     args.geglu = 1 if geglu else 0
     if residual is not None:
         assert residual.shape == (M, n_out) and residual.stride(1) == 1
@@ -208,6 +208,16 @@ def concat_channels(a, b):
     y = torch.empty((rows, a.shape[1] + b.shape[1]), device=a.device, dtype=BF16)
     check(lib.fd_concat_channels(ptr(a), c_int32(a.shape[1]), ptr(b), c_int32(b.shape[1]), ptr(y), c_int64(rows),
                                  stream_ptr()), "fd_concat_channels")
+    return y
+
+
+def slice_channels(x, c0, C):
+    lib = load(); _req(x, BF16, "x")
+    rows, Ctot = x.shape
+    assert x.is_contiguous()
+    y = torch.empty((rows, C), device=x.device, dtype=BF16)
+    check(lib.fd_slice_channels(ptr(x), c_int32(Ctot), c_int32(c0), c_int32(C), ptr(y), c_int64(rows), stream_ptr()),
+          "fd_slice_channels")
     return y
 
 

@@ -1,0 +1,279 @@
+"""Noise schedulers consumed by FlashDiffusion (protocol: SURVEY.md Appendix A "Scheduler protocol").
+
+The reference takes these from diffusers (`DDPMScheduler`, `DPMSolverMultistepScheduler`, `LCMScheduler`;
+reference call sites src/flash/models/flash/flash_diffusion_model.py:139,172,245-257,289-324,781-863 and
+examples/train_flash_sdxl.py:221-236).  diffusers is not installable here, so the scheduler math is
+restated from its published algorithms; all of it is scalar host arithmetic
+plus one elementwise update per step — on CUDA that update runs in the fused kernel
+`fd_step_cfg_dpm` (CFG combine + DPM-Solver++ step), see `DPMSolverMultistepScheduler.fused_cfg_step`.
+
+Decision (1) of SURVEY.md §8c: `add_noise` is the closed form sqrt(abar_t) x + sqrt(1-abar_t) eps for any
+integer timestep (off-schedule DMD / GAN timesteps included).
+"""
+import math
+from types import SimpleNamespace
+from typing import List, Optional, Union
+
+import numpy as np
+import torch
+
+
+def _betas(schedule: str, beta_start: float, beta_end: float, n: int) -> torch.Tensor:
+    if schedule == "linear":
+        return torch.linspace(beta_start, beta_end, n, dtype=torch.float32)
+    if schedule == "scaled_linear":
+        return torch.linspace(beta_start ** 0.5, beta_end ** 0.5, n, dtype=torch.float32) ** 2
+    raise NotImplementedError(schedule)
+
+
+def _spaced_timesteps(num_train: int, num_inference: int, spacing: str, steps_offset: int = 0) -> np.ndarray:
+    if spacing == "trailing":
+        return np.round(np.arange(num_train, 0, -num_train / num_inference)).astype(np.int64) - 1
+    if spacing == "leading":
+        ratio = num_train // num_inference
+        return (np.arange(0, num_inference) * ratio).round()[::-1].copy().astype(np.int64) + steps_offset
+    if spacing == "linspace":
+        return np.linspace(0, num_train - 1, num_inference).round()[::-1].copy().astype(np.int64)
+    raise NotImplementedError(spacing)
+
+
+# repo -> scheduler config used by `from_pretrained` (there is no network; these are the published
+# scheduler_config.json values of the checkpoints the reference examples name)
+_KNOWN_CONFIGS = {
+    "default_sd": dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                       steps_offset=1),
+}
+
+
+class _SchedulerBase:
+    order = 1
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
+                 timestep_spacing="leading", steps_offset=0, prediction_type="epsilon", **extra):
+        self.config = SimpleNamespace(num_train_timesteps=num_train_timesteps, beta_start=beta_start,
+                                      beta_end=beta_end, beta_schedule=beta_schedule,
+                                      timestep_spacing=timestep_spacing, steps_offset=steps_offset,
+                                      prediction_type=prediction_type, **extra)
+        self.betas = _betas(beta_schedule, beta_start, beta_end, num_train_timesteps)
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.init_noise_sigma = 1.0
+        self.num_inference_steps = None
+        self.timesteps = torch.arange(num_train_timesteps - 1, -1, -1, dtype=torch.int64)
+
+    @classmethod
+    def from_pretrained(cls, repo: str = None, subfolder: str = None, revision: str = None, **overrides):
+        cfg = dict(_KNOWN_CONFIGS["default_sd"])
+        cfg.update(overrides)
+        return cls(**cfg)
+
+    @classmethod
+    def from_config(cls, config, **overrides):
+        cfg = dict(vars(config)) if not isinstance(config, dict) else dict(config)
+        cfg.update(overrides)
+        return cls(**cfg)
+
+    def scale_model_input(self, sample, timestep=None):
+        return sample
+
+    def add_noise(self, original_samples, noise, timesteps):
+        ac = self.alphas_cumprod.to(device=original_samples.device, dtype=original_samples.dtype)
+        t = timesteps.to(original_samples.device).long()
+        shape = (-1,) + (1,) * (original_samples.dim() - 1)
+        return ac[t].sqrt().view(shape) * original_samples + (1 - ac[t]).sqrt().view(shape) * noise
+
+    def _default_set_timesteps(self, num_inference_steps):
+        self.num_inference_steps = num_inference_steps
+        ts = _spaced_timesteps(self.config.num_train_timesteps, num_inference_steps,
+                               self.config.timestep_spacing, self.config.steps_offset)
+        self.timesteps = torch.from_numpy(ts)
+
+
+class DDPMScheduler(_SchedulerBase):
+    """Ancestral DDPM sampler (epsilon prediction, fixed_small variance, clip_sample as in diffusers'
+    defaults).  The reference's own test builds every scheduler as `DDPMScheduler()`
+    (tests/test_flash/test_flash_diffusion.py:87-93)."""
+
+    def __init__(self, clip_sample=True, clip_sample_range=1.0, variance_type="fixed_small", **kw):
+        super().__init__(clip_sample=clip_sample, clip_sample_range=clip_sample_range,
+                         variance_type=variance_type, **kw)
+
+    def set_timesteps(self, num_inference_steps=None, device=None, timesteps=None):
+        if timesteps is not None:
+            self.timesteps = torch.as_tensor(np.array(timesteps, dtype=np.int64))
+            self.num_inference_steps = len(self.timesteps)
+            return
+        self._default_set_timesteps(num_inference_steps)
+
+    def _prev_timestep(self, t):
+        n = self.num_inference_steps or self.config.num_train_timesteps
+        return t - self.config.num_train_timesteps // n
+
+    def step(self, model_output, timestep, sample, generator=None, return_dict=False):
+        t = int(timestep)
+        prev_t = self._prev_timestep(t)
+        ac_t = float(self.alphas_cumprod[t])
+        ac_prev = float(self.alphas_cumprod[prev_t]) if prev_t >= 0 else 1.0
+        beta_prod_t, beta_prod_prev = 1 - ac_t, 1 - ac_prev
+        cur_alpha = ac_t / ac_prev
+        cur_beta = 1 - cur_alpha
+        x0 = (sample - beta_prod_t ** 0.5 * model_output) / ac_t ** 0.5
+        if self.config.clip_sample:
+            x0 = x0.clamp(-self.config.clip_sample_range, self.config.clip_sample_range)
+        c0 = (ac_prev ** 0.5 * cur_beta) / beta_prod_t
+        ct = cur_alpha ** 0.5 * beta_prod_prev / beta_prod_t
+        prev = c0 * x0 + ct * sample
+        if t > 0:
+            var = max(beta_prod_prev / beta_prod_t * cur_beta, 1e-20)
+            prev = prev + var ** 0.5 * torch.randn(sample.shape, generator=generator, device=sample.device,
+                                                   dtype=sample.dtype)
+        return (prev,)
+
+
+class DPMSolverMultistepScheduler(_SchedulerBase):
+    """DPM-Solver++ (2M, midpoint), epsilon prediction, `final_sigmas_type="zero"`, `lower_order_final`
+    (SURVEY.md Appendix B.2).  `set_timesteps` resets the multistep history, so a rollout entered at
+    `timesteps[start_idx:]` starts first-order, exactly as in the reference loop
+    (flash_diffusion_model.py:139,288-324)."""
+
+    order = 1
+
+    def __init__(self, solver_order=2, timestep_spacing="leading", **kw):
+        kw.pop("algorithm_type", None)
+        super().__init__(timestep_spacing=timestep_spacing, solver_order=solver_order, **kw)
+        self.model_outputs = [None] * solver_order
+        self.lower_order_nums = 0
+        self._step_index = None
+        self.set_timesteps(self.config.num_train_timesteps)
+
+    def set_timesteps(self, num_inference_steps=None, device=None, timesteps=None):
+        if timesteps is not None:
+            ts = np.array(timesteps, dtype=np.int64)
+            self.num_inference_steps = len(ts)
+        else:
+            ts = _spaced_timesteps(self.config.num_train_timesteps, num_inference_steps,
+                                   self.config.timestep_spacing, self.config.steps_offset)
+            ts = np.clip(ts, 0, self.config.num_train_timesteps - 1)
+            self.num_inference_steps = num_inference_steps
+        ac = self.alphas_cumprod.double().numpy()
+        sig = np.sqrt((1 - ac) / ac)[ts]
+        self.sigmas = torch.from_numpy(np.concatenate([sig, [0.0]]))          # final sigma = 0 (float64)
+        self.timesteps = torch.from_numpy(ts)
+        self.model_outputs = [None] * self.config.solver_order
+        self.lower_order_nums = 0
+        self._step_index = None
+
+    @staticmethod
+    def _alpha_sigma(sigma: float):
+        alpha_t = 1.0 / math.sqrt(sigma * sigma + 1.0)
+        return alpha_t, sigma * alpha_t
+
+    def _index_for(self, timestep) -> int:
+        t = int(timestep)
+        idx = (self.timesteps == t).nonzero()
+        if len(idx) == 0:
+            return len(self.timesteps) - 1
+        return int(idx[1] if len(idx) > 1 else idx[0])
+
+    def step_coefficients(self, timestep):
+        """Host scalars of one update at `timestep`:
+           x0 = (x - sigma_t eps) / alpha_t ;  x_next = c_x x - c_d0 x0 - c_d1r (x0 - x0_prev).
+        Returns (alpha_t, sigma_t, c_x, c_d0, c_d1r) and advances the multistep state."""
+        if self._step_index is None:
+            self._step_index = self._index_for(timestep)
+        i = self._step_index
+        n = len(self.timesteps)
+        sig_s0, sig_t = float(self.sigmas[i]), float(self.sigmas[i + 1])
+        a_s0, s_s0 = self._alpha_sigma(sig_s0)
+        a_t, s_t = self._alpha_sigma(sig_t)
+        lam_s0 = math.log(a_s0) - math.log(s_s0)
+        lower_final = (i == n - 1)
+        lower_second = (i == n - 2) and n < 15
+        first_order = self.config.solver_order == 1 or self.lower_order_nums < 1 or lower_final
+        if s_t == 0.0:
+            expm1_negh, ratio = -1.0, 0.0          # h = +inf
+            h = math.inf
+        else:
+            lam_t = math.log(a_t) - math.log(s_t)
+            h = lam_t - lam_s0
+            expm1_negh, ratio = math.expm1(-h), s_t / s_s0
+        c_x = ratio
+        c_d0 = a_t * expm1_negh
+        c_d1r = 0.0
+        if not first_order and not lower_second:
+            sig_s1 = float(self.sigmas[i - 1])
+            a_s1, s_s1 = self._alpha_sigma(sig_s1)
+            lam_s1 = math.log(a_s1) - math.log(s_s1)
+            r0 = (lam_s0 - lam_s1) / h
+            c_d1r = 0.5 * a_t * expm1_negh / r0
+        if self.lower_order_nums < self.config.solver_order:
+            self.lower_order_nums += 1
+        self._step_index += 1
+        return a_s0, s_s0, c_x, c_d0, c_d1r
+
+    def step(self, model_output, timestep, sample, return_dict=False, **kw):
+        a_s0, s_s0, c_x, c_d0, c_d1r = self.step_coefficients(timestep)
+        x0 = (sample - s_s0 * model_output) / a_s0
+        prev = c_x * sample - c_d0 * x0
+        if c_d1r != 0.0:
+            prev = prev - c_d1r * (x0 - self.model_outputs[-1])
+        self.model_outputs = [self.model_outputs[-1], x0]
+        return (prev,)
+
+    def fused_cfg_step(self, eps_c, eps_u, guidance_scale: float, timestep, sample, x0_prev):
+        """CUDA path: eps = w eps_c + (1-w) eps_u, then the DPM-Solver++ update, in ONE kernel
+        (fd_step_cfg_dpm), in place on `sample` (fp32) and `x0_prev`.  No CPU fallback."""
+        from .b200 import raw
+        a_s0, s_s0, c_x, c_d0, c_d1r = self.step_coefficients(timestep)
+        raw.step_cfg_dpm(eps_c, eps_u, sample, x0_prev, (guidance_scale, a_s0, s_s0, c_x, c_d0, c_d1r))
+        return sample
+
+
+class LCMScheduler(_SchedulerBase):
+    """Latent-consistency sampler: boundary-condition mix with sigma_data 0.5 and
+    timestep_scaling 10, re-noising to the next timestep except on the last step."""
+
+    def __init__(self, original_inference_steps=50, timestep_scaling=10.0, sigma_data=0.5, **kw):
+        super().__init__(original_inference_steps=original_inference_steps, timestep_scaling=timestep_scaling,
+                         sigma_data=sigma_data, **kw)
+        self._step_index = None
+
+    def set_timesteps(self, num_inference_steps=None, device=None, original_inference_steps=None,
+                      timesteps=None, strength=1.0):
+        if timesteps is not None:
+            ts = np.array(timesteps, dtype=np.int64)
+        else:
+            orig = original_inference_steps or self.config.original_inference_steps
+            k = self.config.num_train_timesteps // orig
+            lcm_origin = np.asarray(list(range(1, int(orig * strength) + 1))) * k - 1
+            lcm_origin = lcm_origin[::-1].copy()
+            idx = np.floor(np.linspace(0, len(lcm_origin), num=num_inference_steps, endpoint=False)).astype(np.int64)
+            ts = lcm_origin[idx]
+        self.num_inference_steps = len(ts)
+        self.timesteps = torch.from_numpy(ts.astype(np.int64))
+        self._step_index = None
+
+    def scalings(self, timestep):
+        s = float(timestep) * self.config.timestep_scaling
+        sd = self.config.sigma_data
+        return sd ** 2 / (s ** 2 + sd ** 2), s / (s ** 2 + sd ** 2) ** 0.5
+
+    def step(self, model_output, timestep, sample, generator=None, return_dict=False):
+        if self._step_index is None:
+            self._step_index = int((self.timesteps == int(timestep)).nonzero()[0])
+        i = self._step_index
+        t = int(timestep)
+        last = i == len(self.timesteps) - 1
+        prev_t = int(self.timesteps[i + 1]) if not last else t
+        ac_t = float(self.alphas_cumprod[t])
+        ac_prev = float(self.alphas_cumprod[prev_t]) if prev_t >= 0 else 1.0
+        c_skip, c_out = self.scalings(t)
+        x0 = (sample - (1 - ac_t) ** 0.5 * model_output) / ac_t ** 0.5
+        denoised = c_out * x0 + c_skip * sample
+        if not last:
+            noise = torch.randn(sample.shape, generator=generator, device=sample.device, dtype=sample.dtype)
+            prev = ac_prev ** 0.5 * denoised + (1 - ac_prev) ** 0.5 * noise
+        else:
+            prev = denoised
+        self._step_index += 1
+        return (prev, denoised)

@@ -36,7 +36,7 @@ int fd_sm_arch(void);
  *
  *   acc[M,N] = A1[M,K1] * B1[N,K1]^T  (+ A2[M,K2] * B2[N,K2]^T)          (bf16 in, fp32 acc)
  *   acc += bias[N]                      (fp32, optional)
- *   acc += rowvec[row / rows_per_group, N]   (fp32, optional; the ResnetBlock time-embedding add)
+ *   acc += rowvec[row / rows_per_group, :N] (fp32, row stride ldrv; the ResnetBlock time-embedding add)
  *   geglu: out[:, 16j+i] = acc[:, 32j+i] * gelu(acc[:, 32j+16+i])   (weights packed interleaved)
  *   out (+)= residual[M, Nout]          (bf16, optional)
  *   out -> bf16 (or fp32 when out_fp32)
@@ -64,7 +64,7 @@ typedef struct {
     int32_t tap_dn[FD_MAX_TAPS], tap_dh[FD_MAX_TAPS], tap_dw[FD_MAX_TAPS];
     /* epilogue */
     const float* bias;
-    const float* rowvec; int32_t rows_per_group;
+    const float* rowvec; int32_t rows_per_group; int64_t ldrv;   /* row stride of rowvec (elements) */
     int32_t geglu;
     const void* residual; int64_t ldr;
     void* out; int64_t ldo; int32_t out_fp32;
@@ -150,6 +150,9 @@ int fd_depth_to_space(const void* x, void* y, int32_t NB, int32_t H, int32_t W, 
 /* copy rows [rows, C1] and [rows, C2] side by side into [rows, C1+C2] (skip-connection concat) */
 int fd_concat_channels(const void* a, int32_t C1, const void* b, int32_t C2, void* y, int64_t rows,
                        void* stream);
+/* y[rows, C] = x[rows, c0:c0+C] of a [rows, Ctot] matrix (skip-connection concat backward) */
+int fd_slice_channels(const void* x, int32_t Ctot, int32_t c0, int32_t C, void* y, int64_t rows,
+                      void* stream);
 /* y = a + b (bf16, n elements) */
 int fd_add(const void* a, const void* b, void* y, int64_t n, void* stream);
 /* bf16 [rows, cols] -> bf16 [cols, rows] */
