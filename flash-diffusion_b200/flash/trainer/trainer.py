@@ -1,0 +1,173 @@
+"""Step driver — mirrors reference `TrainingPipeline` (src/flash/trainer/trainer.py:16-251) without Lightning.
+
+Semantics kept from the reference:
+  * `configure_optimizers` (:76-139): optimizer i owns the parameters whose NAME regex-matches
+    `trainable_params[i]` and that require grad; everything matched by no regex is frozen;
+  * `training_step` (:169-218): with N>1 optimizers, for each optimizer i: a FULL `model(batch, step=i)`
+    forward, `zero_grad`, backward of `loss[i]`, `opt.step()`.
+What Lightning's DDP strategy did implicitly (`strategy="ddp_find_unused_parameters_true"`,
+examples/train_flash_sdxl.py:427) is explicit here: the gradients of optimizer i's parameters live in ONE
+flat fp32 bucket that is all-reduced (mean) across ranks with a single `torch.distributed.all_reduce`
+(NCCL over NVLink on B200; gloo in CPU tests) between backward and `opt.step()`.
+"""
+import importlib
+import logging
+import re
+import time
+from typing import Any, Dict, List
+
+import torch
+import torch.distributed as dist
+
+from .training_config import TrainingConfig
+
+
+class _FlatGradBucket:
+    """All gradients of one optimizer as views into one contiguous fp32 buffer (single all-reduce)."""
+
+    def __init__(self, params: List[torch.nn.Parameter]):
+        self.params = params
+        self.flat = None
+
+    def attach(self):
+        if not self.params:
+            return
+        dev = self.params[0].device
+        if self.flat is None or self.flat.device != dev:
+            n = sum(p.numel() for p in self.params)
+            self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
+        else:
+            self.flat.zero_()
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def all_reduce_mean(self):
+        if self.flat is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
+            self.flat.div_(dist.get_world_size())
+
+
+class TrainingPipeline(torch.nn.Module):
+    def __init__(self, model, pipeline_config: TrainingConfig, verbose: bool = False, **kwargs):
+        super().__init__()
+        self.model = model
+        self.pipeline_config = pipeline_config
+        self.log_samples_model_kwargs = pipeline_config.log_samples_model_kwargs
+        self.verbose = verbose
+        log_keys = pipeline_config.log_keys
+        self.log_keys = [log_keys] if isinstance(log_keys, str) else (log_keys or [])
+        self.automatic_optimization = True
+        self.optims = None
+        self._buckets = None
+        self.global_rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        self.timer = None
+
+    @property
+    def device(self):
+        return next(self.model.parameters()).device
+
+    # ---- reference :76-139
+    def configure_optimizers(self):
+        cfg = self.pipeline_config
+        optimizers, buckets = [], []
+        named = list(self.model.named_parameters())
+        for i, opt_name in enumerate(cfg.optimizers_name):
+            patterns = [re.compile(rx) for rx in cfg.trainable_params[i]]
+            params = []
+            for name, p in named:
+                for pat in patterns:          # a parameter matched by two regexes is listed twice, as upstream
+                    if re.match(pat, name) and p.requires_grad:
+                        params.append(p)
+            uniq, seen = [], set()
+            for p in params:
+                if id(p) not in seen:
+                    seen.add(id(p))
+                    uniq.append(p)
+            logging.info(f"Number of trainable parameters for optimizer {i}: {sum(p.numel() for p in uniq)}")
+            opt_cls = getattr(importlib.import_module("torch.optim"), opt_name)
+            optimizers.append(opt_cls([{"params": uniq}], lr=cfg.learning_rates[i], **cfg.optimizers_kwargs[i]))
+            buckets.append(_FlatGradBucket(uniq))
+        if len(optimizers) > 1:
+            self.automatic_optimization = False
+        all_patterns = [re.compile(rx) for rxs in cfg.trainable_params for rx in rxs]
+        for name, p in named:
+            if not any(re.match(pat, name) for pat in all_patterns if p.requires_grad):
+                p.requires_grad = False
+        logging.info(f"Number of trainable parameters: {sum(p.numel() for p in self.model.parameters() if p.requires_grad)}")
+        self.optims, self._buckets = optimizers, buckets
+        self.lr_schedulers = self.configure_lr_schedulers()
+        return optimizers
+
+    def configure_lr_schedulers(self):
+        cfg = self.pipeline_config
+        out = []
+        for i, name in enumerate(cfg.lr_schedulers_name):
+            if name is None:
+                out.append(None)
+                continue
+            cls = getattr(importlib.import_module("torch.optim.lr_scheduler"), name)
+            out.append({"scheduler": cls(self.optims[i], **cfg.lr_schedulers_kwargs[i]),
+                        "interval": cfg.lr_schedulers_interval[i], "monitor": "val_loss",
+                        "frequency": cfg.lr_schedulers_frequency[i]})
+        return None if all(s is None for s in out) else out
+
+    def optimizers(self):
+        if self.optims is None:
+            self.configure_optimizers()
+        return self.optims
+
+    # ---- reference :169-218
+    def training_step(self, train_batch: Dict[str, Any], batch_idx: int = 0, draws=None) -> dict:
+        optimizers = self.optimizers()
+        outputs = {"batch_idx": batch_idx}
+        if self.automatic_optimization:
+            out = self.model(train_batch, device=self.device)
+            loss = out["loss"]
+            loss = loss[0] if isinstance(loss, (list, tuple)) else loss
+            self._buckets[0].attach()
+            loss.backward()
+            self._buckets[0].all_reduce_mean()
+            optimizers[0].step()
+            return {"loss": loss.detach(), "batch_idx": batch_idx, "start_timestep": out.get("start_timestep")}
+        for i, opt in enumerate(optimizers):
+            kw = {} if draws is None else {"draws": draws[i] if isinstance(draws, (list, tuple)) else draws}
+            model_output = self.model(train_batch, device=self.device, step=i, batch_idx=batch_idx, **kw)
+            loss = model_output["loss"]
+            if "start_timestep" in model_output:
+                outputs["start_timestep"] = model_output["start_timestep"]
+            li = loss[i]
+            outputs[f"loss_optimizer_{i}"] = li.detach() if torch.is_tensor(li) else li
+            self._buckets[i].attach()                     # == opt.zero_grad(), grads land in the flat bucket
+            if torch.is_tensor(li) and li.requires_grad:
+                # toggle_optimizer semantics: only optimizer i's parameters accumulate gradients
+                others = [p for j, b in enumerate(self._buckets) if j != i for p in b.params]
+                flags = [p.requires_grad for p in others]
+                for p in others:
+                    p.requires_grad_(False)
+                try:
+                    li.backward()
+                finally:
+                    for p, f in zip(others, flags):
+                        p.requires_grad_(f)
+            self._buckets[i].all_reduce_mean()
+            opt.step()
+        return outputs
+
+    def on_train_start(self):
+        if self.global_rank == 0:
+            self.timer = time.perf_counter()
+
+    def validation_step(self, val_batch, val_idx=0):
+        loss = self.model(val_batch, device=self.device)["loss"]
+        return {"loss": loss, "metrics": self.model.compute_metrics(val_batch)}
+
+    def log_samples(self, batch):
+        logs = self.model.log_samples(batch, device=self.device, **self.log_samples_model_kwargs)
+        N = min(logs[k].shape[0] for k in logs) if logs is not None else 0
+        for key in self.log_keys:
+            if key in batch:
+                logs = logs if logs is not None else {}
+                logs[key] = batch[key][:N] if N > 0 else batch[key]
+        return logs

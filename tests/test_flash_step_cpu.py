@@ -1,0 +1,193 @@
+"""CPU tests of the host logic: FlashDiffusion / TrainingPipeline / schedulers / conditioners.
+
+The denoisers plugged in here are the fp32 ORACLE UNets (tests may use oracle/): the product denoiser is
+CUDA-only by design.  Properties reproduced from the reference's own tests
+(tests/test_flash/test_flash_diffusion.py:146-222): loss sign pattern per `step`, who-gets-updated invariants.
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from flash.models.embedders import (ConditionerWrapper, TimestepsEmbedder, TimestepsEmbedderConfig,
+                                    TorchNNEmbedder, TorchNNEmbedderConfig)
+from flash.models.flash import FlashDiffusion, FlashDiffusionConfig
+from flash.schedulers import DDPMScheduler, DPMSolverMultistepScheduler, LCMScheduler
+from flash.trainer import TrainingConfig, TrainingPipeline
+from oracle import flash_step as OF
+from oracle import schedulers as OS
+from oracle.unet import LoraConfig, UNet2DConditionOracle
+
+TINY = dict(in_channels=4, out_channels=4, down_block_types=["DownBlock2D", "CrossAttnDownBlock2D"],
+            up_block_types=["CrossAttnUpBlock2D", "UpBlock2D"], block_out_channels=[32, 64], layers_per_block=1,
+            cross_attention_dim=32, transformer_layers_per_block=1, attention_head_dim=[1, 2], norm_num_groups=8,
+            use_linear_projection=True, class_embed_type="projection", projection_class_embeddings_input_dim=16 + 3 * 8)
+
+
+def _conditioner():
+    ident = dict(nn_modules=["torch.nn.Identity"], nn_modules_kwargs=[{}])
+    return ConditionerWrapper([
+        TorchNNEmbedder(TorchNNEmbedderConfig(input_key="text_emb", **ident)),
+        TorchNNEmbedder(TorchNNEmbedderConfig(input_key="pooled_emb", **ident)),
+        TimestepsEmbedder(TimestepsEmbedderConfig(input_key="original_size_as_tuple", num_channels=4)),
+        TimestepsEmbedder(TimestepsEmbedderConfig(input_key="crop_coords_top_left", num_channels=4)),
+        TimestepsEmbedder(TimestepsEmbedderConfig(input_key="target_size_as_tuple", num_channels=4, input_dim=7)),
+    ])
+
+
+def _batch(B=2, hw=16, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return {"image": torch.randn(B, 4, hw, hw, generator=g), "text_emb": torch.randn(B, 5, 32, generator=g),
+            "pooled_emb": torch.randn(B, 16, generator=g),
+            "original_size_as_tuple": torch.tensor([[1024., 1024.]] * B), "crop_coords_top_left": torch.zeros(B, 2),
+            "target_size_as_tuple": torch.tensor([[1024., 1024.]] * B)}
+
+
+def _model(gan="lsgan", K=4, dmd=True, seed=0):
+    torch.manual_seed(seed)
+    teacher = UNet2DConditionOracle(**TINY)
+    student = copy.deepcopy(teacher)
+    student.add_adapter(LoraConfig(r=8, lora_alpha=8, init_lora_weights="gaussian",
+                                   target_modules=["to_k", "to_q", "to_v", "to_out.0"]))
+    for n, p in student.named_parameters():
+        if "lora_B" in n:
+            nn.init.normal_(p, std=0.05)
+    teacher.freeze()
+    disc = nn.Sequential(nn.Conv2d(64, 16, 4, 2, 1, bias=False), nn.SiLU(True), nn.Conv2d(16, 1, 4, 1, 0, bias=False),
+                         nn.Flatten())
+    cfg = FlashDiffusionConfig(K=[K], num_iterations_per_K=[100], guidance_scale_min=3.0, guidance_scale_max=7.0,
+                               distill_loss_type="l2", ucg_keys=["text_emb", "pooled_emb"], use_dmd_loss=dmd,
+                               gan_loss_type=gan, timestep_distribution="mixture", mixture_num_components=2,
+                               mixture_var=0.5, switch_teacher=False, allow_full_noise=False)
+    sched = DPMSolverMultistepScheduler.from_pretrained("x", subfolder="scheduler", timestep_spacing="trailing")
+    model = FlashDiffusion(cfg, student_denoiser=student, teacher_denoiser=teacher, teacher_noise_scheduler=sched,
+                           sampling_noise_scheduler=LCMScheduler.from_pretrained("x", timestep_spacing="trailing"),
+                           vae=None, conditioner=_conditioner(), discriminator=disc)
+    return model
+
+
+def test_config_ignores_unknown_kwargs_and_broadcasts():
+    c = FlashDiffusionConfig(K=[8, 8], num_iterations_per_K=[1, 2], removed_field=3)
+    assert c.guidance_scale_min == [3.0, 3.0] and c.mode_probs == [[0.25] * 4] * 2
+    with pytest.raises(Exception, match="Number of timesteps must match"):
+        FlashDiffusionConfig(K=[8, 8], num_iterations_per_K=[1])
+
+
+def test_conditioner_wrapper_ucg_semantics():
+    cw, b = _conditioner(), _batch()
+    c = cw(b)["cond"]
+    assert c["crossattn"].shape == (2, 5, 32) and c["vector"].shape == (2, 16 + 24)
+    u = cw(b, ucg_keys=["text_emb", "pooled_emb"])["cond"]
+    assert (u["crossattn"] == 0).all() and (u["vector"][:, :16] == 0).all()
+    assert torch.equal(u["vector"][:, 16:], c["vector"][:, 16:])       # size/crop features kept
+
+
+def test_dpm_scheduler_matches_oracle_rollout():
+    sched = DPMSolverMultistepScheduler.from_pretrained("x", timestep_spacing="trailing")
+    sched.set_timesteps(32)
+    assert sched.timesteps.tolist() == OS.trailing_timesteps(32).tolist()
+    assert sched.timesteps[0] == 999 and sched.timesteps[-1] == 30
+    ac = OS.alphas_cumprod()
+    assert np.allclose(sched.alphas_cumprod.numpy(), ac, rtol=1e-5)
+    torch.manual_seed(0)
+    x0 = torch.randn(2, 4, 8, 8, dtype=torch.float64)
+    W = torch.randn(4, 4, dtype=torch.float64) * 0.3
+
+    def eps_fn(x, t):
+        return torch.tanh(torch.einsum("ij,bjhw->bihw", W, x)) * (1 + t / 1000.0)
+
+    for K, start in [(32, 0), (32, 8), (32, 24), (8, 3), (4, 0)]:
+        ref = OS.dpm_rollout(eps_fn, x0.clone(), ac, K, start)
+        sched.set_timesteps(K)
+        x = x0.clone()
+        for t in sched.timesteps[start:]:
+            x = sched.step(eps_fn(x, int(t)), t, x)[0]
+        assert torch.allclose(x, ref, rtol=1e-4, atol=1e-4), (K, start)
+
+
+def test_lcm_scheduler_timesteps_and_scalings():
+    lcm = LCMScheduler.from_pretrained("x")
+    lcm.set_timesteps(4)
+    assert lcm.timesteps.tolist() == [999, 759, 499, 259] == OS.lcm_timesteps(4).tolist()
+    cs, co = lcm.scalings(500)
+    rcs, rco = OS.lcm_scalings(500.0)
+    assert abs(cs - rcs) < 1e-12 and abs(co - rco) < 1e-12
+
+
+def _draws(B=2, hw=16, seed=3, start_idx=1):
+    g = torch.Generator().manual_seed(seed)
+    return dict(noise=torch.randn(B, 4, hw, hw, generator=g), start_idx=start_idx, guidance=5.5,
+                dmd_noise=torch.randn(B, 4, hw, hw, generator=g), dmd_timestep=torch.tensor([700, 120][:B]),
+                dmd_guidance=4.25, gan_noise=torch.randn(B, 4, hw, hw, generator=g),
+                gan_timesteps=torch.tensor([250, 750][:B]))
+
+
+@pytest.mark.parametrize("gan", ["lsgan", "hinge", "vanilla"])
+@pytest.mark.parametrize("step", [0, 1])
+def test_forward_matches_oracle_step(gan, step):
+    """Product host logic (batched 2B CFG, scheduler classes, conditioner dedupe) == line-by-line oracle."""
+    model = _model(gan=gan)
+    b, d = _batch(), _draws()
+    out = model(b, step=step, draws=d)
+    cw = model.conditioner
+    cond, uncond = cw(b, set_ucg_rate_zero=True), cw(b, ucg_keys=["text_emb", "pooled_emb"])
+    ref = OF.flash_forward(model.student_denoiser, model.teacher_denoiser, model.discriminator, b["image"], cond,
+                           uncond, d, K=4, step=step, gan_loss_type=gan)
+    assert torch.allclose(out["student_output"], ref["student_output"], rtol=1e-4, atol=1e-5)
+    assert torch.allclose(out["teacher_output"], ref["teacher_output"], rtol=1e-4, atol=1e-5)
+    assert torch.allclose(out["loss"][0], ref["loss_G"], rtol=1e-4, atol=1e-6)
+    if step == 0:
+        assert out["loss"][1] == 0 and out["loss"][0] > 0
+    else:
+        assert torch.allclose(out["loss"][1], ref["loss_D"], rtol=1e-4, atol=1e-6) and out["loss"][1] > 0
+
+
+def test_start_idx_zero_uses_pure_noise():
+    model = _model()
+    b, d = _batch(), _draws(start_idx=0)
+    out = model(b, step=0, draws=d)
+    assert torch.equal(out["noisy_sample"], d["noise"]) and out["start_timestep"] == 999
+
+
+def test_start_index_pmf_is_mixture():
+    model = _model(K=32)
+    model.mixture_num_components, model.mode_probs, model.mixture_var = [4], [[0.25] * 4], [0.5]
+    pmf = model._start_index_pmf(32, 0)
+    assert abs(float(pmf.sum()) - 1) < 1e-6
+    assert sorted(torch.topk(pmf, 4).indices.tolist()) == [0, 8, 16, 24]
+    assert float(pmf[[0, 8, 16, 24]].sum()) > 0.75
+
+
+def test_training_step_update_invariants():
+    """reference tests/test_flash/test_flash_diffusion.py:155-187"""
+    model = _model()
+    pipe = TrainingPipeline(model, TrainingConfig(optimizers_name=["AdamW", "AdamW"], learning_rates=[1e-3, 1e-3],
+                                                  trainable_params=[["student_denoiser"], ["discriminator."]]))
+    pipe.configure_optimizers()
+    assert not pipe.automatic_optimization
+    assert all("lora_" in n for n, p in model.student_denoiser.named_parameters() if p.requires_grad)
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    out = pipe.training_step(_batch(), 0)
+    assert out["loss_optimizer_0"] > 0 and out["loss_optimizer_1"] > 0
+    changed = {n for n, p in model.named_parameters() if not torch.equal(p, before[n])}
+    assert all(("lora_" in n and n.startswith("student_denoiser")) or n.startswith("discriminator") for n in changed)
+    assert any(n.startswith("student_denoiser") for n in changed) and any(n.startswith("discriminator") for n in changed)
+    assert not any(n.startswith("teacher_denoiser") for n in changed)
+
+
+def test_sample_runs_four_steps():
+    model = _model()
+    b = _batch()
+    out, ref = model.sample(torch.randn(2, 4, 16, 16), num_steps=4, guidance_scale=1.0, conditioner_inputs=b)
+    assert out.shape == (2, 4, 16, 16) and ref is None and torch.isfinite(out).all()
+
+
+def test_ddpm_scheduler_protocol():
+    s = DDPMScheduler()
+    s.set_timesteps(10)
+    assert len(s.timesteps) == 10 and s.init_noise_sigma == 1.0
+    x = torch.randn(1, 4, 8, 8)
+    assert s.step(torch.randn_like(x), s.timesteps[0], x)[0].shape == x.shape
+    assert s.add_noise(x, torch.randn_like(x), torch.tensor([5])).shape == x.shape
