@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py — Flash-Diffusion distillation-step throughput on B200 (BASELINE.json metric, config 2).
+
+  python bench.py --gpus N --steps K --warmup W            our arm   (N>1: launched under torchrun)
+  python bench.py --impl reference --gpus N --steps K ...  reference arm: the oracle (fp32 PyTorch restatement of
+                                                           the reference's diffusers path; the reference itself is not
+                                                           installable here) on the host CPU cores
+
+Workload (config.workload): SDXL UNet 1024x1024 (latent 128x128) LoRA-rank-64 distillation step, batch 4 per GPU,
+bf16, K=32 trailing DPM-Solver++ teacher, DMD + lsgan, l2 distill, synthetic latents / text embeddings, random-init
+weights (seed 1234).  A "step" is one full `TrainingPipeline.training_step` (both optimizer turns, reference
+src/flash/trainer/trainer.py:169-218).  The teacher-rollout length depends on the sampled start index
+(flash_diffusion_model.py:167,289); the timed steps pin start_idx to 0, 8, 16, 24 in turn (the four mixture modes,
+uniform weights = stage 3 of flash_sdxl.yaml:27-32, E[n] = 20) so every run does the same work.
+
+One JSON line on stdout (rank 0).  See DESIGN.md §Measurement for every key.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "flash-diffusion_b200"))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+METRIC = "distillation images/sec"
+UNIT = "images/s"
+BATCH_PER_GPU = 4
+MODES = [0, 8, 16, 24]                      # start indices of the 4 mixture modes, K = 32
+F_FWD, F_DM = 6.76e12, 2.93e12              # SDXL UNet FLOPs / sample: full forward, down+mid only
+F_LORA_DW = 2 * 2 * 560 * 0                 # (accounted inside the measured kernels; negligible: see DESIGN.md)
+
+
+def flops_per_image(n):
+    """2*[(4+2n)F + 2 F_dm] + F (student dX) + F_dm (GAN dX through the teacher)."""
+    return 2 * ((4 + 2 * n) * F_FWD + 2 * F_DM) + F_FWD + F_DM
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p["bf16_tflops_sustained"], p["hbm_gbs"], "measured (MEASURED_PEAKS.json, sustained bf16)"
+    except Exception:
+        return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_component_times(threads, full=True):
+    """Oracle (fp32 PyTorch, same math as the reference's diffusers path) on the host cores, SDXL at B=1:
+    one teacher forward; optionally one student(LoRA) forward+backward and one GAN-backbone (down+mid, batch 2)
+    forward+backward.  Returns seconds per component."""
+    from oracle.unet import LoraConfig, SDXL_KWARGS, UNet2DConditionOracle
+    torch.set_num_threads(threads)
+    torch.manual_seed(1234)
+    with torch.device("meta"):
+        net = UNet2DConditionOracle(**SDXL_KWARGS)
+    net = net.to_empty(device="cpu")
+    with torch.no_grad():
+        for p in net.parameters():
+            p.normal_(0, 0.02) if p.dim() >= 2 else p.fill_(1.0 if p.dim() == 1 and p.numel() > 4 else 0.0)
+    x = torch.randn(1, 4, 128, 128)
+    t = torch.tensor([500.0])
+    cond = {"cond": {"crossattn": torch.randn(1, 77, 2048), "vector": torch.randn(1, 2816)}}
+    out = {}
+    net.freeze()
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        net(x, t, cond)
+        out["teacher_fwd"] = time.perf_counter() - t0
+    if full:
+        net.add_adapter(LoraConfig(r=64, lora_alpha=64, init_lora_weights="gaussian",
+                                   target_modules=["to_k", "to_q", "to_v", "to_out.0"]))
+        t0 = time.perf_counter()
+        net(x, t, cond).square().mean().backward()
+        out["student_fwd_bwd"] = time.perf_counter() - t0
+        x2 = torch.cat([x, x]).requires_grad_(True)
+        cond2 = {"cond": {k: torch.cat([v, v]) for k, v in cond["cond"].items()}}
+        t0 = time.perf_counter()
+        net(x2, torch.cat([t, t]), cond2, return_intermediate=True).square().mean().backward()
+        out["gan_backbone_fwd_bwd_2"] = time.perf_counter() - t0
+    return out
+
+
+def cpu_images_per_sec(c, n=20):
+    """images/s of the reference step structure from B=1 component times: per optimizer turn
+    1 student fwd + 2n teacher fwd + 3 DMD fwd + GAN backbone at 2 samples; backward once (turn 0)."""
+    tf = c["teacher_fwd"]
+    sfb = c.get("student_fwd_bwd", 3.0 * tf)
+    gfb = c.get("gan_backbone_fwd_bwd_2", 3.0 * 2 * tf * F_DM / F_FWD)
+    turn_fwd = (1 + 2 * n + 3) * tf + gfb / 3.0
+    step = 2 * turn_fwd + (sfb - tf) + gfb * 2.0 / 3.0       # + student backward + GAN backward
+    return 1.0 / step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    comps, vals = None, []
+    t_all = time.perf_counter()
+    for i in range(args.warmup + args.steps):
+        c = cpu_component_times(cores, full=(i == 0))
+        comps = {**(comps or {}), **c} if i == 0 else {**comps, "teacher_fwd": c["teacher_fwd"]}
+        if i >= args.warmup:
+            vals.append(cpu_images_per_sec(comps))
+    v = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * BATCH_PER_GPU / v, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args.gpus),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "per step: one SDXL teacher forward at B=1 on all host threads (oracle, fp32); "
+                                       "student fwd+bwd and GAN-backbone fwd+bwd timed once; images/s extrapolated "
+                                       "with the reference step structure at E[n]=20",
+                             "components_s": comps},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t_all}
+    print(json.dumps(line))
+
+
+def config_dict(n_gpus):
+    return {"workload": "Flash-SDXL UNet 1024x1024 (latent 128x128) LoRA-rank-64 distillation step "
+                        "(student fwd+bwd, K=32 DPM-Solver++ teacher CFG rollout, DMD, lsgan GAN), bf16, batch 4/GPU",
+            "global_batch": BATCH_PER_GPU * n_gpus, "batch_per_gpu": BATCH_PER_GPU, "latent": [4, 128, 128],
+            "context": [77, 2048], "vector": 2816, "lora_rank": 64, "K": 32,
+            "start_idx_schedule": MODES, "expected_teacher_steps": 20,
+            "parallelism": f"dp{n_gpus}", "l2_policy": "inputs and activations larger than L2 (weights 5.1 GB bf16 per UNet)",
+            "weights": "random-init seed 1234", "distill_loss": "l2 (lpips needs offline-unavailable weights)"}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    from flash import recipes
+    from flash.b200 import lib as fdlib
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = fdlib.load()
+    lib.fd_launch_count.restype = __import__("ctypes").c_longlong
+
+    model, pipe = recipes.build_sdxl_distillation(dev)
+    B = BATCH_PER_GPU
+
+    def host_batch(i):
+        return recipes.synthetic_batch(B, 128, 77, 2048, 1280, seed=1234 + rank + 1000 * i, pin=True)
+
+    def draws(i):
+        return {"start_idx": MODES[i % len(MODES)]}
+
+    def step(batch, i):
+        return pipe.training_step(batch, i, draws=draws(i))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up (weight packing, autotuned heuristics, allocator)
+    for w in range(args.warmup):
+        step({k: v.to(dev) for k, v in host_batch(-1 - w).items()}, 3)     # start_idx 24: shortest rollout
+    resident = [{k: v.to(dev) for k, v in host_batch(i).items()} for i in range(args.steps)]
+
+    def timed(fn):
+        barrier()
+        l0 = lib.fd_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms), lib.fd_launch_count() - l0
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # (1) kernel/device throughput: inputs already resident in HBM
+    ms_dev, launches = timed(lambda: [step(resident[i], i) for i in range(args.steps)])
+    # (2) end to end: pinned host batch -> H2D -> step -> loss read back (D2H), every step
+    hosts = [host_batch(100 + i) for i in range(args.steps)]
+    h2d = sum(v.numel() * v.element_size() for v in hosts[0].values())
+    sink = []
+
+    def e2e_loop():
+        for i in range(args.steps):
+            b = {k: v.to(dev, non_blocking=True) for k, v in hosts[i].items()}
+            out = step(b, i)
+            sink.append((float(out["loss_optimizer_0"]), float(out["loss_optimizer_1"])))
+
+    ms_e2e, _ = timed(e2e_loop)
+    clocks = sampler.stop() if rank == 0 else None
+
+    imgs = B * world * args.steps
+    value = imgs / (ms_dev / 1e3)
+    e2e_value = imgs / (ms_e2e / 1e3)
+
+    # roofline of the dominant kernel family (tcgen05 GEMM / implicit-GEMM conv): per-launch CUDA-event timing on
+    # the launch stream during one extra, untimed teacher CFG evaluation at batch 2B (the op that is ~85% of a step)
+    roof = None
+    if rank == 0:
+        import ctypes
+        peak_tf, peak_hbm, peak_src = peaks()
+        lib.fd_profile_enable(1)
+        with torch.no_grad():
+            b0 = resident[0]
+            cond = model.conditioner(b0, set_ucg_rate_zero=True)
+            unc = model.conditioner(b0, ucg_keys=model.ucg_keys)
+            ts = torch.full((B,), 500, device=dev)
+            model._teacher_pair(model.teacher_denoiser, b0["image"], ts, cond, unc)
+        lib.fd_profile_enable(0)
+        ms = (ctypes.c_double * 4)()
+        fl = (ctypes.c_double * 4)()
+        cnt = (ctypes.c_longlong * 4)()
+        lib.fd_profile_summary(ms, fl, cnt, 4)
+        g_ms, g_fl, g_n = ms[0] + ms[1], fl[0] + fl[1], cnt[0] + cnt[1]
+        ach = g_fl / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "fd::gemm_kernel<BN> (tcgen05 GEMM + implicit-GEMM conv)",
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                "peak_source": peak_src, "launches_timed": int(g_n), "avg_launch_us": 1e3 * g_ms / max(1, g_n),
+                "algorithmic_flops_per_launch": g_fl / max(1, g_n),
+                "attention_fwd": {"achieved_tflops": (fl[2] / (ms[2] / 1e3) / 1e12) if ms[2] > 0 else None,
+                                  "launches": int(cnt[2])},
+                "step_level": {"algorithmic_tflop_per_image": flops_per_image(20) / 1e12,
+                               "achieved_tflops_per_gpu": flops_per_image(20) * value / world / 1e12,
+                               "frac_of_peak": flops_per_image(20) * value / world / 1e12 / peak_tf}}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        c = cpu_component_times(cores, full=True)
+        cpu = {"value": cpu_images_per_sec(c), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "oracle (fp32 PyTorch restatement of the reference path) at SDXL B=1 on all host threads: "
+                         "1 teacher fwd, 1 student fwd+bwd, 1 GAN-backbone fwd+bwd (2 samples); images/s extrapolated "
+                         "with the reference step structure at E[n]=20",
+               "components_s": c}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": config_dict(world), "roofline": roof, "cpu_baseline": cpu,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+                        "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": clocks,
+                "losses_last_step": sink[-1] if sink else None}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -16,5 +16,5 @@ for f in fd_api fd_gemm fd_norm fd_elem fd_attn fd_attn_bwd; do
   OBJS="$OBJS ../lib/$f.o"
 done
 for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -cudart static -o ../lib/libflashb200.so $OBJS
+$NVCC -gencode arch=compute_100a,code=sm_100a -shared -cudart static -o ../lib/libflashb200.so $OBJS
 echo "built $(realpath ../lib/libflashb200.so)"

@@ -1,6 +1,8 @@
 // fd_api.cu — error handling, device queries and TMA descriptor encoding for libflashb200.
+#include <atomic>
 #include <mutex>
 #include <string.h>
+#include <vector>
 
 #include "fd_host.h"
 
@@ -37,6 +39,14 @@ static EncodeTiledFn get_encode_fn() {
 
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box) {
+    // cuTensorMapEncodeTiled is a DRIVER call: it needs the primary context current on this thread.
+    // A thread that has not yet issued a runtime call that binds it (e.g. a PyTorch autograd worker
+    // entering our backward first) would get CUDA_ERROR_INVALID_CONTEXT, so bind it once per thread.
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) {
+        cudaFree(0);
+        ctx_bound = true;
+    }
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
@@ -76,6 +86,35 @@ int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
     return 0;
 }
 
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct ProfRec {
+    cudaEvent_t e0, e1;
+    int cat;
+    double work;
+};
+static bool g_prof = false;
+static std::vector<ProfRec> g_recs;
+static std::mutex g_prof_mu;
+
+ProfScope::ProfScope(cudaStream_t s, int cat, double work) : stream(s), slot(-1) {
+    if (!g_prof) return;
+    ProfRec r;
+    r.cat = cat;
+    r.work = work;
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+    cudaEventRecord(r.e0, s);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_recs.push_back(r);
+    slot = (int)g_recs.size() - 1;
+}
+ProfScope::~ProfScope() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEventRecord(g_recs[slot].e1, stream);
+}
+
 int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -94,6 +133,35 @@ extern "C" {
 const char* fd_last_error(void) { return fd::g_err; }
 
 int fd_version(void) { return 100; }
+
+long long fd_launch_count(void) { return fd::g_launches.load(); }
+
+void fd_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(fd::g_prof_mu);
+    fd::g_prof = on != 0;
+}
+
+int fd_profile_summary(double* ms, double* work, long long* counts, int ncat) {
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(fd::g_prof_mu);
+    for (int i = 0; i < ncat; ++i) {
+        ms[i] = 0;
+        work[i] = 0;
+        counts[i] = 0;
+    }
+    for (auto& r : fd::g_recs) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess && r.cat < ncat) {
+            ms[r.cat] += t;
+            work[r.cat] += r.work;
+            counts[r.cat] += 1;
+        }
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    fd::g_recs.clear();
+    return 0;
+}
 
 int fd_sm_arch(void) {
     int dev = 0;

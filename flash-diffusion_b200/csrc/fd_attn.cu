@@ -292,6 +292,7 @@ extern "C" int fd_attn_fwd(const FdAttnArgs* a, void* stream_) {
         attr_set = true;
     }
     dim3 grid((a->Nq + ATT_BM - 1) / ATT_BM, a->H, a->B);
+    ProfScope prof(stream, PROF_ATTN_FWD, 4.0 * (double)a->B * a->H * (double)a->Nq * (double)a->Nkv * ATT_D);
     attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tq, tk, tv, p);
     FD_CHECK_LAUNCH();
     return 0;

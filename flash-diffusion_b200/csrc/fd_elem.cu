@@ -153,7 +153,8 @@ __global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ 
 }
 
 // bf16 [rows, cols] -> [cols, rows], 32x32 tiles through shared memory
-__global__ void transpose_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int rows, int cols) {
+__global__ void transpose_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int rows, int cols,
+                                 long long ldy) {
     __shared__ bf16 tile[32][33];
     const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -163,7 +164,7 @@ __global__ void transpose_kernel(const bf16* __restrict__ x, bf16* __restrict__ 
     __syncthreads();
     for (int j = threadIdx.y; j < 32; j += blockDim.y) {
         const int c = bx + j, r = by + threadIdx.x;
-        if (r < rows && c < cols) y[(long long)c * rows + r] = tile[threadIdx.x][j];
+        if (r < rows && c < cols) y[(long long)c * ldy + r] = tile[threadIdx.x][j];
     }
 }
 
@@ -339,9 +340,10 @@ extern "C" int fd_add(const void* a, const void* b, void* y, int64_t n, void* st
     return 0;
 }
 
-extern "C" int fd_transpose(const void* x, void* y, int32_t rows, int32_t cols, void* stream) {
+extern "C" int fd_transpose(const void* x, void* y, int32_t rows, int32_t cols, int64_t ldy, void* stream) {
+    FD_CHECK_ARG(ldy >= rows, "fd_transpose: ldy < rows");
     dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
-    transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, rows, cols);
+    transpose_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, rows, cols, ldy);
     FD_CHECK_LAUNCH();
     return 0;
 }

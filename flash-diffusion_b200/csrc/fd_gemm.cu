@@ -378,8 +378,9 @@ extern "C" int fd_gemm(const FdGemmArgs* a, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     FD_CHECK_ARG(a != nullptr, "fd_gemm: null args");
     FD_CHECK_ARG(a->M > 0 && a->N > 0, "fd_gemm: bad M/N %d/%d", a->M, a->N);
-    FD_CHECK_ARG(a->K1 > 0 && a->K1 % 8 == 0, "fd_gemm: K1=%d must be a positive multiple of 8", a->K1);
-    FD_CHECK_ARG(a->K2 >= 0 && a->K2 % 8 == 0, "fd_gemm: K2=%d must be a multiple of 8", a->K2);
+    FD_CHECK_ARG(a->K1 > 0 && a->K2 >= 0, "fd_gemm: bad K1/K2 %d/%d", a->K1, a->K2);
+    // K itself may be ragged (TMA zero-fills the tail of the last 64-wide block of BOTH operands);
+    // only the row strides must be 16-byte multiples (checked when the tensor maps are encoded).
     FD_CHECK_ARG(a->a1 && a->b1 && a->out, "fd_gemm: null operand");
     FD_CHECK_ARG(!a->geglu || (a->N % 32 == 0), "fd_gemm: geglu needs N %% 32 == 0");
     FD_CHECK_ARG(!a->rowvec || a->rows_per_group > 0, "fd_gemm: rowvec needs rows_per_group");
@@ -471,6 +472,9 @@ extern "C" int fd_gemm(const FdGemmArgs* a, void* stream_) {
         tA2 = tA1;
         tB2 = tB1;
     }
+    ProfScope prof(stream, a->conv_taps > 0 ? PROF_CONV : PROF_GEMM,
+                   2.0 * (double)a->M * (double)a->N *
+                       ((a->conv_taps > 0 ? (double)a->conv_taps * a->C : (double)a->K1) + (double)a->K2));
     if (BN == 256) return launch_gemm<256>(tA1, tB1, tA2, tB2, p, stream);
     if (BN == 128) return launch_gemm<128>(tA1, tB1, tA2, tB2, p, stream);
     return launch_gemm<64>(tA1, tB1, tA2, tB2, p, stream);

@@ -32,6 +32,7 @@ void set_error(const char* fmt, ...);
 
 #define FD_CHECK_LAUNCH()                                                                \
     do {                                                                                 \
+        fd::count_launch();                                                              \
         cudaError_t _e = cudaGetLastError();                                             \
         if (_e != cudaSuccess) {                                                         \
             fd::set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e),   \
@@ -46,5 +47,15 @@ int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
                      const uint64_t* strides_bytes, const uint32_t* box);
 
 int num_sms();
+
+// launch accounting (fd_launch_count) and optional per-launch CUDA-event profiling (fd_profile_*)
+void count_launch();
+enum ProfCat { PROF_GEMM = 0, PROF_CONV = 1, PROF_ATTN_FWD = 2, PROF_ATTN_BWD = 3, PROF_NCAT = 4 };
+struct ProfScope {
+    cudaStream_t stream;
+    int slot;
+    ProfScope(cudaStream_t s, int cat, double work);   // work = algorithmic FLOPs of the launch
+    ~ProfScope();
+};
 
 }  // namespace fd

@@ -465,26 +465,66 @@ def geglu(x, pack: LinearPack):
 # ------------------------------------------------------------------------------------------------
 # attention
 # ------------------------------------------------------------------------------------------------
-class _AttnFn(torch.autograd.Function):
+class _AttnSelfFn(torch.autograd.Function):
+    """Self-attention on the fused projection output qkv [B, N, 3*H*64] (q | k | v)."""
+
     @staticmethod
-    def forward(ctx, q, k, v, H):
+    def forward(ctx, qkv, H):
+        inner = H * 64
+        q, k, v = qkv[..., :inner], qkv[..., inner:2 * inner], qkv[..., 2 * inner:]
         o, lse = raw.attention_fwd(q, k, v, H, need_lse=True)
-        ctx.save_for_backward(q, k, v, o, lse)
+        ctx.save_for_backward(qkv, o, lse)
         ctx.H = H
         return o
 
     @staticmethod
     def backward(ctx, do):
-        q, k, v, o, lse = ctx.saved_tensors
-        dq, dk, dv = raw.attention_bwd(q, k, v, o, lse, do.contiguous(), ctx.H)
-        return dq, dk, dv, None
+        qkv, o, lse = ctx.saved_tensors
+        H = ctx.H
+        inner = H * 64
+        q, k, v = qkv[..., :inner], qkv[..., inner:2 * inner], qkv[..., 2 * inner:]
+        dqkv = torch.empty_like(qkv)
+        raw.attention_bwd(q, k, v, o, lse, do.contiguous(), H, dq=dqkv[..., :inner], dk=dqkv[..., inner:2 * inner],
+                          dv=dqkv[..., 2 * inner:])
+        return dqkv, None
 
 
-def attention(q, k, v, H):
-    """q [B,Nq,H*64], k/v [B,Nkv,H*64] (last-dim stride 1 views allowed) -> [B,Nq,H*64]."""
-    if _grad_on(q, k, v):
-        return _AttnFn.apply(q, k, v, H)
-    return raw.attention_fwd(q, k, v, H)
+class _AttnCrossFn(torch.autograd.Function):
+    """Cross-attention: q [B, Nq, H*64], fused kv [B, Nkv, 2*H*64] (k | v)."""
+
+    @staticmethod
+    def forward(ctx, q, kv, H):
+        inner = H * 64
+        o, lse = raw.attention_fwd(q, kv[..., :inner], kv[..., inner:], H, need_lse=True)
+        ctx.save_for_backward(q, kv, o, lse)
+        ctx.H = H
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, kv, o, lse = ctx.saved_tensors
+        H = ctx.H
+        inner = H * 64
+        dkv = torch.empty_like(kv)
+        dq, _, _ = raw.attention_bwd(q, kv[..., :inner], kv[..., inner:], o, lse, do.contiguous(), H,
+                                     dk=dkv[..., :inner], dv=dkv[..., inner:])
+        return dq, dkv, None
+
+
+def attention_self(qkv, H):
+    """qkv [B, N, 3*H*64] -> [B, N, H*64]"""
+    if _grad_on(qkv):
+        return _AttnSelfFn.apply(qkv, H)
+    inner = H * 64
+    return raw.attention_fwd(qkv[..., :inner], qkv[..., inner:2 * inner], qkv[..., 2 * inner:], H)
+
+
+def attention_cross(q, kv, H):
+    """q [B, Nq, H*64], kv [B, Nkv, 2*H*64] -> [B, Nq, H*64]"""
+    if _grad_on(q, kv):
+        return _AttnCrossFn.apply(q, kv, H)
+    inner = H * 64
+    return raw.attention_fwd(q, kv[..., :inner], kv[..., inner:], H)
 
 
 # ------------------------------------------------------------------------------------------------

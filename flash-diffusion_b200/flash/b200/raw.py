@@ -148,6 +148,36 @@ def attention_fwd(q, k, v, H, scale=None, need_lse=False):
     return (o, lse) if need_lse else o
 
 
+def attention_bwd(q, k, v, o, lse, do, H, scale=None, dq=None, dk=None, dv=None):
+    """Gradients of attention_fwd.  dq/dk/dv may be given as (strided) output views, e.g. slices of one fused
+    [B, N, 3*H*64] buffer; otherwise contiguous tensors are allocated."""
+    lib = load(); _req(do, BF16, "do")
+    B, Nq, HD = q.shape
+    Nkv = k.shape[1]
+    assert do.stride(2) == 1 and o.stride(2) == 1
+    dq = torch.empty((B, Nq, HD), device=q.device, dtype=BF16) if dq is None else dq
+    dk = torch.empty((B, Nkv, HD), device=q.device, dtype=BF16) if dk is None else dk
+    dv = torch.empty((B, Nkv, HD), device=q.device, dtype=BF16) if dv is None else dv
+    delta = torch.empty((B, H, Nq), device=q.device, dtype=torch.float32)
+    dq_accum = torch.empty((B, Nq, HD), device=q.device, dtype=torch.float32)
+    a = _l.FdAttnBwdArgs()
+    f = a.f
+    f.q, f.ldq, f.q_batch_stride = ptr(q), q.stride(1), q.stride(0)
+    f.k, f.ldk, f.k_batch_stride = ptr(k), k.stride(1), k.stride(0)
+    f.v, f.ldv, f.v_batch_stride = ptr(v), v.stride(1), v.stride(0)
+    f.o, f.ldo, f.o_batch_stride = ptr(o), o.stride(1), o.stride(0)
+    f.lse = ptr(lse)
+    f.B, f.H, f.Nq, f.Nkv = B, H, Nq, Nkv
+    f.scale = scale if scale is not None else 64 ** -0.5
+    a.d_o, a.lddo, a.do_batch_stride = ptr(do), do.stride(1), do.stride(0)
+    a.dq, a.lddq, a.dq_batch_stride = ptr(dq), dq.stride(1), dq.stride(0)
+    a.dk, a.lddk, a.dk_batch_stride = ptr(dk), dk.stride(1), dk.stride(0)
+    a.dv, a.lddv, a.dv_batch_stride = ptr(dv), dv.stride(1), dv.stride(0)
+    a.delta, a.dq_accum = ptr(delta), ptr(dq_accum)
+    check(lib.fd_attn_bwd(byref(a), stream_ptr()), "fd_attn_bwd")
+    return dq, dk, dv
+
+
 # ------------------------------------------------------------------ layout / elementwise
 def nchw_to_nhwc(x, Cpad):
     lib = load(); _req(x, torch.float32, "x")
@@ -230,12 +260,15 @@ def add(a, b):
 
 
 def transpose(x):
+    """bf16 [rows, cols] -> [cols, rows]; the result's row stride is padded to a multiple of 8 elements so that
+    it is a valid TMA operand for any `rows` (the returned view has the exact shape)."""
     lib = load(); _req(x, BF16, "x")
     rows, cols = x.shape
     assert x.is_contiguous()
-    y = torch.empty((cols, rows), device=x.device, dtype=BF16)
-    check(lib.fd_transpose(ptr(x), ptr(y), c_int32(rows), c_int32(cols), stream_ptr()), "fd_transpose")
-    return y
+    ld = (rows + 7) // 8 * 8
+    buf = torch.empty((cols, ld), device=x.device, dtype=BF16)
+    check(lib.fd_transpose(ptr(x), ptr(buf), c_int32(rows), c_int32(cols), c_int64(ld), stream_ptr()), "fd_transpose")
+    return buf[:, :rows]
 
 
 def cast_scale(x, scale=1.0):

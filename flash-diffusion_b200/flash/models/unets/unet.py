@@ -311,14 +311,11 @@ class DiffusersUNet2DCondWrapper(nn.Module):
         inner = H * 64
         if not a.is_cross:
             qkv = ops.linear(x, self._pack(("qkv", id(a)), lambda: LinearPack([a.to_q, a.to_k, a.to_v])))
-            qkv3 = qkv.view(B, -1, 3 * inner)
-            q, k, v = qkv3[..., :inner], qkv3[..., inner:2 * inner], qkv3[..., 2 * inner:]
+            o = ops.attention_self(qkv.view(B, -1, 3 * inner), H).view(-1, inner)
         else:
             q = ops.linear(x, self._pack(("q", id(a)), lambda: LinearPack(a.to_q))).view(B, -1, inner)
             kv = ops.linear(ctx, self._pack(("kv", id(a)), lambda: LinearPack([a.to_k, a.to_v])))
-            kv3 = kv.view(B, -1, 2 * inner)
-            k, v = kv3[..., :inner], kv3[..., inner:]
-        o = ops.attention(q, k, v, H).view(-1, inner)
+            o = ops.attention_cross(q, kv.view(B, -1, 2 * inner), H).view(-1, inner)
         return ops.linear(o, self._pack(("o", id(a)), lambda: LinearPack(a.to_out[0])), residual=residual)
 
     def _transformer(self, t, x, geom, ctx):

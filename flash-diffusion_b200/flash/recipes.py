@@ -1,0 +1,155 @@
+"""Builders for the BASELINE configurations on synthetic data (SURVEY.md §8d, Appendix C recipe).
+
+`build_sdxl_distillation(...)` assembles config 2 exactly as examples/train_flash_sdxl.py does — teacher
+UNet (:66-118), deep-copied student + LoRA r=64 on to_q/to_k/to_v/to_out.0 (:206-217), discriminator
+(:239-267), DPM-Solver++ teacher scheduler with trailing spacing (:221-236), FlashDiffusion (:271-300) and the
+two-optimizer TrainingPipeline (:397-412) — with the two things that cannot exist offline replaced:
+random-init weights instead of the HF checkpoint, and synthetic text embeddings fed through the reference's
+own conditioner API (TorchNNEmbedder(Identity) / TimestepsEmbedder) instead of the CLIP encoders; `vae=None`
+so the batch carries latents (flash_diffusion_model.py:182-185) and the distill loss is l2.
+"""
+import copy
+import math
+
+import torch
+import torch.nn as nn
+
+from .models.embedders import (ConditionerWrapper, TimestepsEmbedder, TimestepsEmbedderConfig, TorchNNEmbedder,
+                               TorchNNEmbedderConfig)
+from .models.flash import FlashDiffusion, FlashDiffusionConfig
+from .models.lora import LoraConfig
+from .models.unets import DiffusersUNet2DCondWrapper
+from .schedulers import DPMSolverMultistepScheduler, LCMScheduler
+from .trainer import TrainingConfig, TrainingPipeline
+
+SDXL_UNET_KWARGS = dict(
+    in_channels=4, out_channels=4, center_input_sample=False, flip_sin_to_cos=True, freq_shift=0,
+    down_block_types=["DownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D"],
+    mid_block_type="UNetMidBlock2DCrossAttn", up_block_types=["CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "UpBlock2D"],
+    only_cross_attention=False, block_out_channels=[320, 640, 1280], layers_per_block=2, downsample_padding=1,
+    mid_block_scale_factor=1, dropout=0.0, act_fn="silu", norm_num_groups=32, norm_eps=1e-05,
+    cross_attention_dim=2048, transformer_layers_per_block=[1, 2, 10], attention_head_dim=[5, 10, 20],
+    use_linear_projection=True, class_embed_type="projection", projection_class_embeddings_input_dim=2816)
+
+TINY_UNET_KWARGS = dict(
+    in_channels=4, out_channels=4, down_block_types=["DownBlock2D", "CrossAttnDownBlock2D"],
+    up_block_types=["CrossAttnUpBlock2D", "UpBlock2D"], block_out_channels=[64, 128], layers_per_block=1,
+    cross_attention_dim=96, transformer_layers_per_block=[1, 2], attention_head_dim=[1, 2],
+    use_linear_projection=True, class_embed_type="projection", projection_class_embeddings_input_dim=48 + 3 * 16)
+
+
+@torch.no_grad()
+def init_random_(module: nn.Module, seed: int):
+    """Deterministic random init directly on the module's device (fan-in scaled normal weights, zero biases,
+    unit norms).  Same seed -> same weights on every rank."""
+    g = torch.Generator(device=next(module.parameters()).device).manual_seed(seed)
+    for name, p in module.named_parameters():
+        if p.dim() >= 2:
+            fan_in = p[0].numel()
+            p.normal_(0.0, 1.0 / math.sqrt(fan_in), generator=g)
+        elif name.endswith("bias"):
+            p.zero_()
+        else:
+            p.fill_(1.0)           # GroupNorm / LayerNorm weights
+    return module
+
+
+def sdxl_discriminator(color_dim=1280, feature_dim=256):
+    """examples/train_flash_sdxl.py:239-267"""
+    d = feature_dim
+    return nn.Sequential(
+        nn.Conv2d(color_dim, d, 4, 2, 1, bias=False), nn.SiLU(True),
+        nn.Conv2d(d, d * 2, 4, 2, 1, bias=False), nn.GroupNorm(4, d * 2), nn.SiLU(True),
+        nn.Conv2d(d * 2, d * 4, 4, 2, 1, bias=False), nn.GroupNorm(4, d * 4), nn.SiLU(True),
+        nn.Conv2d(d * 4, 1, 4, 1, 0, bias=False), nn.Flatten())
+
+
+def tiny_discriminator(color_dim=128):
+    return nn.Sequential(nn.Conv2d(color_dim, 32, 4, 2, 1, bias=False), nn.SiLU(True),
+                         nn.Conv2d(32, 32, 4, 2, 1, bias=False), nn.GroupNorm(4, 32), nn.SiLU(True),
+                         nn.Conv2d(32, 1, 4, 1, 0, bias=False), nn.Flatten())
+
+
+def synthetic_conditioner(fourier_channels=256):
+    """text / pooled embeddings through Identity embedders, size/crop ids through
+    TimestepsEmbedder — the same slots the CLIP embedders fill in examples/train_flash_sdxl.py:137-195."""
+    ident = dict(nn_modules=["torch.nn.Identity"], nn_modules_kwargs=[{}])
+    return ConditionerWrapper([
+        TorchNNEmbedder(TorchNNEmbedderConfig(input_key="text_emb", **ident)),
+        TorchNNEmbedder(TorchNNEmbedderConfig(input_key="pooled_emb", **ident)),
+        TimestepsEmbedder(TimestepsEmbedderConfig(input_key="original_size_as_tuple", num_channels=fourier_channels)),
+        TimestepsEmbedder(TimestepsEmbedderConfig(input_key="crop_coords_top_left", num_channels=fourier_channels)),
+        TimestepsEmbedder(TimestepsEmbedderConfig(input_key="target_size_as_tuple", num_channels=fourier_channels)),
+    ])
+
+
+def synthetic_batch(B, latent_hw, ctx_tokens, ctx_dim, pooled_dim, seed, device="cpu", pin=False, image_px=1024.0):
+    g = torch.Generator().manual_seed(seed)
+    batch = {
+        "image": torch.randn(B, 4, latent_hw, latent_hw, generator=g),
+        "text_emb": torch.randn(B, ctx_tokens, ctx_dim, generator=g),
+        "pooled_emb": torch.randn(B, pooled_dim, generator=g),
+        "original_size_as_tuple": torch.tensor([[image_px, image_px]] * B),
+        "crop_coords_top_left": torch.zeros(B, 2),
+        "target_size_as_tuple": torch.tensor([[image_px, image_px]] * B),
+    }
+    if pin:
+        batch = {k: v.pin_memory() for k, v in batch.items()}
+    if device != "cpu":
+        batch = {k: v.to(device) for k, v in batch.items()}
+    return batch
+
+
+def build_distillation(unet_kwargs, discriminator, device, *, lora_rank=64, K=32, seed=1234, lora_b_std=0.01,
+                       fourier_channels=256, stage=2, lr=1e-5):
+    """teacher / student(LoRA) / discriminator / FlashDiffusion / TrainingPipeline on `device`."""
+    with torch.device("meta"):
+        teacher = DiffusersUNet2DCondWrapper(**unet_kwargs)
+    teacher = teacher.to_empty(device=device)
+    init_random_(teacher, seed)
+    student = copy.deepcopy(teacher)
+    student.add_adapter(LoraConfig(r=lora_rank, lora_alpha=lora_rank, init_lora_weights="gaussian",
+                                   target_modules=["to_k", "to_q", "to_v", "to_out.0"]))
+    if lora_b_std > 0:
+        g = torch.Generator(device=device).manual_seed(seed + 1)
+        with torch.no_grad():
+            for n, p in student.named_parameters():
+                if "lora_B" in n:
+                    p.normal_(0.0, lora_b_std, generator=g)
+    teacher.freeze()
+    torch.manual_seed(seed + 2)
+    discriminator = discriminator.to(device)
+    # flash_sdxl.yaml:11-32 — K=32 every stage, mixture over 4 modes; stage index selects the yaml's per-stage
+    # loss scales and mode probabilities (stage 2 = uniform modes, E[n] = 20)
+    adv = [0.0, 0.1, 0.2, 0.3][stage]
+    dmd = [0.0, 0.3, 0.5, 0.7][stage]
+    probs = [[0.0, 0.0, 0.5, 0.5], [0.1, 0.3, 0.3, 0.3], [0.25, 0.25, 0.25, 0.25], [0.4, 0.2, 0.2, 0.2]][stage]
+    cfg = FlashDiffusionConfig(
+        K=[K], num_iterations_per_K=[10 ** 9], guidance_scale_min=3.0, guidance_scale_max=13.0,
+        distill_loss_type="l2", ucg_keys=["text_emb", "pooled_emb"], timestep_distribution="mixture",
+        mixture_num_components=4, mixture_var=0.5, use_dmd_loss=True, dmd_loss_scale=dmd, distill_loss_scale=1.0,
+        adversarial_loss_scale=adv, gan_loss_type="lsgan", mode_probs=[probs], use_teacher_as_real=False,
+        use_empty_prompt=False, input_key="image")
+    sched = DPMSolverMultistepScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0",
+                                                        subfolder="scheduler", timestep_spacing="trailing")
+    lcm = LCMScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", subfolder="scheduler",
+                                       timestep_spacing="trailing")
+    model = FlashDiffusion(cfg, student_denoiser=student, teacher_denoiser=teacher, teacher_noise_scheduler=sched,
+                           sampling_noise_scheduler=lcm, vae=None, conditioner=synthetic_conditioner(fourier_channels),
+                           discriminator=discriminator).to(device)
+    pipe = TrainingPipeline(model, TrainingConfig(
+        optimizers_name=["AdamW", "AdamW"], learning_rates=[lr, lr],
+        trainable_params=[["student_denoiser"], ["discriminator."]]))
+    pipe.configure_optimizers()
+    return model, pipe
+
+
+def build_sdxl_distillation(device, **kw):
+    return build_distillation(SDXL_UNET_KWARGS, sdxl_discriminator(), device, **kw)
+
+
+def build_tiny_distillation(device, **kw):
+    kw.setdefault("lora_rank", 64)
+    kw.setdefault("K", 4)
+    kw.setdefault("fourier_channels", 8)
+    return build_distillation(TINY_UNET_KWARGS, tiny_discriminator(), device, **kw)

@@ -30,6 +30,14 @@ const char* fd_last_error(void);
 int fd_version(void);
 /* compute capability (major*10+minor) of the current device, or negative if no device */
 int fd_sm_arch(void);
+/* number of kernels this library has launched in this process (bench.py's `gpu_launches`) */
+long long fd_launch_count(void);
+/* Per-launch CUDA-event timing of the tensor-core kernels on their launch stream (bench.py roofline).
+ * categories: 0 plain GEMM, 1 implicit-GEMM conv, 2 attention fwd, 3 attention bwd.
+ * fd_profile_summary synchronises the device, fills ms / algorithmic FLOPs / launch counts per category
+ * and clears the records. */
+void fd_profile_enable(int on);
+int fd_profile_summary(double* ms, double* flops, long long* counts, int ncat);
 
 /* ------------------------------------------------------------------------------------------
  * fd_gemm — tcgen05/TMA GEMM with an optional second K segment and a fused epilogue.
@@ -155,8 +163,8 @@ int fd_slice_channels(const void* x, int32_t Ctot, int32_t c0, int32_t C, void* 
                       void* stream);
 /* y = a + b (bf16, n elements) */
 int fd_add(const void* a, const void* b, void* y, int64_t n, void* stream);
-/* bf16 [rows, cols] -> bf16 [cols, rows] */
-int fd_transpose(const void* x, void* y, int32_t rows, int32_t cols, void* stream);
+/* bf16 [rows, cols] -> bf16 [cols, rows] written with row stride ldy >= rows */
+int fd_transpose(const void* x, void* y, int32_t rows, int32_t cols, int64_t ldy, void* stream);
 /* fp32 -> bf16 with scale (weight packing, LoRA B * alpha/r) */
 int fd_cast_scale(const float* x, void* y, int64_t n, float scale, void* stream);
 /* SiLU on fp32 [n] -> bf16 (ResnetBlock2D time-embedding nonlinearity) */

@@ -113,6 +113,8 @@ def test_layout_and_elementwise(raw):
     assert torch.equal(cat, torch.cat([a.view(-1, C), b], dim=1))
     assert torch.equal(raw.add(b, b), (b.float() * 2).bfloat16())
     assert torch.equal(raw.transpose(b), b.t().contiguous())
+    b2 = torch.randn(77, 40, device="cuda").bfloat16()
+    assert torch.equal(raw.transpose(b2), b2.t())
     w = torch.randn(33, 70, device="cuda")
     assert torch.equal(raw.cast_scale(w, 0.5), (w * 0.5).bfloat16())
     assert _rel(raw.silu_f32_to_bf16(w), F.silu(w)) < 4e-3
