@@ -119,9 +119,9 @@ def test_lcm_scheduler_timesteps_and_scalings():
 def _draws(B=2, hw=16, seed=3, start_idx=1):
     g = torch.Generator().manual_seed(seed)
     return dict(noise=torch.randn(B, 4, hw, hw, generator=g), start_idx=start_idx, guidance=5.5,
-                dmd_noise=torch.randn(B, 4, hw, hw, generator=g), dmd_timestep=torch.tensor([700, 120][:B]),
+                dmd_noise=torch.randn(B, 4, hw, hw, generator=g), dmd_timestep=torch.tensor([700, 120, 333, 901][:B]),
                 dmd_guidance=4.25, gan_noise=torch.randn(B, 4, hw, hw, generator=g),
-                gan_timesteps=torch.tensor([250, 750][:B]))
+                gan_timesteps=torch.tensor([250, 750, 10, 500][:B]))
 
 
 @pytest.mark.parametrize("gan", ["lsgan", "hinge", "vanilla"])
