@@ -210,9 +210,14 @@ def run_ours(args):
         step({k: v.to(dev) for k, v in host_batch(-1 - w).items()}, 3)     # start_idx 24: shortest rollout
     resident = [{k: v.to(dev) for k, v in host_batch(i).items()} for i in range(args.steps)]
 
+    from flash.b200 import graphs
+
+    def launches_now():
+        return lib.fd_launch_count() + graphs.REPLAYED_LAUNCHES
+
     def timed(fn):
         barrier()
-        l0 = lib.fd_launch_count()
+        l0 = launches_now()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
@@ -221,7 +226,7 @@ def run_ours(args):
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms), lib.fd_launch_count() - l0
+        return float(ms), launches_now() - l0
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -252,6 +257,7 @@ def run_ours(args):
     if rank == 0:
         import ctypes
         peak_tf, peak_hbm, peak_src = peaks()
+        model.use_cuda_graphs = False            # eager launches so that every launch gets its CUDA events
         lib.fd_profile_enable(1)
         with torch.no_grad():
             b0 = resident[0]
@@ -260,6 +266,7 @@ def run_ours(args):
             ts = torch.full((B,), 500, device=dev)
             model._teacher_pair(model.teacher_denoiser, b0["image"], ts, cond, unc)
         lib.fd_profile_enable(0)
+        model.use_cuda_graphs = True
         ms = (ctypes.c_double * 4)()
         fl = (ctypes.c_double * 4)()
         cnt = (ctypes.c_longlong * 4)()

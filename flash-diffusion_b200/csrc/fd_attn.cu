@@ -2,15 +2,16 @@
 //
 //   O = softmax(Q K^T * scale) V       per (batch, head), Q/K/V read in place from [B, N, H*64]
 //
-// One CTA per (128-query tile, head, batch); 6 warps:
-//   warp 0    TMA producer  : Q once, K/V tiles (128 keys) through a 2-stage ring
-//   warp 1    MMA issuer    : S = Q K^T (tcgen05, 128x128x64) and O += P V (128x64x128), TMEM accum
-//   warps 2-5 softmax       : tcgen05.ld S, online softmax (exp2, warp-free: one row per thread),
-//                             P -> shared memory (bf16, 128B-swizzled K-major), O rescale in TMEM
-// TMEM: S in columns [0,128), O in [128,192).  V is consumed as an MN-major B operand straight
+// One CTA per (256 queries = two 128-row tiles, head, batch); 10 warps:
+//   warp 0    TMA producer  : Q0,Q1 once, K/V tiles (128 keys) through a 3-stage ring
+//   warp 1    MMA issuer    : S_w = Q_w K^T (tcgen05 128x128x64) and O_w += P_w V (128x64x128) for w = 0,1,
+//                             interleaved so that the softmax of one tile overlaps the MMAs of the other
+//   warps 2-5 / 6-9 softmax : one warpgroup per query tile; the S row goes to registers in one tcgen05.ld round
+//                             trip and the S buffer is released at once (S(j+1) is issued while softmax(j) runs);
+//                             FMNMX3 row max, FFMA2 + ex2.approx + FADD2, P -> smem (bf16, 128B-swizzled K-major);
+//                             O rescaled in TMEM only when the running maximum grew by more than 2^8
+// TMEM: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384).  V is consumed as an MN-major B operand straight
 // from its row-major [key, d] tile, so no transpose is materialised.
-// Two CTAs fit per SM (112 KB smem, 256 TMEM columns each) and overlap each other's
-// softmax / MMA phases.
 //
 // UPSTREAM math: diffusers Attention + AttnProcessor2_0 -> F.scaled_dot_product_attention
 // (SURVEY.md §2.2); reference call path src/flash/models/unets/unet.py:108-119.
@@ -19,15 +20,14 @@
 
 namespace fd {
 
-constexpr int ATT_BM = 128;   // queries per CTA
+constexpr int ATT_BM = 256;   // queries per CTA: two 128-row tiles, one softmax warpgroup each
 constexpr int ATT_BN = 128;   // keys per tile
 constexpr int ATT_D = 64;
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_STAGES = 3;
+constexpr int ATT_THREADS = 64 + 256;         // TMA warp, MMA warp, 2 x 4 softmax warps
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB
-// No alignment slack: two CTAs must fit in 228 KB; the dynamic smem window is 1024-aligned
-// (checked at kernel entry).
-constexpr int ATT_SMEM = ATT_TILE_BYTES /*Q*/ + 4 * ATT_TILE_BYTES /*K,V x2*/ +
-                         2 * ATT_TILE_BYTES /*P*/ + 256;
+// Q0,Q1 | K,V x stages | P0,P1 (2 sub-tiles each) | barriers
+constexpr int ATT_SMEM = 2 * ATT_TILE_BYTES + 2 * ATT_STAGES * ATT_TILE_BYTES + 4 * ATT_TILE_BYTES + 256 + 1024;
 
 struct AttnKParams {
     int Nq, Nkv;
@@ -51,30 +51,66 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
         : "memory");
 }
 
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+// packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2): halves the issue slots of the softmax inner loop
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    uint64_t ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    float2 d;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+    uint64_t ra, rb, rd;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1,%2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    float2 d;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+
+// Rescale threshold (log2 domain): O and l are only rescaled when the running row maximum grew by more
+// than this; otherwise the stale maximum keeps being used (P <= 2^8, exact in fp32 accumulation, and the
+// final O / l is invariant to the reference maximum).
+constexpr float ATT_RESCALE_THRESHOLD = 8.0f;
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnKParams p) {
     extern __shared__ uint8_t smem_raw[];
-    if ((smem_u32(smem_raw) & 1023u) != 0) {
-        if (threadIdx.x == 0) printf("fd_attn: dynamic smem base not 1024-aligned\n");
-        __trap();
-    }
-    uint8_t* sQ = smem_raw;
-    uint8_t* sK = sQ + ATT_TILE_BYTES;          // 2 stages
-    uint8_t* sV = sK + 2 * ATT_TILE_BYTES;      // 2 stages
-    uint8_t* sP = sV + 2 * ATT_TILE_BYTES;      // 2 sub-tiles of [128][64]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * ATT_TILE_BYTES);
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    uint8_t* sQ = smem;                                   // 2 tiles
+    uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;                // ATT_STAGES tiles
+    uint8_t* sV = sK + ATT_STAGES * ATT_TILE_BYTES;       // ATT_STAGES tiles
+    uint8_t* sP = sV + ATT_STAGES * ATT_TILE_BYTES;       // 2 x (2 sub-tiles of [128][64])
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * ATT_TILE_BYTES);
     uint64_t* q_full = bars;
-    uint64_t* kv_full = bars + 1;   // [2]
-    uint64_t* kv_empty = bars + 3;  // [2]
-    uint64_t* s_full = bars + 5;
-    uint64_t* p_ready = bars + 6;
-    uint64_t* o_done = bars + 7;
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* kv_full = bars + 1;                  // [ATT_STAGES]
+    uint64_t* kv_empty = kv_full + ATT_STAGES;     // [ATT_STAGES]
+    uint64_t* s_full = kv_empty + ATT_STAGES;      // [2]  S_w(j) written by the tensor core
+    uint64_t* s_free = s_full + 2;                 // [2]  S_w(j) copied to registers: S_w(j+1) may be issued
+    uint64_t* p_ready = s_free + 2;                // [2]  P_w(j) in smem
+    uint64_t* pv_done = p_ready + 2;               // [2]  O_w += P_w(j) V(j) complete
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pv_done + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int q_tile = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
+    const int q_blk = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
     const int n_kv_tiles = (p.Nkv + ATT_BN - 1) / ATT_BN;
 
     if (warp == 0 && lane == 0) {
@@ -84,146 +120,205 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     if (warp == 1 && lane == 0) {
         mbar_init(q_full, 1);
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < ATT_STAGES; ++s) {
             mbar_init(&kv_full[s], 1);
             mbar_init(&kv_empty[s], 1);
         }
-        mbar_init(s_full, 1);
-        mbar_init(p_ready, 128);
-        mbar_init(o_done, 1);
+        for (int w = 0; w < 2; ++w) {
+            mbar_init(&s_full[w], 1);
+            mbar_init(&s_free[w], 128);
+            mbar_init(&p_ready[w], 128);
+            mbar_init(&pv_done[w], 1);
+        }
         fence_barrier_init();
     }
     if (warp == 0) {
-        tmem_alloc(tmem_holder, 256);
+        tmem_alloc(tmem_holder, 512);
         tmem_relinquish();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
-    const uint32_t tmem_S = tmem_base;
-    const uint32_t tmem_O = tmem_base + 128;
+    // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
-            tma_load_3d(&tmQ, q_full, sQ, head * ATT_D, q_tile * ATT_BM, batch);
+            mbar_arrive_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+            tma_load_3d(&tmQ, q_full, sQ, head * ATT_D, q_blk * ATT_BM, batch);
+            tma_load_3d(&tmQ, q_full, sQ + ATT_TILE_BYTES, head * ATT_D, q_blk * ATT_BM + 128, batch);
+            int st = 0;
+            uint32_t ph = 0;
             for (int j = 0; j < n_kv_tiles; ++j) {
-                const int st = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
                 mbar_wait(&kv_empty[st], ph ^ 1u);
                 mbar_arrive_expect_tx(&kv_full[st], 2 * ATT_TILE_BYTES);
                 tma_load_3d(&tmK, &kv_full[st], sK + st * ATT_TILE_BYTES, head * ATT_D, j * ATT_BN, batch);
                 tma_load_3d(&tmV, &kv_full[st], sV + st * ATT_TILE_BYTES, head * ATT_D, j * ATT_BN, batch);
+                if (++st == ATT_STAGES) {
+                    st = 0;
+                    ph ^= 1u;
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             constexpr uint32_t idesc_qk = make_idesc_bf16(128, ATT_BN, 0, 0);
             constexpr uint32_t idesc_pv = make_idesc_bf16(128, ATT_D, 0, 1);  // B (=V) MN-major
-            mbar_wait(q_full, 0);
             const uint32_t q_addr = smem_u32(sQ);
             const uint32_t p_addr = smem_u32(sP);
-            for (int j = 0; j < n_kv_tiles; ++j) {
-                const int st = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
-                mbar_wait(&kv_full[st], ph);
-                tc_fence_after();
+            auto issue_s = [&](int w, int st) {
                 const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES);
-                const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES);
+                const uint32_t qa = q_addr + w * ATT_TILE_BYTES;
 #pragma unroll
                 for (int k = 0; k < ATT_D / 16; ++k)
-                    tc_mma_bf16(tmem_S, make_desc_k_sw128(q_addr + k * 32), make_desc_k_sw128(k_addr + k * 32),
-                                idesc_qk, k != 0 ? 1u : 0u);
-                tc_commit(s_full);
-                mbar_wait(p_ready, j & 1);
-                tc_fence_after();
+                    tc_mma_bf16(tmem_base + w * 128, make_desc_k_sw128(qa + k * 32),
+                                make_desc_k_sw128(k_addr + k * 32), idesc_qk, k != 0 ? 1u : 0u);
+                tc_commit(&s_full[w]);
+            };
+            auto issue_pv = [&](int w, int st, int j) {
+                const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES);
+                const uint32_t pa = p_addr + w * 2 * ATT_TILE_BYTES;
 #pragma unroll
                 for (int k = 0; k < ATT_BN / 16; ++k)
-                    tc_mma_bf16(tmem_O, make_desc_k_sw128(p_addr + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32),
-                                make_desc_mn_sw128(v_addr + k * 2048, 0, 1024), idesc_pv,
-                                (j | k) != 0 ? 1u : 0u);
-                tc_commit(&kv_empty[st]);
-                tc_commit(o_done);
+                    tc_mma_bf16(tmem_base + 256 + w * 64,
+                                make_desc_k_sw128(pa + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32),
+                                make_desc_mn_sw128(v_addr + k * 2048, 0, 1024), idesc_pv, (j | k) != 0 ? 1u : 0u);
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(&kv_full[0], 0);
+            tc_fence_after();
+            issue_s(0, 0);
+            issue_s(1, 0);
+            // Event-driven issue: per query tile w, S_w(j+1) may go as soon as S_w(j) was copied to registers
+            // (s_free) and K(j+1) has landed; P_w(j) V(j) as soon as P_w(j) is in smem (p_ready).  Whichever
+            // event fires first is served first, so a late warpgroup never delays the other one.
+            int next_s[2] = {1, 1};      // next S tile to issue
+            int next_pv[2] = {0, 0};     // next P V tile to issue
+            int kv_seen = 1;             // number of K/V tiles known to have landed
+            while (next_pv[0] < n_kv_tiles || next_pv[1] < n_kv_tiles) {
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                    const int js = next_s[w];
+                    if (js < n_kv_tiles) {
+                        // needs: s_free[w](js-1) and kv_full(js)
+                        if (mbar_try_wait(&s_free[w], (js - 1) & 1)) {
+                            bool kv_ok = js < kv_seen;
+                            if (!kv_ok && js == kv_seen) {
+                                const int stg = js % ATT_STAGES;
+                                if (mbar_try_wait(&kv_full[stg], (js / ATT_STAGES) & 1)) {
+                                    kv_seen = js + 1;
+                                    kv_ok = true;
+                                }
+                            }
+                            if (kv_ok) {
+                                tc_fence_after();
+                                issue_s(w, js % ATT_STAGES);
+                                next_s[w] = js + 1;
+                            }
+                        }
+                    }
+                    const int jp = next_pv[w];
+                    if (jp < n_kv_tiles && mbar_try_wait(&p_ready[w], jp & 1)) {
+                        tc_fence_after();
+                        issue_pv(w, jp % ATT_STAGES, jp);
+                        tc_commit(&pv_done[w]);
+                        next_pv[w] = jp + 1;
+                        // the K/V stage of tile jp is free once BOTH query tiles have issued their P V on it
+                        if (next_pv[w ^ 1] > jp) tc_commit(&kv_empty[jp % ATT_STAGES]);
+                    }
+                }
             }
         }
     } else {
-        // softmax warps 2..5: TMEM lane quarter = warp % 4
+        // softmax warpgroup w = 0 (warps 2-5) / 1 (warps 6-9); TMEM lane quarter = warp % 4
+        const int w = (warp - 2) >> 2;
         const int quarter = warp & 3;
-        const int row = quarter * 32 + lane;              // row within the query tile
+        const int row = quarter * 32 + lane;                       // row within this 128-query tile
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-        float m_run = -INFINITY, l_run = 0.f;
+        const uint32_t tmem_S = tmem_base + w * 128;
+        const uint32_t tmem_O = tmem_base + 256 + w * 64;
+        uint8_t* sPw = sP + w * 2 * ATT_TILE_BYTES;
+        float m_used = -INFINITY, l_run = 0.f;
         for (int j = 0; j < n_kv_tiles; ++j) {
-            mbar_wait(s_full, j & 1);
+            mbar_wait(&s_full[w], j & 1);
             tc_fence_after();
             const int kv_valid = min(ATT_BN, p.Nkv - j * ATT_BN);
-            // pass 1: row max
-            float mx = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < ATT_BN / 32; ++c) {
-                if (c * 32 >= kv_valid) break;
-                uint32_t r[32];
-                tmem_ld_32x32(tmem_S + lane_base + c * 32, r);
-                tmem_ld_wait();
+            // the whole S row (128 fp32) comes to registers in ONE TMEM round trip; the S buffer is then free
+            uint32_t sr[4][32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (c * 32 + i < kv_valid) mx = fmaxf(mx, __uint_as_float(r[i]));
+            for (int c = 0; c < 4; ++c) tmem_ld_32x32(tmem_S + lane_base + c * 32, sr[c]);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&s_free[w]);
+            if (kv_valid < ATT_BN) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c * 32 + i >= kv_valid) sr[c][i] = 0xff800000u;      // -inf: exp2 -> 0
             }
-            const float m_new = fmaxf(m_run, mx * p.scale_log2);
-            const float alpha = exp2f(m_run - m_new);
-            // previous P V must be complete before O / P are touched again
+            float mxs[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int i = 0; i < 32; i += 2)
+                    mxs[c] = max3(mxs[c], __uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1]));
+            const float mx = fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3]));
+            const float m_new = mx * p.scale_log2;
+            const bool grow = m_new > m_used + ATT_RESCALE_THRESHOLD;      // first tile: m_used = -inf -> true
+            const float alpha = (grow && j > 0) ? fast_exp2(m_used - m_new) : 1.0f;
+            if (grow) m_used = m_new;
+            l_run *= alpha;
+            const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+            const float2 nm2 = make_float2(-m_used, -m_used);
+            float2 ps2 = make_float2(0.f, 0.f);
+            uint32_t pk[4][16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float2 x = ffma2(make_float2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), sc2, nm2);
+                    const float2 e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+                    ps2 = fadd2(ps2, e);
+                    pk[c][i >> 1] = pack_bf16x2(e.x, e.y);
+                }
+            }
+            l_run += ps2.x + ps2.y;
+            // P_w(j-1) V(j-1) must have completed before O is rescaled or the P buffer is overwritten
             if (j > 0) {
-                mbar_wait(o_done, (j - 1) & 1);
+                mbar_wait(&pv_done[w], (j - 1) & 1);
                 tc_fence_after();
+                if (__any_sync(0xffffffffu, alpha != 1.0f)) {
 #pragma unroll 1
-                for (int c = 0; c < ATT_D / 32; ++c) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(tmem_O + lane_base + c * 32, r);
-                    tmem_ld_wait();
+                    for (int c = 0; c < ATT_D / 32; ++c) {
+                        uint32_t r[32];
+                        tmem_ld_32x32(tmem_O + lane_base + c * 32, r);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-                    tmem_st_32x32(tmem_O + lane_base + c * 32, r);
-                }
-                tmem_st_wait();
-            }
-            // pass 2: exponentials -> P (bf16) in swizzled K-major shared memory
-            float psum = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < ATT_BN / 32; ++c) {
-                uint32_t r[32];
-                uint32_t pk[16];
-                if (c * 32 < kv_valid) {
-                    tmem_ld_32x32(tmem_S + lane_base + c * 32, r);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        float p0 = (c * 32 + i < kv_valid) ? exp2f(__uint_as_float(r[i]) * p.scale_log2 - m_new) : 0.f;
-                        float p1 = (c * 32 + i + 1 < kv_valid) ? exp2f(__uint_as_float(r[i + 1]) * p.scale_log2 - m_new) : 0.f;
-                        psum += p0 + p1;
-                        pk[i >> 1] = pack_bf16x2(p0, p1);
+                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                        tmem_st_32x32(tmem_O + lane_base + c * 32, r);
                     }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) pk[i] = 0u;
+                    tmem_st_wait();
                 }
-                uint8_t* sub = sP + (c >> 1) * ATT_TILE_BYTES + row * 128;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint8_t* sub = sPw + (c >> 1) * ATT_TILE_BYTES + row * 128;
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
                     const int chunk = ((c & 1) * 4 + q4) ^ (row & 7);
                     *reinterpret_cast<uint4*>(sub + chunk * 16) =
-                        make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+                        make_uint4(pk[c][4 * q4], pk[c][4 * q4 + 1], pk[c][4 * q4 + 2], pk[c][4 * q4 + 3]);
                 }
             }
-            l_run = l_run * alpha + psum;
-            m_run = m_new;
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(p_ready);
+            mbar_arrive(&p_ready[w]);
         }
         // epilogue: O / l -> bf16
-        mbar_wait(o_done, (n_kv_tiles - 1) & 1);
+        mbar_wait(&pv_done[w], (n_kv_tiles - 1) & 1);
         tc_fence_after();
-        const int q_row = q_tile * ATT_BM + row;
+        const int q_row = q_blk * ATT_BM + w * 128 + row;
         const float inv_l = 1.f / l_run;
         bf16* orow = p.o + (long long)batch * p.o_batch_stride + (long long)q_row * p.ldo + head * ATT_D;
 #pragma unroll 1
@@ -244,14 +339,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
         }
         if (p.lse != nullptr && q_row < p.Nq)
-            p.lse[((long long)batch * p.H + head) * p.Nq + q_row] = (m_run + log2f(l_run)) * 0.69314718055994531f;
+            p.lse[((long long)batch * p.H + head) * p.Nq + q_row] = (m_used + log2f(l_run)) * 0.69314718055994531f;
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 256);
+        tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -259,7 +354,7 @@ static int make_qkv_tmap(CUtensorMap* m, const void* base, int H, int N, int B, 
                          int64_t batch_stride) {
     const uint64_t dims[3] = {(uint64_t)H * ATT_D, (uint64_t)N, (uint64_t)B};
     const uint64_t str[2] = {(uint64_t)ld * 2, (uint64_t)batch_stride * 2};
-    const uint32_t box[3] = {(uint32_t)ATT_D, 128u, 1u};
+    const uint32_t box[3] = {(uint32_t)ATT_D, 128u, 1u};   // 128-row tiles for Q (two per CTA), K and V
     return encode_tmap_bf16(m, base, 3, dims, str, box);
 }
 

@@ -13,6 +13,8 @@
 //
 // Reference math replaced: torch linear / conv2d calls under
 // src/flash/models/unets/unet.py:108-119 (see include/flashb200.h, fd_gemm).
+#include <stdlib.h>
+
 #include "fd_common.cuh"
 #include "fd_host.h"
 
@@ -46,6 +48,19 @@ struct GemmCfg {
     static constexpr int TMEM_COLS = 2 * BN;  // 128 / 256 / 512: powers of two
     static constexpr int SMEM_BYTES = STAGES * (A_BYTES + B_BYTES) + 256 + 1024;
 };
+
+// Tile rasterisation: consecutive tile indices (= what the 148 persistent CTAs work on at the same time) walk
+// GROUP_M m-tiles x all n-tiles, m fastest, so a wave touches ~16 A row-panels and ~9 B panels instead of
+// 148 A panels and 1 B panel: each A panel is fetched from DRAM once per group and re-used out of L2.
+constexpr int GROUP_M = 16;
+__device__ __forceinline__ void tile_coords(const GemmKParams& p, int tile, int& mt, int& nt) {
+    const int per_group = GROUP_M * p.num_n_tiles;
+    const int g = tile / per_group;
+    const int r = tile - g * per_group;
+    const int gm = min(GROUP_M, p.num_m_tiles - g * GROUP_M);
+    nt = r / gm;
+    mt = g * GROUP_M + (r - nt * gm);
+}
 
 __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int row, int col0,
                                                uint32_t (&r)[32]) {
@@ -227,8 +242,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int mt = tile % p.num_m_tiles;
-                const int nt = tile / p.num_m_tiles;
+                int mt, nt;
+                tile_coords(p, tile, mt, nt);
                 int n0 = 0, h0 = 0, w0 = 0;
                 if (p.conv_taps) {
                     const int row0 = mt * BM;
@@ -303,8 +318,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int mt = tile % p.num_m_tiles;
-            const int nt = tile / p.num_m_tiles;
+            int mt, nt;
+            tile_coords(p, tile, mt, nt);
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const int row = mt * BM + q * 32 + lane;
@@ -331,27 +346,256 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
     }
 }
 
+// ------------------------------------------------------------------------------------------ CTA-pair kernel
+// 256 x BN output tile per CTA PAIR (cluster of 2, tcgen05 cta_group::2).  Each CTA stages its own 128 rows of A
+// and its own BN/2 rows of B; the pair's tensor cores read both halves, so per-SM shared-memory traffic per MMA
+// (and L2->SM operand traffic) is half that of the single-CTA 128 x BN tile: 64 B/clk read + 64 B/clk TMA fill
+// at BN = 256 instead of 96 + 96.  The leader CTA (rank 0) issues every MMA; both CTAs run a TMA producer and an
+// epilogue for their own 128 accumulator rows (TMEM lanes).
+template <int BN>
+struct PairCfg {
+    static constexpr int A_BYTES = BM * BK * 2;
+    static constexpr int BH_BYTES = (BN / 2) * BK * 2;
+    static constexpr int STAGES = (BN == 256) ? 6 : 8;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int SMEM_BYTES = STAGES * (A_BYTES + BH_BYTES) + 256 + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
+                 const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                 const GemmKParams p) {
+    using Cfg = PairCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::BH_BYTES);
+    uint64_t* full = bars;               // used in the leader CTA only
+    uint64_t* empty = bars + STAGES;     // per CTA
+    uint64_t* tfull = bars + 2 * STAGES; // per CTA
+    uint64_t* tempty = tfull + 2;        // used in the leader CTA only
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA1);
+        tma_prefetch_desc(&tmB1);
+        if (p.kb2 > 0) {
+            tma_prefetch_desc(&tmA2);
+            tma_prefetch_desc(&tmB2);
+        }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 2);      // leader's arrive.expect_tx + peer's remote arrive
+            mbar_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 8);    // one arrival per epilogue warp of each CTA
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) {
+        tmem_alloc_pair(tmem_holder, Cfg::TMEM_COLS);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    const int num_m2 = (p.M + 2 * BM - 1) / (2 * BM);
+    const int total_tiles = num_m2 * p.num_n_tiles;
+    const int kb_total = p.kb1 + p.kb2;
+    const int pair_id = blockIdx.x >> 1;
+    const int num_pairs = gridDim.x >> 1;
+    GemmKParams pp = p;
+    pp.num_m_tiles = num_m2;             // tile_coords works on pair tiles
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
+                int mt2, nt;
+                tile_coords(pp, tile, mt2, nt);
+                const int row0 = mt2 * 2 * BM + (int)rank * BM;
+                int n0 = 0, h0 = 0, w0 = 0;
+                if (p.conv_taps) {
+                    const int hw = p.H * p.W;
+                    n0 = row0 / hw;
+                    const int rem = row0 - n0 * hw;
+                    h0 = rem / p.W;
+                    w0 = rem - h0 * p.W;
+                }
+                const int brow = nt * BN + (int)rank * (BN / 2);
+                for (int kb = 0; kb < kb_total; ++kb) {
+                    mbar_wait(&empty[stage], phase ^ 1u);
+                    const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), 0);
+                    if (leader)
+                        mbar_arrive_expect_tx(&full[stage], 2 * (Cfg::A_BYTES + Cfg::BH_BYTES));
+                    else
+                        mbar_arrive_cluster(full_leader);
+                    uint8_t* a_dst = sA + stage * Cfg::A_BYTES;
+                    uint8_t* b_dst = sB + stage * Cfg::BH_BYTES;
+                    if (kb < p.kb1) {
+                        if (p.conv_taps) {
+                            const int tap = kb / p.cblocks;
+                            const int cb = kb - tap * p.cblocks;
+                            tma_load_4d_pair(&tmA1, full_leader, a_dst, cb * BK, w0 + p.tap_dw[tap],
+                                             h0 + p.tap_dh[tap], n0 + p.tap_dn[tap]);
+                        } else {
+                            tma_load_2d_pair(&tmA1, full_leader, a_dst, kb * BK, row0);
+                        }
+                        tma_load_2d_pair(&tmB1, full_leader, b_dst, kb * BK, brow);
+                    } else {
+                        const int k2 = kb - p.kb1;
+                        tma_load_2d_pair(&tmA2, full_leader, a_dst, k2 * BK, row0);
+                        tma_load_2d_pair(&tmB2, full_leader, b_dst, k2 * BK, brow);
+                    }
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
+                mbar_wait(&tempty[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < kb_total; ++kb) {
+                    mbar_wait(&full[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
+                    const uint32_t b_addr = smem_u32(sB + stage * Cfg::BH_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        tc_mma_bf16_pair(d_tmem, make_desc_k_sw128(a_addr + k * 32),
+                                         make_desc_k_sw128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+                    tc_commit_pair(&empty[stage]);
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                tc_commit_pair(&tfull[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else if (warp >= 4) {
+        const int q = warp - 4;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
+            int mt2, nt;
+            tile_coords(pp, tile, mt2, nt);
+            mbar_wait(&tfull[acc], acc_phase);
+            tc_fence_after();
+            const int row = mt2 * 2 * BM + (int)rank * BM + q * 32 + lane;
+            const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                tmem_ld_32x32(t_addr + c * 32, r);
+                tmem_ld_wait();
+                epilogue_chunk(p, row, nt * BN + c * 32, r);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (leader)
+                    mbar_arrive(&tempty[acc]);
+                else
+                    mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[acc]), 0));
+            }
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
 // ------------------------------------------------------------------------------------------ host
 
+// Tile configuration: BN in {64,128,256} single-CTA (128-row tiles) or {128,256} CTA-pair (256-row tiles,
+// returned as 512 + BN).  Cost = waves x (tile rows x BN) / efficiency, efficiencies from the smem-traffic
+// model calibrated on B200.
 static int choose_bn(int M, int N, int force) {
-    if (force == 64 || force == 128 || force == 256) return force;
+    if (force == 64 || force == 128 || force == 256 || force == 512 + 128 || force == 512 + 256) return force;
     const int sms = num_sms();
-    const int mt = (M + BM - 1) / BM;
-    const int cands[3] = {256, 128, 64};
-    const double eff[3] = {1.0, 0.92, 0.62};
+    struct Cand { int code, rows, bn; double eff; };
+    static const Cand cands[5] = {{512 + 256, 256, 256, 1.00}, {512 + 128, 256, 128, 0.80}, {256, 128, 256, 0.72},
+                                  {128, 128, 128, 0.58}, {64, 128, 64, 0.36}};
+    static const bool no_pair = getenv("FD_NO_PAIR") != nullptr;
     int best = 128;
     double best_cost = 1e30;
-    for (int i = 0; i < 3; ++i) {
-        const int bn = cands[i];
-        const long long tiles = (long long)mt * ((N + bn - 1) / bn);
-        const long long waves = (tiles + sms - 1) / sms;
-        const double cost = (double)waves * bn / eff[i];
+    for (int i = no_pair ? 2 : 0; i < 5; ++i) {
+        const Cand& c = cands[i];
+        const long long tiles = (long long)((M + c.rows - 1) / c.rows) * ((N + c.bn - 1) / c.bn);
+        const int units = c.rows == 256 ? sms / 2 : sms;
+        const long long waves = (tiles + units - 1) / units;
+        const double cost = (double)waves * c.rows * c.bn / c.eff / (c.rows == 256 ? 2.0 : 1.0);
         if (cost < best_cost - 1e-9) {
             best_cost = cost;
-            best = bn;
+            best = c.code;
         }
     }
     return best;
+}
+
+template <int BN>
+static int launch_gemm_pair(const CUtensorMap& tA1, const CUtensorMap& tB1, const CUtensorMap& tA2,
+                            const CUtensorMap& tB2, const GemmKParams& p, cudaStream_t stream) {
+    using Cfg = PairCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        FD_CHECK_CUDA(cudaFuncSetAttribute(gemm_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int total = ((p.M + 2 * BM - 1) / (2 * BM)) * p.num_n_tiles;
+    int pairs = num_sms() / 2;
+    if (total < pairs) pairs = total;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<BN>, tA1, tB1, tA2, tB2, p));
+    FD_CHECK_LAUNCH();
+    return 0;
 }
 
 template <int BN>
@@ -385,7 +629,10 @@ extern "C" int fd_gemm(const FdGemmArgs* a, void* stream_) {
     FD_CHECK_ARG(!a->geglu || (a->N % 32 == 0), "fd_gemm: geglu needs N %% 32 == 0");
     FD_CHECK_ARG(!a->rowvec || a->rows_per_group > 0, "fd_gemm: rowvec needs rows_per_group");
 
-    const int BN = choose_bn(a->M, a->N, a->force_bn);
+    const int code = choose_bn(a->M, a->N, a->force_bn);
+    const bool pair = code >= 512;
+    const int BN = pair ? code - 512 : code;
+    const uint32_t b_box_rows = pair ? BN / 2 : BN;
     GemmKParams p;
     memset(&p, 0, sizeof(p));
     p.M = a->M;
@@ -451,7 +698,7 @@ extern "C" int fd_gemm(const FdGemmArgs* a, void* stream_) {
     {
         const uint64_t dims[2] = {(uint64_t)a->K1, (uint64_t)a->N};
         const uint64_t str[1] = {(uint64_t)a->ldb1 * 2};
-        const uint32_t box[2] = {(uint32_t)BK, (uint32_t)BN};
+        const uint32_t box[2] = {(uint32_t)BK, b_box_rows};
         rc = encode_tmap_bf16(&tB1, a->b1, 2, dims, str, box);
         if (rc) return rc;
     }
@@ -465,7 +712,7 @@ extern "C" int fd_gemm(const FdGemmArgs* a, void* stream_) {
         if (rc) return rc;
         const uint64_t dimsb[2] = {(uint64_t)a->K2, (uint64_t)a->N};
         const uint64_t strb[1] = {(uint64_t)a->ldb2 * 2};
-        const uint32_t boxb[2] = {(uint32_t)BK, (uint32_t)BN};
+        const uint32_t boxb[2] = {(uint32_t)BK, b_box_rows};
         rc = encode_tmap_bf16(&tB2, a->b2, 2, dimsb, strb, boxb);
         if (rc) return rc;
     } else {
@@ -475,6 +722,10 @@ extern "C" int fd_gemm(const FdGemmArgs* a, void* stream_) {
     ProfScope prof(stream, a->conv_taps > 0 ? PROF_CONV : PROF_GEMM,
                    2.0 * (double)a->M * (double)a->N *
                        ((a->conv_taps > 0 ? (double)a->conv_taps * a->C : (double)a->K1) + (double)a->K2));
+    if (pair) {
+        if (BN == 256) return launch_gemm_pair<256>(tA1, tB1, tA2, tB2, p, stream);
+        return launch_gemm_pair<128>(tA1, tB1, tA2, tB2, p, stream);
+    }
     if (BN == 256) return launch_gemm<256>(tA1, tB1, tA2, tB2, p, stream);
     if (BN == 128) return launch_gemm<128>(tA1, tB1, tA2, tB2, p, stream);
     return launch_gemm<64>(tA1, tB1, tA2, tB2, p, stream);

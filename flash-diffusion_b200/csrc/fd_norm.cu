@@ -235,10 +235,18 @@ __global__ void ln_fwd_kernel(const bf16* __restrict__ x, const float* __restric
         if (vi < nvec) {
             float o[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                float t = (v[i][j] - mean) * rstd;
-                if (gamma != nullptr) t = t * gamma[vi * 8 + j] + (beta != nullptr ? beta[vi * 8 + j] : 0.f);
-                o[j] = t;
+            for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd;
+            if (gamma != nullptr) {
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+                o[0] *= g0.x; o[1] *= g0.y; o[2] *= g0.z; o[3] *= g0.w;
+                o[4] *= g1.x; o[5] *= g1.y; o[6] *= g1.z; o[7] *= g1.w;
+                if (beta != nullptr) {
+                    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8));
+                    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + vi * 8 + 4));
+                    o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w;
+                    o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+                }
             }
             store8(yr + vi * 8, o);
         }
@@ -263,10 +271,15 @@ __global__ void ln_bwd_kernel(const bf16* __restrict__ x, const float* __restric
         if (vi < nvec) {
             load8(xr + vi * 8, xh[i]);
             load8(dr + vi * 8, dg[i]);
+            if (gamma != nullptr) {
+                const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8));
+                const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + vi * 8 + 4));
+                dg[i][0] *= g0.x; dg[i][1] *= g0.y; dg[i][2] *= g0.z; dg[i][3] *= g0.w;
+                dg[i][4] *= g1.x; dg[i][5] *= g1.y; dg[i][6] *= g1.z; dg[i][7] *= g1.w;
+            }
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 xh[i][j] = (xh[i][j] - mean) * rstd;
-                if (gamma != nullptr) dg[i][j] *= gamma[vi * 8 + j];
                 s1 += dg[i][j];
                 s2 += dg[i][j] * xh[i][j];
             }

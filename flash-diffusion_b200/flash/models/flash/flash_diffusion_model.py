@@ -85,6 +85,8 @@ class FlashDiffusion(BaseModel):
                 self.register_buffer("sqrt_alpha_cumprod", torch.sqrt(1 - teacher_noise_scheduler.sigmas ** 2))
                 self.register_buffer("sigmas", teacher_noise_scheduler.sigmas)
         # B200 options
+        self.use_cuda_graphs = True      # replay frozen-teacher evaluations from a CUDA graph (same kernels)
+        self.__dict__["_graphed"] = {}
         self.batch_cfg = True            # cond+uncond as one 2B call (output-preserving)
         self.dedupe_conditioning = True  # one conditioner pass when every ucg_rate is 0 (output-preserving)
 
@@ -140,12 +142,24 @@ class FlashDiffusion(BaseModel):
     def _ucg_is_deterministic(self):
         return self.conditioner is None or all(c.ucg_rate == 0 for c in self.conditioner.conditioners)
 
-    def _teacher_pair(self, denoiser, sample, timestep, cond, uncond, **kw):
+    def _call_frozen(self, denoiser, sample, timestep, conditioning, clone=True, **kw):
+        """Frozen-denoiser evaluation; on CUDA it is replayed from a CUDA graph (flash.b200.graphs)."""
+        if self.use_cuda_graphs and sample.is_cuda:
+            from ...b200.graphs import GraphedDenoiser
+            if GraphedDenoiser.eligible(denoiser, sample):
+                g = self.__dict__["_graphed"].get(id(denoiser))
+                if g is None:
+                    g = self.__dict__["_graphed"][id(denoiser)] = GraphedDenoiser(denoiser)
+                return g(sample, timestep, conditioning, clone=clone, **kw)
+        return denoiser(sample=sample, timestep=timestep, conditioning=conditioning, **kw)
+
+    def _teacher_pair(self, denoiser, sample, timestep, cond, uncond, clone=True, **kw):
         """eps_cond, eps_uncond of the frozen teacher; one 2B call when batching is on."""
         if self.batch_cfg and cond is not None:
             B = sample.shape[0]
-            both = denoiser(sample=torch.cat([sample, sample], dim=0), timestep=torch.cat([timestep, timestep], dim=0),
-                            conditioning=_cat_conditioning(cond, uncond), **kw)
+            both = self._call_frozen(denoiser, torch.cat([sample, sample], dim=0),
+                                     torch.cat([timestep, timestep], dim=0), _cat_conditioning(cond, uncond),
+                                     clone=clone, **kw)
             return both[:B], both[B:]
         return (denoiser(sample=sample, timestep=timestep, conditioning=cond, **kw),
                 denoiser(sample=sample, timestep=timestep, conditioning=uncond, **kw))
@@ -231,7 +245,7 @@ class FlashDiffusion(BaseModel):
             timestep = torch.tensor([t], device=x.device).repeat(B)
             x_in = sched.scale_model_input(x, t)
             eps_c, eps_u = self._teacher_pair(self.teacher_denoiser, x_in, timestep, conditioning,
-                                              unconditional_conditioning)
+                                              unconditional_conditioning, clone=not fused)
             if fused:
                 sched.fused_cfg_step(eps_c.contiguous(), eps_u.contiguous(), w, t, x, x0_prev)
             else:
@@ -300,8 +314,8 @@ class FlashDiffusion(BaseModel):
         # frozen teacher backbone -> mid-block features (reference :563-569); on the discriminator turn the
         # reference detaches the fake features (:600), so no graph is needed there at all
         with torch.set_grad_enabled(generator_turn and torch.is_grad_enabled()):
-            feats = self.disc_backbone(sample=noisy_sample, timestep=torch.cat([timesteps, timesteps], dim=0),
-                                       conditioning=cond2, return_intermediate=True)
+            feats = self._call_frozen(self.disc_backbone, noisy_sample, torch.cat([timesteps, timesteps], dim=0),
+                                      cond2, return_intermediate=True)
         f_fake, f_real = feats.chunk(2, dim=0)
         D = self.discriminator
         dev = student_output.device

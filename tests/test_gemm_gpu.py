@@ -17,7 +17,7 @@ def raw():
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (4096, 640, 640), (308, 1280, 2048),
                                    (1024, 320, 1280), (16384, 1920, 640), (4, 1280, 320), (200, 72, 200)])
-@pytest.mark.parametrize("bn", [0, 64, 128, 256])
+@pytest.mark.parametrize("bn", [0, 64, 128, 256, 512 + 128, 512 + 256])
 def test_gemm_plain(raw, M, N, K, bn):
     torch.manual_seed(M + N + K)
     a = torch.randn(M, K, device="cuda").bfloat16()
@@ -30,7 +30,8 @@ def test_gemm_plain(raw, M, N, K, bn):
     assert _rel(out32, ref) < 1e-5, _rel(out32, ref)
 
 
-def test_gemm_epilogue_and_lora(raw):
+@pytest.mark.parametrize("bn", [0, 512 + 128, 512 + 256])
+def test_gemm_epilogue_and_lora(raw, bn):
     torch.manual_seed(0)
     M, N, K, r = 1024, 640, 640, 64
     x = torch.randn(M, K, device="cuda").bfloat16()
@@ -43,7 +44,7 @@ def test_gemm_epilogue_and_lora(raw):
     ref = x.float() @ w.float().t() + t.float() @ lb.float().t() + bias + res.float() \
         + rowvec.repeat_interleave(M // 4, dim=0)
     out = raw.gemm(x, w, a2=t, b2=lb, bias=bias, residual=res, rowvec=rowvec, rows_per_group=M // 4,
-                   out_fp32=True)
+                   out_fp32=True, force_bn=bn)
     assert _rel(out, ref) < 1e-5, _rel(out, ref)
 
 
@@ -67,7 +68,8 @@ def test_gemm_geglu(raw):
 
 @pytest.mark.parametrize("NB,H,W,Cin,Cout", [(2, 32, 32, 64, 64), (1, 64, 64, 320, 320), (2, 128, 128, 64, 128),
                                              (4, 8, 8, 128, 192), (1, 16, 16, 1920, 640), (2, 32, 32, 8, 320)])
-def test_conv3x3(raw, NB, H, W, Cin, Cout):
+@pytest.mark.parametrize("bn", [0, 128, 512 + 128, 512 + 256])
+def test_conv3x3(raw, NB, H, W, Cin, Cout, bn):
     torch.manual_seed(NB + H + Cin)
     x = torch.randn(NB, Cin, H, W, device="cuda").bfloat16()
     w = (torch.randn(Cout, Cin, 3, 3, device="cuda") / (9 * Cin) ** 0.5).bfloat16()
@@ -81,5 +83,15 @@ def test_conv3x3(raw, NB, H, W, Cin, Cout):
     wp[..., :Cin] = w.permute(0, 2, 3, 1)
     wp = wp.reshape(Cout, 9 * cpad).contiguous()
     out = raw.gemm(x_nhwc, wp, bias=bias, out_fp32=True, M=NB * H * W,
-                   conv=dict(NB_in=NB, H=H, W=W, C=Cin, taps=raw.TAPS_3X3))
+                   conv=dict(NB_in=NB, H=H, W=W, C=Cin, taps=raw.TAPS_3X3), force_bn=bn)
     assert _rel(out, ref) < 3e-5, _rel(out, ref)
+
+
+def test_gemm_ragged_k(raw):
+    torch.manual_seed(5)
+    M, N, K = 640, 192, 154                      # K not a multiple of 8: row strides padded to 160
+    abuf = torch.randn(M, 160, device="cuda").bfloat16()
+    bbuf = torch.randn(N, 160, device="cuda").bfloat16()
+    a, b = abuf[:, :K], bbuf[:, :K]
+    out = raw.gemm(a, b, out_fp32=True)
+    assert _rel(out, a.float() @ b.float().t()) < 1e-5

@@ -31,8 +31,21 @@ with torch.no_grad():
     n = 5
     for _ in range(n):
         m(x, t, cond)
+    issue = (time.time() - t0) / n * 1e3
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
     wall = (time.time() - t0) / n * 1e3
-print(f"SDXL UNet fwd B={B}: {ms:.2f} ms GPU ({wall:.2f} ms wall)  -> {6.76 * B / ms:.1f} TFLOP/s "
-      f"({6.76 * B / ms / 1374.2 * 1000 * 100:.1f}% of sustained bf16 peak)")
+print(f"SDXL UNet fwd B={B}: {ms:.2f} ms GPU ({wall:.2f} ms wall, host issue {issue:.2f} ms)  -> "
+      f"{6.76 * B / ms * 1e3:.0f} TFLOP/s ({6.76 * B / ms / 1374.2 * 1000 * 100:.1f}% of sustained bf16 peak)")
+from flash.b200 import lib as fdlib
+import ctypes
+l = fdlib.load()
+l.fd_profile_enable(1)
+with torch.no_grad():
+    m(x, t, cond)
+l.fd_profile_enable(0)
+ms_, fl_, cnt_ = (ctypes.c_double * 4)(), (ctypes.c_double * 4)(), (ctypes.c_longlong * 4)()
+l.fd_profile_summary(ms_, fl_, cnt_, 4)
+for i, name in enumerate(["gemm", "conv", "attn_fwd", "attn_bwd"]):
+    if cnt_[i]:
+        print(f"  {name:9s} launches {cnt_[i]:5d}  {ms_[i]:8.2f} ms  {fl_[i] / ms_[i] / 1e9:8.1f} TFLOP/s")
