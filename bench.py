@@ -90,75 +90,94 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
-def cpu_component_times(threads, full=True):
-    """Oracle (fp32 PyTorch, same math as the reference's diffusers path) on the host cores, SDXL at B=1:
-    one teacher forward; optionally one student(LoRA) forward+backward and one GAN-backbone (down+mid, batch 2)
-    forward+backward.  Returns seconds per component."""
-    from oracle.unet import LoraConfig, SDXL_KWARGS, UNet2DConditionOracle
-    torch.set_num_threads(threads)
-    torch.manual_seed(1234)
-    with torch.device("meta"):
-        net = UNet2DConditionOracle(**SDXL_KWARGS)
-    net = net.to_empty(device="cpu")
-    with torch.no_grad():
-        for p in net.parameters():
-            p.normal_(0, 0.02) if p.dim() >= 2 else p.fill_(1.0 if p.dim() == 1 and p.numel() > 4 else 0.0)
-    x = torch.randn(1, 4, 128, 128)
-    t = torch.tensor([500.0])
-    cond = {"cond": {"crossattn": torch.randn(1, 77, 2048), "vector": torch.randn(1, 2816)}}
-    out = {}
-    net.freeze()
-    with torch.no_grad():
-        t0 = time.perf_counter()
-        net(x, t, cond)
-        out["teacher_fwd"] = time.perf_counter() - t0
-    if full:
-        net.add_adapter(LoraConfig(r=64, lora_alpha=64, init_lora_weights="gaussian",
-                                   target_modules=["to_k", "to_q", "to_v", "to_out.0"]))
-        t0 = time.perf_counter()
-        net(x, t, cond).square().mean().backward()
-        out["student_fwd_bwd"] = time.perf_counter() - t0
-        x2 = torch.cat([x, x]).requires_grad_(True)
-        cond2 = {"cond": {k: torch.cat([v, v]) for k, v in cond["cond"].items()}}
-        t0 = time.perf_counter()
-        net(x2, torch.cat([t, t]), cond2, return_intermediate=True).square().mean().backward()
-        out["gan_backbone_fwd_bwd_2"] = time.perf_counter() - t0
-    return out
+# Bounded CPU sample (a full SDXL step is ~2.5 PFLOP per batch: hours on CPU): the SDXL UNet MID BLOCK
+# (ResnetBlock2D + Transformer2D depth 10 at 1024 tokens x 1280 channels, 20 heads, ctx 77x2048 + ResnetBlock2D;
+# examples/train_flash_sdxl.py:66-118) of the ORACLE (fp32 PyTorch restatement of the reference's diffusers path) at
+# batch 1.  Its analytic cost is F_MID FLOPs; the measured CPU FLOP rate is extrapolated to the whole step with
+# the reference step structure (SURVEY.md §8d formula).
+F_MID = 797.28e9
+_CPU = {}
 
 
-def cpu_images_per_sec(c, n=20):
-    """images/s of the reference step structure from B=1 component times: per optimizer turn
-    1 student fwd + 2n teacher fwd + 3 DMD fwd + GAN backbone at 2 samples; backward once (turn 0)."""
-    tf = c["teacher_fwd"]
-    sfb = c.get("student_fwd_bwd", 3.0 * tf)
-    gfb = c.get("gan_backbone_fwd_bwd_2", 3.0 * 2 * tf * F_DM / F_FWD)
-    turn_fwd = (1 + 2 * n + 3) * tf + gfb / 3.0
-    step = 2 * turn_fwd + (sfb - tf) + gfb * 2.0 / 3.0       # + student backward + GAN backward
-    return 1.0 / step
+def cpu_threads():
+    return min(os.cpu_count() or 1, 32)
+
+
+def _cpu_mid_block(lora):
+    key = "lora" if lora else "plain"
+    if key not in _CPU:
+        from oracle.unet import LoraConfig, MidBlock, UNet2DConditionOracle  # noqa: F401
+        torch.manual_seed(1234)
+        mid = MidBlock(1280, 1280, 32, 1e-5, dict(heads=20, dim_head=64, num_layers=10, cross_attention_dim=2048,
+                                                   groups=32, use_linear_projection=True))
+        if lora:
+            UNet2DConditionOracle.add_adapter(mid, LoraConfig(r=64, lora_alpha=64, init_lora_weights="gaussian",
+                                                              target_modules=["to_k", "to_q", "to_v", "to_out.0"]))
+        else:
+            for p_ in mid.parameters():
+                p_.requires_grad = False
+        _CPU[key] = mid
+    return _CPU[key]
+
+
+def cpu_sample(backward=False):
+    """seconds for one mid-block forward (no grad) or forward+backward (LoRA) at batch 1 on the host cores."""
+    torch.set_num_threads(cpu_threads())
+    mid = _cpu_mid_block(lora=backward)
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(1, 1280, 32, 32, generator=g)
+    temb = torch.randn(1, 1280, generator=g)
+    ctx = torch.randn(1, 77, 2048, generator=g)
+    if backward:
+        x.requires_grad_(True)
+        t0 = time.perf_counter()
+        mid(x, temb, ctx).square().mean().backward()
+        return time.perf_counter() - t0
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        mid(x, temb, ctx)
+        return time.perf_counter() - t0
+
+
+def cpu_images_per_sec(t_fwd, t_fwd_bwd=None, n=20):
+    """images/s of the reference step: forward FLOPs 2[(4+2n)F + 2F_dm] at the measured forward rate,
+    backward FLOPs (F + F_dm) at the measured backward rate (fwd+bwd sample minus a forward)."""
+    rate_f = F_MID / t_fwd
+    if t_fwd_bwd is not None and t_fwd_bwd > t_fwd:
+        rate_b = 2.0 * F_MID / (t_fwd_bwd - t_fwd)        # dX + dW(LoRA) ~ 2x forward FLOPs of the sample
+    else:
+        rate_b = rate_f
+    fwd = 2 * ((4 + 2 * n) * F_FWD + 2 * F_DM)
+    bwd = 2 * (F_FWD + F_DM)
+    return 1.0 / (fwd / rate_f + bwd / rate_b)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    comps, vals = None, []
     t_all = time.perf_counter()
+    cpu_sample()                                   # build + first-touch outside the timed samples
+    t_fb = cpu_sample(backward=True)
+    t_fb = min(t_fb, cpu_sample(backward=True))
+    vals, tf = [], []
     for i in range(args.warmup + args.steps):
-        c = cpu_component_times(cores, full=(i == 0))
-        comps = {**(comps or {}), **c} if i == 0 else {**comps, "teacher_fwd": c["teacher_fwd"]}
+        t = cpu_sample()
         if i >= args.warmup:
-            vals.append(cpu_images_per_sec(comps))
+            tf.append(t)
+            vals.append(cpu_images_per_sec(t, t_fb))
     v = sum(vals) / len(vals)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * BATCH_PER_GPU / v, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config_dict(args.gpus),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "per step: one SDXL teacher forward at B=1 on all host threads (oracle, fp32); "
-                                       "student fwd+bwd and GAN-backbone fwd+bwd timed once; images/s extrapolated "
-                                       "with the reference step structure at E[n]=20",
-                             "components_s": comps},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+                             "sample": "per step: one forward of the SDXL UNet mid block (797 GFLOP: Res + Transformer2D "
+                                       "depth 10 @1024 tok x 1280 ch + Res) of the fp32 oracle at batch 1; fwd+bwd (LoRA) "
+                                       "timed twice up front; images/s extrapolated by FLOPs with the reference step "
+                                       "structure at E[n]=20 (616 TFLOP/image)",
+                             "t_fwd_s": sum(tf) / len(tf), "t_fwd_bwd_s": t_fb,
+                             "cpu_tflops_fwd": F_MID / (sum(tf) / len(tf)) / 1e12, "host_cores": os.cpu_count()},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t_all}
     print(json.dumps(line))
@@ -285,13 +304,15 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        c = cpu_component_times(cores, full=True)
-        cpu = {"value": cpu_images_per_sec(c), "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "oracle (fp32 PyTorch restatement of the reference path) at SDXL B=1 on all host threads: "
-                         "1 teacher fwd, 1 student fwd+bwd, 1 GAN-backbone fwd+bwd (2 samples); images/s extrapolated "
-                         "with the reference step structure at E[n]=20",
-               "components_s": c}
+        cpu_sample()
+        t_f = min(cpu_sample() for _ in range(3))
+        t_fb = min(cpu_sample(backward=True) for _ in range(2))
+        cpu = {"value": cpu_images_per_sec(t_f, t_fb), "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+               "sample": "fp32 oracle (PyTorch restatement of the reference's diffusers path), SDXL UNet mid block "
+                         "(797 GFLOP) at batch 1: forward x3, forward+backward(LoRA) x2; images/s extrapolated by FLOPs "
+                         "with the reference step structure at E[n]=20 (616 TFLOP/image)",
+               "t_fwd_s": t_f, "t_fwd_bwd_s": t_fb, "cpu_tflops_fwd": F_MID / t_f / 1e12,
+               "host_cores": os.cpu_count()}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -22,7 +22,7 @@ namespace fd {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;   // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: epilogue (2 per lane quarter)
 
 struct GemmKParams {
     int M, N, kb1, kb2, num_m_tiles, num_n_tiles;
@@ -38,6 +38,10 @@ struct GemmKParams {
     void* out;
     long long ldo;
     int out_fp32;
+    const float* ln_stats;
+    const float* ln_colsum;
+    float ln_inv_c, ln_eps;
+    float* rowstats_out;
 };
 
 template <int BN>
@@ -62,8 +66,40 @@ __device__ __forceinline__ void tile_coords(const GemmKParams& p, int tile, int&
     mt = g * GROUP_M + (r - nt * gm);
 }
 
+// per-row state carried across the 32-column chunks of one tile
+struct RowState {
+    float ln_mean, ln_rstd;   // LayerNorm fold inputs for this row
+    float s1, s2;             // running (sum, sum of squares) of the stored outputs (rowstats_out)
+};
+
+__device__ __forceinline__ void row_state_init(const GemmKParams& p, int row, RowState& rs) {
+    rs.s1 = rs.s2 = 0.f;
+    rs.ln_mean = 0.f;
+    rs.ln_rstd = 1.f;
+    if (p.ln_stats != nullptr && row < p.M) {
+        const float2 st = *reinterpret_cast<const float2*>(p.ln_stats + 2 * (long long)row);
+        const float mean = st.x * p.ln_inv_c;
+        const float var = fmaxf(st.y * p.ln_inv_c - mean * mean, 0.f);
+        rs.ln_mean = mean;
+        rs.ln_rstd = rsqrtf(var + p.ln_eps);
+    }
+}
+
+__device__ __forceinline__ void row_state_flush(const GemmKParams& p, int row, const RowState& rs) {
+    if (p.rowstats_out != nullptr && row < p.M) {
+        atomicAdd(p.rowstats_out + 2 * (long long)row, rs.s1);
+        atomicAdd(p.rowstats_out + 2 * (long long)row + 1, rs.s2);
+    }
+}
+
+__device__ __forceinline__ void stats_of_bf16x2(uint32_t u, RowState& rs) {
+    const float2 f = unpack_bf16x2(u);
+    rs.s1 += f.x + f.y;
+    rs.s2 += f.x * f.x + f.y * f.y;
+}
+
 __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int row, int col0,
-                                               uint32_t (&r)[32]) {
+                                               uint32_t (&r)[32], RowState& rs) {
     // r holds acc[row, col0 .. col0+31] as fp32 bit patterns
     const bool row_ok = row < p.M;
     const int N = p.N;
@@ -72,6 +108,26 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int row, in
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+
+    if (p.ln_stats != nullptr) {
+        // LayerNorm(x) W^T = rstd * (x W'^T - mean * colsum(W'))
+        const float nm = -rs.ln_mean;
+        if (full) {
+            const float4* c4 = reinterpret_cast<const float4*>(p.ln_colsum + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 c = __ldg(c4 + j);
+                v[4 * j + 0] = rs.ln_rstd * fmaf(nm, c.x, v[4 * j + 0]);
+                v[4 * j + 1] = rs.ln_rstd * fmaf(nm, c.y, v[4 * j + 1]);
+                v[4 * j + 2] = rs.ln_rstd * fmaf(nm, c.z, v[4 * j + 2]);
+                v[4 * j + 3] = rs.ln_rstd * fmaf(nm, c.w, v[4 * j + 3]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (col0 + j < N) v[j] = rs.ln_rstd * fmaf(nm, __ldg(p.ln_colsum + col0 + j), v[j]);
+        }
+    }
 
     if (p.bias != nullptr) {
         if (full) {
@@ -135,9 +191,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int row, in
         } else {
             uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + oc0);
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-                o4[j] = make_uint4(pack_bf16x2(o[8 * j], o[8 * j + 1]), pack_bf16x2(o[8 * j + 2], o[8 * j + 3]),
-                                   pack_bf16x2(o[8 * j + 4], o[8 * j + 5]), pack_bf16x2(o[8 * j + 6], o[8 * j + 7]));
+            for (int j = 0; j < 2; ++j) {
+                const uint4 u = make_uint4(pack_bf16x2(o[8 * j], o[8 * j + 1]), pack_bf16x2(o[8 * j + 2], o[8 * j + 3]),
+                                           pack_bf16x2(o[8 * j + 4], o[8 * j + 5]), pack_bf16x2(o[8 * j + 6], o[8 * j + 7]));
+                o4[j] = u;
+                if (p.rowstats_out != nullptr) {
+                    stats_of_bf16x2(u.x, rs); stats_of_bf16x2(u.y, rs); stats_of_bf16x2(u.z, rs); stats_of_bf16x2(u.w, rs);
+                }
+            }
         }
         return;
     }
@@ -163,9 +224,14 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int row, in
         } else {
             uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + col0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                o4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                   pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+            for (int j = 0; j < 4; ++j) {
+                const uint4 u = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                           pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+                o4[j] = u;
+                if (p.rowstats_out != nullptr) {
+                    stats_of_bf16x2(u.x, rs); stats_of_bf16x2(u.y, rs); stats_of_bf16x2(u.z, rs); stats_of_bf16x2(u.w, rs);
+                }
+            }
         }
     } else {
 #pragma unroll
@@ -176,8 +242,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int row, in
                     x += __bfloat162float(p.residual[(long long)row * p.ldr + col0 + j]);
                 if (p.out_fp32)
                     reinterpret_cast<float*>(p.out)[(long long)row * p.ldo + col0 + j] = x;
-                else
-                    reinterpret_cast<bf16*>(p.out)[(long long)row * p.ldo + col0 + j] = __float2bfloat16(x);
+                else {
+                    const bf16 xb = __float2bfloat16(x);
+                    reinterpret_cast<bf16*>(p.out)[(long long)row * p.ldo + col0 + j] = xb;
+                    const float xf = __bfloat162float(xb);
+                    rs.s1 += xf;
+                    rs.s2 += xf * xf;
+                }
             }
         }
     }
@@ -221,7 +292,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], 128);
+            mbar_init(&tempty[a], 256);
         }
         fence_barrier_init();
     }
@@ -314,7 +385,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
             }
         }
     } else if (warp >= 4) {
-        const int q = warp - 4;  // TMEM lane quarter == warp_id % 4
+        const int q = (warp - 4) & 3;      // TMEM lane quarter == warp_id % 4
+        const int half = (warp - 4) >> 2;  // which half of the tile's columns this warp drains
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -324,13 +396,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
             tc_fence_after();
             const int row = mt * BM + q * 32 + lane;
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+            RowState rs;
+            row_state_init(p, row, rs);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
                 uint32_t r[32];
                 tmem_ld_32x32(t_addr + c * 32, r);
                 tmem_ld_wait();
-                epilogue_chunk(p, row, nt * BN + c * 32, r);
+                epilogue_chunk(p, row, nt * BN + c * 32, r, rs);
             }
+            row_state_flush(p, row, rs);
             tc_fence_before();
             mbar_arrive(&tempty[acc]);
             acc ^= 1;
@@ -400,7 +475,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(&tfull[a], 1);
-            mbar_init(&tempty[a], 8);    // one arrival per epilogue warp of each CTA
+            mbar_init(&tempty[a], 16);   // one arrival per epilogue warp (8) of each CTA
         }
         fence_barrier_init();
     }
@@ -501,7 +576,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
             }
         }
     } else if (warp >= 4) {
-        const int q = warp - 4;
+        const int q = (warp - 4) & 3;
+        const int half = (warp - 4) >> 2;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
@@ -511,13 +587,16 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
             tc_fence_after();
             const int row = mt2 * 2 * BM + (int)rank * BM + q * 32 + lane;
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+            RowState rs;
+            row_state_init(p, row, rs);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
+            for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
                 uint32_t r[32];
                 tmem_ld_32x32(t_addr + c * 32, r);
                 tmem_ld_wait();
-                epilogue_chunk(p, row, nt * BN + c * 32, r);
+                epilogue_chunk(p, row, nt * BN + c * 32, r, rs);
             }
+            row_state_flush(p, row, rs);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -649,6 +728,14 @@ extern "C" int fd_gemm(const FdGemmArgs* a, void* stream_) {
     p.out = a->out;
     p.ldo = a->ldo;
     p.out_fp32 = a->out_fp32;
+    p.ln_stats = a->ln_stats;
+    p.ln_colsum = a->ln_colsum;
+    p.ln_inv_c = a->ln_inv_c;
+    p.ln_eps = a->ln_eps;
+    p.rowstats_out = a->rowstats_out;
+    FD_CHECK_ARG(!a->ln_stats || (a->ln_colsum && a->K2 == 0), "fd_gemm: LayerNorm fold needs ln_colsum and no K2 segment");
+    FD_CHECK_ARG(!a->rowstats_out || !a->out_fp32, "fd_gemm: rowstats_out needs a bf16 output");
+    if (a->rowstats_out) FD_CHECK_CUDA(cudaMemsetAsync(a->rowstats_out, 0, sizeof(float) * 2 * (size_t)a->M, stream));
 
     CUtensorMap tA1, tB1, tA2, tB2;
     int rc;

@@ -32,6 +32,8 @@ class FdGemmArgs(Structure):
         ("residual", c_void_p), ("ldr", c_int64),
         ("out", c_void_p), ("ldo", c_int64), ("out_fp32", c_int32),
         ("force_bn", c_int32),
+        ("ln_stats", c_void_p), ("ln_colsum", c_void_p), ("ln_inv_c", c_float), ("ln_eps", c_float),
+        ("rowstats_out", c_void_p),
     ]
 
 

@@ -338,6 +338,26 @@ class LinearPack:
             return raw.cast_scale(w.t().contiguous(), 1.0)
         return self.cache.get(("t", len(self.bases), self.geglu), [b.weight for b in self.bases], build)
 
+    def pack_ln(self, norm):
+        """LayerNorm folded into this GEMM: B = W * gamma (bf16), colsum_n = sum_k bf16(W*gamma)[n,k] (what the tensor
+        core really multiplies), bias' = b + W beta.  See fd_gemm (include/flashb200.h)."""
+        def build():
+            w = torch.cat([self._w2d(b).float() for b in self.bases], dim=0)
+            bs = [b.bias for b in self.bases]
+            bias = torch.cat([x.detach().float() if x is not None else torch.zeros(b.weight.shape[0], device=w.device)
+                              for x, b in zip(bs, self.bases)])
+            gamma, beta = norm.weight.detach().float(), norm.bias.detach().float()
+            bias = bias + w @ beta
+            wg = w * gamma[None, :]
+            if self.geglu:
+                wp, bp = pack_geglu(wg, bias)
+            else:
+                wp, bp = raw.cast_scale(wg.contiguous(), 1.0), bias.contiguous()
+            return {"w": wp, "b": bp, "colsum": wp.float().sum(dim=1).contiguous()}
+        params = [b.weight for b in self.bases] + [b.bias for b in self.bases if b.bias is not None] + \
+                 [norm.weight, norm.bias]
+        return self.cache.get(("ln", len(self.bases), self.geglu), params, build)
+
     # LoRA: T = x [A_1;..;A_n]^T  (M x n*r);  y += T @ blockdiag(s B_i)^T
     def lora_params(self):
         ps = []
@@ -429,11 +449,31 @@ def _lora_weight_grads(pack, lp, x, t, dy, dt):
     return grads
 
 
-def linear(x, pack: LinearPack, residual=None):
+def linear(x, pack: LinearPack, residual=None, want_stats=None):
+    """y = x W^T + b (+LoRA) (+residual).  want_stats None: return y.  True/False: return (y, stats) where stats are
+    the [M,2] row statistics of y (fused into the GEMM epilogue) when requested and the no-grad, LoRA-free path is
+    taken, else None."""
     lora_params = pack.lora_params() if pack.has_lora else []
     if _grad_on(x, residual, *lora_params):
-        return _LinearFn.apply(x, residual, pack, *lora_params)
-    return _linear_fwd_raw(x, pack, residual)[0]
+        y = _LinearFn.apply(x, residual, pack, *lora_params)
+        return y if want_stats is None else (y, None)
+    if want_stats and not pack.has_lora:
+        p = pack.pack()
+        stats = torch.empty((x.shape[0], 2), device=x.device, dtype=torch.float32)
+        return raw.gemm(x, p["w"], bias=p["b"], residual=residual, rowstats=stats), stats
+    y = _linear_fwd_raw(x, pack, residual)[0]
+    return y if want_stats is None else (y, None)
+
+
+def ln_foldable(x, stats, pack: LinearPack):
+    return stats is not None and not pack.has_lora and not _grad_on(x)
+
+
+def linear_ln(x, stats, norm, pack: LinearPack):
+    """LayerNorm(x) W^T + b with the LayerNorm folded into the GEMM epilogue (no LayerNorm pass over memory).
+    `stats` are the row sums produced by the GEMM that wrote x."""
+    p = pack.pack_ln(norm)
+    return raw.gemm(x, p["w"], bias=p["b"], geglu=pack.geglu, ln=(stats, p["colsum"], x.shape[1], norm.eps))
 
 
 class _GegluFn(torch.autograd.Function):

@@ -26,7 +26,7 @@ def _req(t, dtype, name):
 
 
 def gemm(a1, b1, *, a2=None, b2=None, bias=None, rowvec=None, rows_per_group=0, geglu=False,
-         residual=None, out=None, out_fp32=False, conv=None, M=None, force_bn=0):
+         residual=None, out=None, out_fp32=False, conv=None, M=None, force_bn=0, ln=None, rowstats=None):
     """acc = a1 @ b1.T (+ a2 @ b2.T) with the fused epilogue of fd_gemm (include/flashb200.h).
 
     a1: [M, K1] bf16 (or, with conv=dict(NB_in,H,W,C,taps), an NHWC tensor), b1: [N, K1] bf16.
@@ -74,6 +74,15 @@ def gemm(a1, b1, *, a2=None, b2=None, bias=None, rowvec=None, rows_per_group=0, 
         args.residual, args.ldr = ptr(residual), residual.stride(0)
     args.out, args.ldo, args.out_fp32 = ptr(out), out.stride(0), 1 if out_fp32 else 0
     args.force_bn = force_bn
+    if ln is not None:
+        # LayerNorm fold: ln = (row_stats [M,2] fp32 raw sums, colsum [N] fp32, channels C, eps)
+        st, colsum, C, eps = ln
+        assert st.dtype == torch.float32 and st.shape == (M, 2) and st.is_contiguous()
+        assert colsum.dtype == torch.float32 and colsum.numel() == N and colsum.is_contiguous()
+        args.ln_stats, args.ln_colsum, args.ln_inv_c, args.ln_eps = ptr(st), ptr(colsum), 1.0 / C, eps
+    if rowstats is not None:
+        assert rowstats.dtype == torch.float32 and rowstats.shape == (M, 2) and rowstats.is_contiguous()
+        args.rowstats_out = ptr(rowstats)
     check(lib.fd_gemm(byref(args), stream_ptr()), "fd_gemm")
     return out
 

@@ -304,30 +304,43 @@ class DiffusersUNet2DCondWrapper(nn.Module):
             return ops.conv3x3(h, geom, c2, x2=x)
         return ops.conv3x3(h, geom, c2, residual=x)
 
-    def _attention(self, a, x, ctx, B, residual):
+    def _attention(self, a, x, ctx, B, residual, norm, stats):
+        """x: the residual stream (un-normalised), `norm` its LayerNorm.  When the producer GEMM left row statistics
+        (`stats`) and no gradient / LoRA is involved, the LayerNorm is folded into the projection GEMM; otherwise the
+        LayerNorm kernel runs.  Returns (new residual stream, its row statistics or None)."""
         H = a.heads
         if a.dim_head != 64:
             raise NotImplementedError(f"attention kernel is built for head dim 64 (got {a.dim_head})")
         inner = H * 64
-        if not a.is_cross:
-            qkv = ops.linear(x, self._pack(("qkv", id(a)), lambda: LinearPack([a.to_q, a.to_k, a.to_v])))
-            o = ops.attention_self(qkv.view(B, -1, 3 * inner), H).view(-1, inner)
+        first = self._pack(("qkv" if not a.is_cross else "q", id(a)),
+                           lambda: LinearPack([a.to_q, a.to_k, a.to_v] if not a.is_cross else a.to_q))
+        if ops.ln_foldable(x, stats, first):
+            proj = ops.linear_ln(x, stats, norm, first)
         else:
-            q = ops.linear(x, self._pack(("q", id(a)), lambda: LinearPack(a.to_q))).view(B, -1, inner)
+            proj = ops.linear(ops.layer_norm(x, norm), first)
+        if not a.is_cross:
+            o = ops.attention_self(proj.view(B, -1, 3 * inner), H).view(-1, inner)
+        else:
             kv = ops.linear(ctx, self._pack(("kv", id(a)), lambda: LinearPack([a.to_k, a.to_v])))
-            o = ops.attention_cross(q, kv.view(B, -1, 2 * inner), H).view(-1, inner)
-        return ops.linear(o, self._pack(("o", id(a)), lambda: LinearPack(a.to_out[0])), residual=residual)
+            o = ops.attention_cross(proj.view(B, -1, inner), kv.view(B, -1, 2 * inner), H).view(-1, inner)
+        return ops.linear(o, self._pack(("o", id(a)), lambda: LinearPack(a.to_out[0])), residual=residual,
+                          want_stats=True)
 
     def _transformer(self, t, x, geom, ctx):
         B = geom[0]
         h = ops.group_norm(x, geom, t.norm, silu=False)
-        h = ops.linear(h, self._pack(("pi", id(t)), lambda: LinearPack(t.proj_in)))
-        for blk in t.transformer_blocks:
-            h = self._attention(blk.attn1, ops.layer_norm(h, blk.norm1), None, B, residual=h)
-            h = self._attention(blk.attn2, ops.layer_norm(h, blk.norm2), ctx, B, residual=h)
-            g = ops.geglu(ops.layer_norm(h, blk.norm3),
-                          self._pack(("ff1", id(blk)), lambda: LinearPack(blk.ff.net[0].proj, geglu=True)))
-            h = ops.linear(g, self._pack(("ff2", id(blk)), lambda: LinearPack(blk.ff.net[2])), residual=h)
+        h, st = ops.linear(h, self._pack(("pi", id(t)), lambda: LinearPack(t.proj_in)), want_stats=True)
+        n = len(t.transformer_blocks)
+        for i, blk in enumerate(t.transformer_blocks):
+            h, st = self._attention(blk.attn1, h, None, B, h, blk.norm1, st)
+            h, st = self._attention(blk.attn2, h, ctx, B, h, blk.norm2, st)
+            ff1 = self._pack(("ff1", id(blk)), lambda: LinearPack(blk.ff.net[0].proj, geglu=True))
+            if ops.ln_foldable(h, st, ff1):
+                g = ops.linear_ln(h, st, blk.norm3, ff1)
+            else:
+                g = ops.geglu(ops.layer_norm(h, blk.norm3), ff1)
+            h, st = ops.linear(g, self._pack(("ff2", id(blk)), lambda: LinearPack(blk.ff.net[2])), residual=h,
+                               want_stats=(i + 1 < n))
         return ops.linear(h, self._pack(("po", id(t)), lambda: LinearPack(t.proj_out)), residual=x)
 
     def forward(self, sample: torch.Tensor, timestep: Union[torch.Tensor, float, int],

@@ -43,11 +43,17 @@ int fd_profile_summary(double* ms, double* flops, long long* counts, int ncat);
  * fd_gemm — tcgen05/TMA GEMM with an optional second K segment and a fused epilogue.
  *
  *   acc[M,N] = A1[M,K1] * B1[N,K1]^T  (+ A2[M,K2] * B2[N,K2]^T)          (bf16 in, fp32 acc)
+ *   LayerNorm fold (optional, ln_stats != NULL): the A operand is the RAW residual stream x and B is W*gamma;
+ *     acc <- rstd[row] * (acc - mean[row] * ln_colsum[col])     with (mean, rstd) from ln_stats[row] =
+ *     (sum x, sum x^2) over ln_inv_c^-1 channels — i.e. LayerNorm(x) W^T without a LayerNorm pass over memory
+ *     (bias must then hold b + W beta).  UPSTREAM BasicTransformerBlock.norm1/2/3 -> to_q/k/v, ff.net.0.proj.
  *   acc += bias[N]                      (fp32, optional)
  *   acc += rowvec[row / rows_per_group, :N] (fp32, row stride ldrv; the ResnetBlock time-embedding add)
  *   geglu: out[:, 16j+i] = acc[:, 32j+i] * gelu(acc[:, 32j+16+i])   (weights packed interleaved)
  *   out (+)= residual[M, Nout]          (bf16, optional)
  *   out -> bf16 (or fp32 when out_fp32)
+ *   rowstats_out (optional): [M,2] fp32 += (sum, sum of squares) of the stored (bf16-rounded) output row — the
+ *     statistics the NEXT LayerNorm-folded GEMM consumes; zeroed by the call.
  *
  * Segment 2 is how LoRA (peft `y = base(x) + (x A^T) B^T * alpha/r`; reference call sites
  * examples/train_flash_sdxl.py:210-217) is folded in: A2 = x A^T [M,r], B2 = s*B [N,r]; it is also
@@ -76,7 +82,10 @@ typedef struct {
     int32_t geglu;
     const void* residual; int64_t ldr;
     void* out; int64_t ldo; int32_t out_fp32;
-    int32_t force_bn;   /* 0 = heuristic, else 64/128/256 */
+    int32_t force_bn;   /* 0 = heuristic, else 64/128/256 single-CTA, 512+128 / 512+256 CTA-pair */
+    /* LayerNorm fold */
+    const float* ln_stats; const float* ln_colsum; float ln_inv_c; float ln_eps;
+    float* rowstats_out;
 } FdGemmArgs;
 int fd_gemm(const FdGemmArgs* args, void* stream);
 

@@ -95,3 +95,34 @@ def test_gemm_ragged_k(raw):
     a, b = abuf[:, :K], bbuf[:, :K]
     out = raw.gemm(a, b, out_fp32=True)
     assert _rel(out, a.float() @ b.float().t()) < 1e-5
+
+
+@pytest.mark.parametrize("bn", [0, 128, 512 + 256])
+@pytest.mark.parametrize("geglu", [False, True])
+def test_gemm_layernorm_fold_and_rowstats(raw, bn, geglu):
+    """LayerNorm(x) W^T + b via the folded epilogue == explicit LayerNorm then GEMM; producer row statistics."""
+    torch.manual_seed(7)
+    M, C, N = 1024, 640, 1280
+    h0 = torch.randn(M, C, device="cuda").bfloat16()
+    w0 = (torch.randn(C, C, device="cuda") / C ** 0.5).bfloat16()
+    res = (torch.randn(M, C, device="cuda") * 2 + 0.7).bfloat16()
+    stats = torch.empty(M, 2, device="cuda")
+    x = raw.gemm(h0, w0, residual=res, rowstats=stats, force_bn=bn)          # producer: residual stream + its stats
+    xf = x.float()
+    assert _rel(stats[:, 0], xf.sum(1)) < 1e-4 and _rel(stats[:, 1], (xf * xf).sum(1)) < 1e-4
+    gamma, beta = torch.randn(C, device="cuda") * 0.5 + 1.0, torch.randn(C, device="cuda") * 0.3
+    w = torch.randn(N, C, device="cuda") / C ** 0.5
+    b = torch.randn(N, device="cuda")
+    ref = torch.nn.functional.layer_norm(xf, (C,), gamma, beta, 1e-5) @ w.t() + b
+    wg = (w * gamma[None, :])
+    bias = b + w @ beta
+    if geglu:
+        val, gate = ref.chunk(2, dim=-1)
+        ref = val * torch.nn.functional.gelu(gate)
+        wv, wgt = wg[:N // 2].view(-1, 16, C), wg[N // 2:].view(-1, 16, C)
+        wg = torch.stack([wv, wgt], dim=1).reshape(N, C)
+        bias = torch.stack([bias[:N // 2].view(-1, 16), bias[N // 2:].view(-1, 16)], dim=1).reshape(-1)
+    wp = wg.contiguous().bfloat16()
+    colsum = wp.float().sum(1).contiguous()
+    out = raw.gemm(x, wp, bias=bias.contiguous(), geglu=geglu, ln=(stats, colsum, C, 1e-5), out_fp32=True, force_bn=bn)
+    assert _rel(out, ref) < 6e-3, _rel(out, ref)
