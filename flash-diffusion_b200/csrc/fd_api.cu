@@ -93,16 +93,20 @@ struct ProfRec {
     cudaEvent_t e0, e1;
     int cat;
     double work;
+    int M, N, K;
 };
 static bool g_prof = false;
 static std::vector<ProfRec> g_recs;
 static std::mutex g_prof_mu;
 
-ProfScope::ProfScope(cudaStream_t s, int cat, double work) : stream(s), slot(-1) {
+ProfScope::ProfScope(cudaStream_t s, int cat, double work, int M, int N, int K) : stream(s), slot(-1) {
     if (!g_prof) return;
     ProfRec r;
     r.cat = cat;
     r.work = work;
+    r.M = M;
+    r.N = N;
+    r.K = K;
     if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
     cudaEventRecord(r.e0, s);
     std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -139,6 +143,21 @@ long long fd_launch_count(void) { return fd::g_launches.load(); }
 void fd_profile_enable(int on) {
     std::lock_guard<std::mutex> lk(fd::g_prof_mu);
     fd::g_prof = on != 0;
+}
+
+int fd_profile_dump(const char* path) {
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(fd::g_prof_mu);
+    FILE* f = fopen(path, "w");
+    if (!f) return -1;
+    fprintf(f, "cat,M,N,K,ms,flops\n");
+    for (auto& r : fd::g_recs) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, r.e0, r.e1) == cudaSuccess)
+            fprintf(f, "%d,%d,%d,%d,%.6f,%.0f\n", r.cat, r.M, r.N, r.K, t, r.work);
+    }
+    fclose(f);
+    return 0;
 }
 
 int fd_profile_summary(double* ms, double* work, long long* counts, int ncat) {

@@ -431,8 +431,8 @@ template <int BN>
 struct PairCfg {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int BH_BYTES = (BN / 2) * BK * 2;
-    static constexpr int STAGES = (BN == 256) ? 6 : 8;
-    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int STAGES = (BN == 256) ? 6 : (BN == 160 ? 7 : 8);
+    static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;   // power of two >= 2 accumulator stages
     static constexpr int SMEM_BYTES = STAGES * (A_BYTES + BH_BYTES) + 256 + 1024;
 };
 
@@ -589,8 +589,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
             RowState rs;
             row_state_init(p, row, rs);
+            constexpr int NCH = BN / 32, SPLIT = (NCH + 1) / 2;
 #pragma unroll 1
-            for (int c = half * (BN / 64); c < (half + 1) * (BN / 64); ++c) {
+            for (int c = half ? SPLIT : 0; c < (half ? NCH : SPLIT); ++c) {
                 uint32_t r[32];
                 tmem_ld_32x32(t_addr + c * 32, r);
                 tmem_ld_wait();
@@ -624,15 +625,17 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
 // returned as 512 + BN).  Cost = waves x (tile rows x BN) / efficiency, efficiencies from the smem-traffic
 // model calibrated on B200.
 static int choose_bn(int M, int N, int force) {
-    if (force == 64 || force == 128 || force == 256 || force == 512 + 128 || force == 512 + 256) return force;
+    if (force == 64 || force == 128 || force == 256 || force == 512 + 128 || force == 512 + 160 ||
+        force == 512 + 256)
+        return force;
     const int sms = num_sms();
     struct Cand { int code, rows, bn; double eff; };
-    static const Cand cands[5] = {{512 + 256, 256, 256, 1.00}, {512 + 128, 256, 128, 0.80}, {256, 128, 256, 0.72},
-                                  {128, 128, 128, 0.58}, {64, 128, 64, 0.36}};
+    static const Cand cands[6] = {{512 + 256, 256, 256, 1.00}, {512 + 160, 256, 160, 0.80}, {512 + 128, 256, 128, 0.80},
+                                  {256, 128, 256, 0.72}, {128, 128, 128, 0.58}, {64, 128, 64, 0.36}};
     static const bool no_pair = getenv("FD_NO_PAIR") != nullptr;
     int best = 128;
     double best_cost = 1e30;
-    for (int i = no_pair ? 2 : 0; i < 5; ++i) {
+    for (int i = no_pair ? 3 : 0; i < 6; ++i) {
         const Cand& c = cands[i];
         const long long tiles = (long long)((M + c.rows - 1) / c.rows) * ((N + c.bn - 1) / c.bn);
         const int units = c.rows == 256 ? sms / 2 : sms;
@@ -808,9 +811,11 @@ extern "C" int fd_gemm(const FdGemmArgs* a, void* stream_) {
     }
     ProfScope prof(stream, a->conv_taps > 0 ? PROF_CONV : PROF_GEMM,
                    2.0 * (double)a->M * (double)a->N *
-                       ((a->conv_taps > 0 ? (double)a->conv_taps * a->C : (double)a->K1) + (double)a->K2));
+                       ((a->conv_taps > 0 ? (double)a->conv_taps * a->C : (double)a->K1) + (double)a->K2),
+                   a->M, a->N, a->K1 + a->K2);
     if (pair) {
         if (BN == 256) return launch_gemm_pair<256>(tA1, tB1, tA2, tB2, p, stream);
+        if (BN == 160) return launch_gemm_pair<160>(tA1, tB1, tA2, tB2, p, stream);
         return launch_gemm_pair<128>(tA1, tB1, tA2, tB2, p, stream);
     }
     if (BN == 256) return launch_gemm<256>(tA1, tB1, tA2, tB2, p, stream);

@@ -54,7 +54,7 @@ enum ProfCat { PROF_GEMM = 0, PROF_CONV = 1, PROF_ATTN_FWD = 2, PROF_ATTN_BWD = 
 struct ProfScope {
     cudaStream_t stream;
     int slot;
-    ProfScope(cudaStream_t s, int cat, double work);   // work = algorithmic FLOPs of the launch
+    ProfScope(cudaStream_t s, int cat, double work, int M = 0, int N = 0, int K = 0);   // work = algorithmic FLOPs
     ~ProfScope();
 };
 

@@ -38,6 +38,8 @@ long long fd_launch_count(void);
  * and clears the records. */
 void fd_profile_enable(int on);
 int fd_profile_summary(double* ms, double* flops, long long* counts, int ncat);
+/* writes one CSV row per recorded launch (cat,M,N,K,ms,flops) WITHOUT clearing the records */
+int fd_profile_dump(const char* path);
 
 /* ------------------------------------------------------------------------------------------
  * fd_gemm — tcgen05/TMA GEMM with an optional second K segment and a fused epilogue.

@@ -17,7 +17,7 @@ def raw():
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (4096, 640, 640), (308, 1280, 2048),
                                    (1024, 320, 1280), (16384, 1920, 640), (4, 1280, 320), (200, 72, 200)])
-@pytest.mark.parametrize("bn", [0, 64, 128, 256, 512 + 128, 512 + 256])
+@pytest.mark.parametrize("bn", [0, 64, 128, 256, 512 + 128, 512 + 160, 512 + 256])
 def test_gemm_plain(raw, M, N, K, bn):
     torch.manual_seed(M + N + K)
     a = torch.randn(M, K, device="cuda").bfloat16()
@@ -30,7 +30,7 @@ def test_gemm_plain(raw, M, N, K, bn):
     assert _rel(out32, ref) < 1e-5, _rel(out32, ref)
 
 
-@pytest.mark.parametrize("bn", [0, 512 + 128, 512 + 256])
+@pytest.mark.parametrize("bn", [0, 512 + 128, 512 + 160, 512 + 256])
 def test_gemm_epilogue_and_lora(raw, bn):
     torch.manual_seed(0)
     M, N, K, r = 1024, 640, 640, 64
@@ -68,7 +68,7 @@ def test_gemm_geglu(raw):
 
 @pytest.mark.parametrize("NB,H,W,Cin,Cout", [(2, 32, 32, 64, 64), (1, 64, 64, 320, 320), (2, 128, 128, 64, 128),
                                              (4, 8, 8, 128, 192), (1, 16, 16, 1920, 640), (2, 32, 32, 8, 320)])
-@pytest.mark.parametrize("bn", [0, 128, 512 + 128, 512 + 256])
+@pytest.mark.parametrize("bn", [0, 128, 512 + 128, 512 + 160, 512 + 256])
 def test_conv3x3(raw, NB, H, W, Cin, Cout, bn):
     torch.manual_seed(NB + H + Cin)
     x = torch.randn(NB, Cin, H, W, device="cuda").bfloat16()
@@ -97,7 +97,7 @@ def test_gemm_ragged_k(raw):
     assert _rel(out, a.float() @ b.float().t()) < 1e-5
 
 
-@pytest.mark.parametrize("bn", [0, 128, 512 + 256])
+@pytest.mark.parametrize("bn", [0, 128, 512 + 160, 512 + 256])
 @pytest.mark.parametrize("geglu", [False, True])
 def test_gemm_layernorm_fold_and_rowstats(raw, bn, geglu):
     """LayerNorm(x) W^T + b via the folded epilogue == explicit LayerNorm then GEMM; producer row statistics."""

@@ -8,9 +8,9 @@ import torch
 
 from flash.b200 import raw
 
-SHAPES = [(32768, 640, 640), (32768, 1920, 640), (8192, 1280, 1280), (8192, 3840, 1280), (8192, 10240, 1280),
+SHAPES = [(131072, 320, 2880), (32768, 640, 640), (32768, 1920, 640), (8192, 1280, 1280), (8192, 3840, 1280), (8192, 10240, 1280),
           (8192, 1280, 5120), (32768, 5120, 640), (32768, 640, 2560), (16384, 2560, 1280)]
-CFGS = [0, 64, 128, 256, 512 + 128, 512 + 256]
+CFGS = [0, 256, 512 + 128, 512 + 160, 512 + 256]
 only = [int(a) for a in sys.argv[1:]]
 if only:
     CFGS = only

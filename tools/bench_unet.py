@@ -44,6 +44,8 @@ l.fd_profile_enable(1)
 with torch.no_grad():
     m(x, t, cond)
 l.fd_profile_enable(0)
+os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+l.fd_profile_dump(os.path.join(ROOT, 'gpurun_out', f'gemm_shapes_B{B}.csv').encode())
 ms_, fl_, cnt_ = (ctypes.c_double * 4)(), (ctypes.c_double * 4)(), (ctypes.c_longlong * 4)()
 l.fd_profile_summary(ms_, fl_, cnt_, 4)
 for i, name in enumerate(["gemm", "conv", "attn_fwd", "attn_bwd"]):
