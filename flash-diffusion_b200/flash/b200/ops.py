@@ -300,26 +300,49 @@ class LinearPack:
     """Kernel-side view of one or several nn.Linear (or LoRA-wrapped Linear) sharing an input; several
     are fused along N (self-attention q/k/v, cross-attention k/v)."""
 
-    def __init__(self, layers, geglu=False):
+    def __init__(self, layers, geglu=False, head_pad=None, pad_cols=False):
+        """head_pad = (H, d, dp): zero-pad every head from d to dp channels — output rows of q/k/v projections
+        (pad_cols=False) or input columns of the attention out-projection (pad_cols=True) — so that the attention
+        kernel sees a head dim that is a multiple of 16 (softmax(QK^T)V is unchanged by zero channels)."""
         self.layers = layers if isinstance(layers, (list, tuple)) else [layers]
         self.geglu = geglu
+        self.head_pad, self.pad_cols = head_pad, pad_cols
         self.bases = [getattr(l, "base_layer", l) for l in self.layers]
         self.loras = [l if hasattr(l, "base_layer") else None for l in self.layers]
         self.has_lora = any(l is not None for l in self.loras)
         self.cache = cache_of(self.bases[0])
         self.N = sum(b.weight.shape[0] for b in self.bases)
         self.K = self.bases[0].weight.shape[1]
+        if head_pad is not None and head_pad[1] != head_pad[2] and (self.has_lora or geglu):
+            raise NotImplementedError("head padding with LoRA / GEGLU packs")
 
     def _w2d(self, b):
-        return b.weight.detach().reshape(b.weight.shape[0], -1)       # Linear or 1x1 Conv2d
+        w = b.weight.detach().reshape(b.weight.shape[0], -1)          # Linear or 1x1 Conv2d
+        if self.head_pad is not None and self.head_pad[1] != self.head_pad[2]:
+            H, d, dp = self.head_pad
+            if self.pad_cols:
+                w = torch.nn.functional.pad(w.reshape(w.shape[0], H, d), (0, dp - d)).reshape(w.shape[0], H * dp)
+            else:
+                w = torch.nn.functional.pad(w.reshape(H, d, w.shape[1]), (0, 0, 0, dp - d)).reshape(H * dp, w.shape[1])
+        return w
+
+    def _bias(self, b):
+        bias = b.bias
+        if bias is None:
+            return None
+        bias = bias.detach().float()
+        if self.head_pad is not None and self.head_pad[1] != self.head_pad[2] and not self.pad_cols:
+            H, d, dp = self.head_pad
+            bias = torch.nn.functional.pad(bias.reshape(H, d), (0, dp - d)).reshape(H * dp)
+        return bias
 
     def pack(self):
         def build():
             ws = [self._w2d(b).float() for b in self.bases]
-            bs = [b.bias for b in self.bases]
+            bs = [self._bias(b) for b in self.bases]
             bias = None
             if any(x is not None for x in bs):
-                bias = torch.cat([x.detach().float() if x is not None else
+                bias = torch.cat([x if x is not None else
                                   torch.zeros(w.shape[0], device=w.device) for x, w in zip(bs, ws)]).contiguous()
             w = torch.cat(ws, dim=0)
             if self.geglu:
@@ -342,10 +365,11 @@ class LinearPack:
         """LayerNorm folded into this GEMM: B = W * gamma (bf16), colsum_n = sum_k bf16(W*gamma)[n,k] (what the tensor
         core really multiplies), bias' = b + W beta.  See fd_gemm (include/flashb200.h)."""
         def build():
-            w = torch.cat([self._w2d(b).float() for b in self.bases], dim=0)
-            bs = [b.bias for b in self.bases]
-            bias = torch.cat([x.detach().float() if x is not None else torch.zeros(b.weight.shape[0], device=w.device)
-                              for x, b in zip(bs, self.bases)])
+            ws = [self._w2d(b).float() for b in self.bases]
+            w = torch.cat(ws, dim=0)
+            bs = [self._bias(b) for b in self.bases]
+            bias = torch.cat([x if x is not None else torch.zeros(wi.shape[0], device=w.device)
+                              for x, wi in zip(bs, ws)])
             gamma, beta = norm.weight.detach().float(), norm.bias.detach().float()
             bias = bias + w @ beta
             wg = w * gamma[None, :]
@@ -551,20 +575,33 @@ class _AttnCrossFn(torch.autograd.Function):
         return dq, dkv, None
 
 
-def attention_self(qkv, H):
-    """qkv [B, N, 3*H*64] -> [B, N, H*64]"""
-    if _grad_on(qkv):
-        return _AttnSelfFn.apply(qkv, H)
-    inner = H * 64
-    return raw.attention_fwd(qkv[..., :inner], qkv[..., inner:2 * inner], qkv[..., 2 * inner:], H)
+def _no_grad_generic(name, *ts):
+    if _grad_on(*ts):
+        raise NotImplementedError(f"{name}: the attention backward kernel is built for head dim 64 without masks; "
+                                  "other head dims / key-padding masks are forward-only this round")
 
 
-def attention_cross(q, kv, H):
-    """q [B, Nq, H*64], kv [B, Nkv, 2*H*64] -> [B, Nq, H*64]"""
-    if _grad_on(q, kv):
-        return _AttnCrossFn.apply(q, kv, H)
-    inner = H * 64
-    return raw.attention_fwd(q, kv[..., :inner], kv[..., inner:], H)
+def attention_self(qkv, H, head_dim=64, scale=None):
+    """qkv [B, N, 3*H*d] -> [B, N, H*d]"""
+    if head_dim == 64:
+        if _grad_on(qkv):
+            return _AttnSelfFn.apply(qkv, H)
+    else:
+        _no_grad_generic("attention_self", qkv)
+    inner = H * head_dim
+    return raw.attention_fwd(qkv[..., :inner], qkv[..., inner:2 * inner], qkv[..., 2 * inner:], H, scale=scale,
+                             head_dim=head_dim)
+
+
+def attention_cross(q, kv, H, head_dim=64, scale=None, kv_len=None):
+    """q [B, Nq, H*d], kv [B, Nkv, 2*H*d] -> [B, Nq, H*d]; kv_len [B] int32 masks padded keys."""
+    if head_dim == 64 and kv_len is None:
+        if _grad_on(q, kv):
+            return _AttnCrossFn.apply(q, kv, H)
+    else:
+        _no_grad_generic("attention_cross", q, kv)
+    inner = H * head_dim
+    return raw.attention_fwd(q, kv[..., :inner], kv[..., inner:], H, scale=scale, head_dim=head_dim, kv_len=kv_len)
 
 
 # ------------------------------------------------------------------------------------------------

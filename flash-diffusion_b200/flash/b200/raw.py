@@ -137,12 +137,14 @@ def layernorm_bwd(x, stats, gamma, dy):
 
 
 # ------------------------------------------------------------------ attention
-def attention_fwd(q, k, v, H, scale=None, need_lse=False):
-    """q [B,Nq,H*64] view (last-dim stride 1), k/v [B,Nkv,H*64] views -> o [B,Nq,H*64] bf16."""
+def attention_fwd(q, k, v, H, scale=None, need_lse=False, head_dim=64, kv_len=None):
+    """q [B,Nq,H*d] view (last-dim stride 1), k/v [B,Nkv,H*d] views -> o [B,Nq,H*d] bf16.
+    d = 64 runs the tuned kernel (fd_attn_fwd); any other multiple of 16 up to 192, or a key-padding mask
+    kv_len [B] int32, runs fd_attn_fwd_generic."""
     lib = load(); _req(q, BF16, "q"); _req(k, BF16, "k"); _req(v, BF16, "v")
     B, Nq, HD = q.shape
     Nkv = k.shape[1]
-    assert HD == H * 64 and q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1
+    assert HD == H * head_dim and q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1
     o = torch.empty((B, Nq, HD), device=q.device, dtype=BF16)
     lse = torch.empty((B, H, Nq), device=q.device, dtype=torch.float32) if need_lse else None
     a = _l.FdAttnArgs()
@@ -152,8 +154,13 @@ def attention_fwd(q, k, v, H, scale=None, need_lse=False):
     a.o, a.ldo, a.o_batch_stride = ptr(o), o.stride(1), o.stride(0)
     a.lse = ptr(lse)
     a.B, a.H, a.Nq, a.Nkv = B, H, Nq, Nkv
-    a.scale = scale if scale is not None else 64 ** -0.5
-    check(lib.fd_attn_fwd(byref(a), stream_ptr()), "fd_attn_fwd")
+    a.scale = scale if scale is not None else head_dim ** -0.5
+    if head_dim == 64 and kv_len is None:
+        check(lib.fd_attn_fwd(byref(a), stream_ptr()), "fd_attn_fwd")
+    else:
+        if kv_len is not None:
+            assert kv_len.dtype == torch.int32 and kv_len.numel() == B and kv_len.is_cuda
+        check(lib.fd_attn_fwd_generic(byref(a), c_int32(head_dim), ptr(kv_len), stream_ptr()), "fd_attn_fwd_generic")
     return (o, lse) if need_lse else o
 
 

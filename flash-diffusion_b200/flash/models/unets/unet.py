@@ -308,23 +308,25 @@ class DiffusersUNet2DCondWrapper(nn.Module):
         """x: the residual stream (un-normalised), `norm` its LayerNorm.  When the producer GEMM left row statistics
         (`stats`) and no gradient / LoRA is involved, the LayerNorm is folded into the projection GEMM; otherwise the
         LayerNorm kernel runs.  Returns (new residual stream, its row statistics or None)."""
-        H = a.heads
-        if a.dim_head != 64:
-            raise NotImplementedError(f"attention kernel is built for head dim 64 (got {a.dim_head})")
-        inner = H * 64
+        H, d = a.heads, a.dim_head
+        dp = (d + 15) // 16 * 16                       # head dim the attention kernel sees (zero-padded channels)
+        hp = (H, d, dp) if dp != d else None
+        scale = d ** -0.5
+        inner = H * dp
         first = self._pack(("qkv" if not a.is_cross else "q", id(a)),
-                           lambda: LinearPack([a.to_q, a.to_k, a.to_v] if not a.is_cross else a.to_q))
+                           lambda: LinearPack([a.to_q, a.to_k, a.to_v] if not a.is_cross else a.to_q, head_pad=hp))
         if ops.ln_foldable(x, stats, first):
             proj = ops.linear_ln(x, stats, norm, first)
         else:
             proj = ops.linear(ops.layer_norm(x, norm), first)
         if not a.is_cross:
-            o = ops.attention_self(proj.view(B, -1, 3 * inner), H).view(-1, inner)
+            o = ops.attention_self(proj.view(B, -1, 3 * inner), H, head_dim=dp, scale=scale).view(-1, inner)
         else:
-            kv = ops.linear(ctx, self._pack(("kv", id(a)), lambda: LinearPack([a.to_k, a.to_v])))
-            o = ops.attention_cross(proj.view(B, -1, inner), kv.view(B, -1, 2 * inner), H).view(-1, inner)
-        return ops.linear(o, self._pack(("o", id(a)), lambda: LinearPack(a.to_out[0])), residual=residual,
-                          want_stats=True)
+            kv = ops.linear(ctx, self._pack(("kv", id(a)), lambda: LinearPack([a.to_k, a.to_v], head_pad=hp)))
+            o = ops.attention_cross(proj.view(B, -1, inner), kv.view(B, -1, 2 * inner), H, head_dim=dp,
+                                    scale=scale).view(-1, inner)
+        return ops.linear(o, self._pack(("o", id(a)), lambda: LinearPack(a.to_out[0], head_pad=hp, pad_cols=True)),
+                          residual=residual, want_stats=True)
 
     def _transformer(self, t, x, geom, ctx):
         B = geom[0]

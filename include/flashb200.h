@@ -132,6 +132,10 @@ typedef struct {
     float scale;
 } FdAttnArgs;
 int fd_attn_fwd(const FdAttnArgs* args, void* stream);
+/* Same contract for head dims other than 64 (multiple of 16, <= 192; q/k/v/o rows are H*head_dim wide) and an optional
+ * key-padding mask kv_len[B] (keys >= kv_len[b] are ignored) — SD1.5 (d=40/80/160 zero-padded to 48/80/160 by the
+ * weight packs) and PixArt-alpha (d=72 -> 80, masked T5 context).  Forward only. */
+int fd_attn_fwd_generic(const FdAttnArgs* args, int32_t head_dim, const int32_t* kv_len, void* stream);
 
 typedef struct {
     FdAttnArgs f;                 /* forward tensors (o = forward output, lse required) */

@@ -157,3 +157,27 @@ def test_step_kernels(raw):
     so = raw.step_student_output(z, eps_c, sa, sg, cs, co)
     v = lambda t: t.view(-1, 1, 1, 1)
     assert torch.allclose(so, v(cs) * z + v(co) * (z - v(sg) * eps_c) / v(sa), atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize("B,H,Nq,Nkv,d,masked", [(2, 8, 256, 256, 48, False), (1, 8, 1024, 77, 80, False),
+                                                   (2, 4, 200, 333, 160, False), (2, 3, 256, 120, 80, True),
+                                                   (1, 2, 128, 384, 128, False), (2, 2, 130, 300, 64, True)])
+def test_attention_generic_head_dims_and_mask(raw, B, H, Nq, Nkv, d, masked):
+    """fd_attn_fwd_generic: SD1.5 / PixArt head dims (zero-padded to multiples of 16) and key-padding masks."""
+    torch.manual_seed(d + Nq)
+    q = torch.randn(B, Nq, H * d, device="cuda").bfloat16()
+    k = torch.randn(B, Nkv, H * d, device="cuda").bfloat16()
+    v = torch.randn(B, Nkv, H * d, device="cuda").bfloat16()
+    kv_len = torch.tensor([Nkv - 17 * (i + 1) for i in range(B)], device="cuda", dtype=torch.int32) if masked else None
+    scale = 0.11
+    o, lse = raw.attention_fwd(q, k, v, H, scale=scale, need_lse=True, head_dim=d, kv_len=kv_len)
+    qf = q.float().view(B, Nq, H, d).transpose(1, 2)
+    kf = k.float().view(B, Nkv, H, d).transpose(1, 2)
+    vf = v.float().view(B, Nkv, H, d).transpose(1, 2)
+    s = qf @ kf.transpose(-1, -2) * scale
+    if masked:
+        mask = torch.arange(Nkv, device="cuda")[None, :] >= kv_len[:, None]
+        s = s.masked_fill(mask[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, dim=-1) @ vf).transpose(1, 2).reshape(B, Nq, H * d)
+    assert _rel(o, ref) < 1e-2, _rel(o, ref)
+    assert _rel(lse, torch.logsumexp(s, dim=-1)) < 1e-4

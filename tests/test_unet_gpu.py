@@ -86,3 +86,19 @@ def test_sdxl_unet_forward_full_size():
         ref = ora(x, t, cond)
     assert torch.isfinite(out).all()
     assert _rel(out, ref) < 2e-2, _rel(out, ref)
+
+
+def test_sd15_unet_forward_head_dims_40_80_160():
+    """BASELINE config 1 architecture (examples/train_flash_sd.py:56-114: 8 heads -> head dims 40/80/160) at 512x512
+    (latent 64x64), forward only, against the fp32 oracle."""
+    from oracle.unet import SD15_KWARGS
+    prod, ora = _pair(SD15_KWARGS, lora=False, seed=7)
+    x, t, cond = _inputs(2, 64, 64, 768, 0)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    with torch.no_grad():
+        out = prod(x, t, cond)
+        ref = ora(x, t, cond)
+    assert _rel(out, ref) < 2e-2, _rel(out, ref)
+    with pytest.raises(NotImplementedError):
+        prod(x.requires_grad_(True), t, cond)
