@@ -264,6 +264,11 @@ def run_ours(args):
             sink.append((float(out["loss_optimizer_0"]), float(out["loss_optimizer_1"])))
 
     ms_e2e, _ = timed(e2e_loop)
+    # (3) same steps with the output-preserving dead-work elision on the discriminator turn: reported
+    #     separately, never as `value`
+    model.elide_unused_generator_pass = True
+    ms_lean, _ = timed(lambda: [step(resident[i], i) for i in range(args.steps)])
+    model.elide_unused_generator_pass = False
     clocks = sampler.stop() if rank == 0 else None
 
     imgs = B * world * args.steps
@@ -321,6 +326,11 @@ def run_ours(args):
                 "config": config_dict(world), "roofline": roof, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                         "ms_per_step": ms_e2e / args.steps},
+                "lean": {"value": imgs / (ms_lean / 1e3), "unit": UNIT, "ms_per_step": ms_lean / args.steps,
+                         "note": "same step with the generator objective elided on the discriminator turn, where the "
+                                 "reference recomputes and discards it (output-preserving: identical loss_D / updates, "
+                                 "tests/test_flash_step_cpu.py::test_lean_discriminator_turn_is_output_preserving); "
+                                 "algorithmic FLOPs per image drop from 616 to ~330 TFLOP"},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "losses_last_step": sink[-1] if sink else None}
         print(json.dumps(line))

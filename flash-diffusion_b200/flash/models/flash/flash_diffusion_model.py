@@ -87,6 +87,12 @@ class FlashDiffusion(BaseModel):
         # B200 options
         self.use_cuda_graphs = True      # replay frozen-teacher evaluations from a CUDA graph (same kernels)
         self.__dict__["_graphed"] = {}
+        # Output-preserving dead-work elision: on the discriminator turn (odd `step`) the
+        # trainer back-propagates ONLY loss[1] (reference trainer.py:213-217), which depends on the detached student
+        # output, the GAN backbone features and the discriminator — not on the teacher rollout, the distillation loss
+        # or the DMD loss the reference recomputes and discards there.  Off by default (strict reference schedule);
+        # when on, those are skipped (loss[0] is returned as None) and the student runs without an autograd graph.
+        self.elide_unused_generator_pass = False
         self.batch_cfg = True            # cond+uncond as one 2B call (output-preserving)
         self.dedupe_conditioning = True  # one conditioner pass when every ucg_rate is 0 (output-preserving)
 
@@ -206,8 +212,11 @@ class FlashDiffusion(BaseModel):
             noisy_sample_init = sched.add_noise(z, noise, start_timestep)
         student_in = sched.scale_model_input(noisy_sample_init, start_timestep)
 
-        student_noise_pred = self.student_denoiser(sample=student_in, timestep=start_timestep,
-                                                   conditioning=student_conditioning)
+        lean = (self.elide_unused_generator_pass and step % 2 == 1 and not self.use_teacher_as_real
+                and self.discriminator is not None)
+        with torch.set_grad_enabled(torch.is_grad_enabled() and not lean):
+            student_noise_pred = self.student_denoiser(sample=student_in, timestep=start_timestep,
+                                                       conditioning=student_conditioning)
         c_skip, c_out = self._scalings_for_boundary_conditions(start_timestep)
         c_skip, c_out = append_dims(c_skip, z.ndim), append_dims(c_out, z.ndim)
         student_x0 = self._predicted_x_0(student_noise_pred, start_timestep.type(torch.int64), noisy_sample_init,
@@ -218,9 +227,13 @@ class FlashDiffusion(BaseModel):
         else:
             guidance_scale = torch.rand(1).to(z.device) * (g_max - g_min) + g_min
 
+        student_output = c_skip * noisy_sample_init + c_out * student_x0
+        if lean:
+            gan_loss = self._gan_loss(z, batch, student_output, None, conditioning, None, step=step, draws=draws)
+            return {"loss": [None, gan_loss[1]], "teacher_output": None, "student_output": student_output,
+                    "noisy_sample": noisy_sample_init, "start_timestep": int(start_timestep[0])}
         teacher_output = self._teacher_rollout(noisy_sample_init, conditioning, unconditional_conditioning,
                                                int(start_idx), guidance_scale)
-        student_output = c_skip * noisy_sample_init + c_out * student_x0
 
         loss = self._distill_loss(student_output, teacher_output) * self.distill_loss_scale[K_step]
         if self.use_dmd_loss:

@@ -191,3 +191,24 @@ def test_ddpm_scheduler_protocol():
     x = torch.randn(1, 4, 8, 8)
     assert s.step(torch.randn_like(x), s.timesteps[0], x)[0].shape == x.shape
     assert s.add_noise(x, torch.randn_like(x), torch.tensor([5])).shape == x.shape
+
+
+def test_lean_discriminator_turn_is_output_preserving():
+    """Eliding the generator objective on the discriminator turn leaves loss[1] and the discriminator
+    update unchanged."""
+    b, d = _batch(), _draws()
+    strict = _model()
+    lean = _model()
+    lean.elide_unused_generator_pass = True
+    o_s = strict(b, step=1, draws=d)
+    o_l = lean(b, step=1, draws=d)
+    assert o_l["loss"][0] is None and o_l["teacher_output"] is None
+    assert torch.allclose(o_l["loss"][1], o_s["loss"][1], rtol=1e-6, atol=1e-8)
+    assert torch.allclose(o_l["student_output"], o_s["student_output"], rtol=1e-6, atol=1e-7)
+    o_s["loss"][1].backward()
+    o_l["loss"][1].backward()
+    for (n1, p1), (n2, p2) in zip(strict.discriminator.named_parameters(), lean.discriminator.named_parameters()):
+        assert torch.allclose(p1.grad, p2.grad, rtol=1e-5, atol=1e-8), n1
+    assert all(p.grad is None for p in lean.student_denoiser.parameters())
+    # generator turn untouched
+    assert lean(b, step=0, draws=d)["loss"][0] is not None
