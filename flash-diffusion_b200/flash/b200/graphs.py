@@ -32,8 +32,16 @@ class GraphedDenoiser:
 
     @staticmethod
     def eligible(denoiser, sample):
-        return (sample.is_cuda and not torch.is_grad_enabled() and not sample.requires_grad
-                and not any(p.requires_grad for p in denoiser.parameters()))
+        """Frozen modules always; a module with trainable (LoRA) parameters only in eval mode (sampling): its
+        kernel-side adapter packs are rebuilt after every optimizer step, which would invalidate the pointers baked
+        into a graph, so during training it runs eagerly.  In eval mode the parameter versions are checked before
+        every replay and the graph is re-captured if anything changed."""
+        if not sample.is_cuda or torch.is_grad_enabled() or sample.requires_grad:
+            return False
+        return (not denoiser.training) or not any(p.requires_grad for p in denoiser.parameters())
+
+    def _param_signature(self):
+        return sum(p._version for p in self.denoiser.parameters() if p.requires_grad)
 
     def _signature(self, sample, timestep, conditioning, kw):
         cond = conditioning["cond"]
@@ -55,6 +63,7 @@ class GraphedDenoiser:
         with torch.cuda.graph(graph), torch.no_grad():
             out = self.denoiser(sample=static["sample"], timestep=static["timestep"], conditioning=static["cond"], **kw)
         static["launches"] = _host_launches() - l0
+        static["params"] = self._param_signature()
         static["out"] = out
         static["graph"] = graph
         return static
@@ -62,6 +71,8 @@ class GraphedDenoiser:
     def __call__(self, sample, timestep, conditioning, clone=True, **kw):
         sig = self._signature(sample, timestep, conditioning, kw)
         st = self.graphs.get(sig)
+        if st is not None and st["params"] != self._param_signature():
+            st = None                       # trainable parameters changed since capture: re-capture
         if st is None:
             st = self._capture(sample, timestep, conditioning, kw)
             self.graphs[sig] = st

@@ -102,3 +102,29 @@ def test_sd15_unet_forward_head_dims_40_80_160():
     assert _rel(out, ref) < 2e-2, _rel(out, ref)
     with pytest.raises(NotImplementedError):
         prod(x.requires_grad_(True), t, cond)
+
+
+def test_cuda_graph_replay_matches_eager():
+    """flash.b200.graphs.GraphedDenoiser: replay == eager launches (frozen teacher, and LoRA student in eval mode with
+    re-capture after a parameter update)."""
+    from flash.b200.graphs import GraphedDenoiser
+    prod, _ = _pair(SMALL, lora=True)
+    prod.eval()
+    x, t, cond = _inputs(2, 32, 32, 96, 48)
+    with torch.no_grad():
+        assert GraphedDenoiser.eligible(prod, x)
+        g = GraphedDenoiser(prod)
+        eager = prod(x, t, cond)
+        assert torch.equal(g(x, t, cond), eager)
+        x2, t2, cond2 = _inputs(2, 32, 32, 96, 48, seed=5)
+        assert torch.equal(g(x2, t2, cond2), prod(x2, t2, cond2))
+        assert len(g.graphs) == 1
+        for n, p in prod.named_parameters():
+            if "lora_B" in n:
+                p.mul_(1.5)                                   # in-place update bumps the version counter
+        new = prod(x, t, cond)
+        assert not torch.equal(new, eager)
+        assert torch.equal(g(x, t, cond), new)                # re-captured with the new adapter packs
+    prod.train()
+    with torch.no_grad():
+        assert not GraphedDenoiser.eligible(prod, x)          # training-mode LoRA module stays eager
