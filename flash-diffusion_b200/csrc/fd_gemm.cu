@@ -25,7 +25,7 @@ constexpr int BK = 64;
 constexpr int GEMM_THREADS = 384;   // warps 0-3: TMA / MMA / TMEM alloc / spare; warps 4-11: epilogue (2 per lane quarter)
 
 struct GemmKParams {
-    int M, N, kb1, kb2, num_m_tiles, num_n_tiles;
+    int M, N, kb1, kb2, num_m_tiles, num_n_tiles, group_m;
     int conv_taps, cblocks, H, W, tile_w, tile_h;
     int tap_dn[FD_MAX_TAPS], tap_dh[FD_MAX_TAPS], tap_dw[FD_MAX_TAPS];
     const float* bias;
@@ -56,14 +56,13 @@ struct GemmCfg {
 // Tile rasterisation: consecutive tile indices (= what the 148 persistent CTAs work on at the same time) walk
 // GROUP_M m-tiles x all n-tiles, m fastest, so a wave touches ~16 A row-panels and ~9 B panels instead of
 // 148 A panels and 1 B panel: each A panel is fetched from DRAM once per group and re-used out of L2.
-constexpr int GROUP_M = 16;
 __device__ __forceinline__ void tile_coords(const GemmKParams& p, int tile, int& mt, int& nt) {
-    const int per_group = GROUP_M * p.num_n_tiles;
+    const int per_group = p.group_m * p.num_n_tiles;
     const int g = tile / per_group;
     const int r = tile - g * per_group;
-    const int gm = min(GROUP_M, p.num_m_tiles - g * GROUP_M);
+    const int gm = min(p.group_m, p.num_m_tiles - g * p.group_m);
     nt = r / gm;
-    mt = g * GROUP_M + (r - nt * gm);
+    mt = g * p.group_m + (r - nt * gm);
 }
 
 // per-row state carried across the 32-column chunks of one tile
@@ -721,6 +720,10 @@ extern "C" int fd_gemm(const FdGemmArgs* a, void* stream_) {
     p.N = a->N;
     p.num_m_tiles = (a->M + BM - 1) / BM;
     p.num_n_tiles = (a->N + BN - 1) / BN;
+    {
+        static const int env_gm = getenv("FD_GROUP_M") ? atoi(getenv("FD_GROUP_M")) : 0;
+        p.group_m = env_gm > 0 ? env_gm : (pair ? 8 : 16);   // pair tiles are 256 rows: 8 x 256 = 16 x 128
+    }
     p.bias = a->bias;
     p.rowvec = a->rowvec;
     p.rows_per_group = a->rows_per_group;
