@@ -2,15 +2,18 @@
 //
 //   O = softmax(Q K^T * scale) V       per (batch, head), Q/K/V read in place from [B, N, H*64]
 //
-// One CTA per (256 queries = two 128-row tiles, head, batch); 10 warps:
+// One CTA per (256 queries = two 128-row tiles, head, batch); 18 warps:
 //   warp 0    TMA producer  : Q0,Q1 once, K/V tiles (128 keys) through a 3-stage ring
 //   warp 1    MMA issuer    : S_w = Q_w K^T (tcgen05 128x128x64) and O_w += P_w V (128x64x128) for w = 0,1,
 //                             interleaved so that the softmax of one tile overlaps the MMAs of the other
-//   warps 2-5 / 6-9 softmax : one warpgroup per query tile; the S row goes to registers in one tcgen05.ld round
-//                             trip and the S buffer is released at once (S(j+1) is issued while softmax(j) runs);
+//   warps 2-17 softmax      : per query tile 8 warps = 2 column halves x 4 TMEM lane quarters (a thread owns 64 of
+//                             its row's 128 scores; the halves exchange the row max through smem); the scores go
+//                             to registers in one tcgen05.ld round trip and the S buffer is released at once
+//                             (S(j+1) is issued while softmax(j) runs);
 //                             FMNMX3 row max, FFMA2 + ex2.approx + FADD2, P -> smem (bf16, 128B-swizzled K-major);
 //                             O rescaled in TMEM only when the running maximum grew by more than 2^8
-// TMEM: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384).  V is consumed as an MN-major B operand straight
+// TMEM: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384) P0 [384,448) P1 [448,512) (P = bf16 pairs, the A
+// operand of O += P V is read from TMEM, so P never touches shared memory).  V is an MN-major B operand straight
 // from its row-major [key, d] tile, so no transpose is materialised.
 //
 // UPSTREAM math: diffusers Attention + AttnProcessor2_0 -> F.scaled_dot_product_attention
@@ -18,16 +21,20 @@
 #include "fd_common.cuh"
 #include "fd_host.h"
 
+#ifndef FD_ATTN_P_TMEM
+#define FD_ATTN_P_TMEM 1   // P operand of the P V product lives in TMEM (tcgen05.mma A-from-TMEM) instead of smem
+#endif
+
 namespace fd {
 
 constexpr int ATT_BM = 256;   // queries per CTA: two 128-row tiles, one softmax warpgroup each
 constexpr int ATT_BN = 128;   // keys per tile
 constexpr int ATT_D = 64;
 constexpr int ATT_STAGES = 3;
-constexpr int ATT_THREADS = 64 + 256;         // TMA warp, MMA warp, 2 x 4 softmax warps
+constexpr int ATT_THREADS = 64 + 512;         // TMA warp, MMA warp, 2 tiles x 2 column halves x 4 softmax warps
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB
 // Q0,Q1 | K,V x stages | P0,P1 (2 sub-tiles each) | barriers
-constexpr int ATT_SMEM = 2 * ATT_TILE_BYTES + 2 * ATT_STAGES * ATT_TILE_BYTES + 4 * ATT_TILE_BYTES + 256 + 1024;
+constexpr int ATT_SMEM = 2 * ATT_TILE_BYTES + 2 * ATT_STAGES * ATT_TILE_BYTES + 4 * ATT_TILE_BYTES + 256 + 4096 + 1024;
 
 struct AttnKParams {
     int Nq, Nkv;
@@ -107,6 +114,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint64_t* p_ready = s_free + 2;                // [2]  P_w(j) in smem
     uint64_t* pv_done = p_ready + 2;               // [2]  O_w += P_w(j) V(j) complete
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pv_done + 2);
+    float* mx_buf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [tile][parity][half][128]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -126,8 +134,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
         for (int w = 0; w < 2; ++w) {
             mbar_init(&s_full[w], 1);
-            mbar_init(&s_free[w], 128);
-            mbar_init(&p_ready[w], 128);
+            mbar_init(&s_free[w], 256);
+            mbar_init(&p_ready[w], 256);
             mbar_init(&pv_done[w], 1);
         }
         fence_barrier_init();
@@ -177,12 +185,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             };
             auto issue_pv = [&](int w, int st, int j) {
                 const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES);
+#if FD_ATTN_P_TMEM
+                // A operand (P, bf16) straight from TMEM: 8 columns (= 16 keys) per MMA
+#pragma unroll
+                for (int k = 0; k < ATT_BN / 16; ++k)
+                    tc_mma_bf16_ts(tmem_base + 256 + w * 64, tmem_base + 384 + w * 64 + k * 8,
+                                   make_desc_mn_sw128(v_addr + k * 2048, 0, 1024), idesc_pv, (j | k) != 0 ? 1u : 0u);
+#else
                 const uint32_t pa = p_addr + w * 2 * ATT_TILE_BYTES;
 #pragma unroll
                 for (int k = 0; k < ATT_BN / 16; ++k)
                     tc_mma_bf16(tmem_base + 256 + w * 64,
                                 make_desc_k_sw128(pa + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32),
                                 make_desc_mn_sw128(v_addr + k * 2048, 0, 1024), idesc_pv, (j | k) != 0 ? 1u : 0u);
+#endif
             };
             mbar_wait(q_full, 0);
             mbar_wait(&kv_full[0], 0);
@@ -201,11 +217,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     const int js = next_s[w];
                     if (js < n_kv_tiles) {
                         // needs: s_free[w](js-1) and kv_full(js)
-                        if (mbar_try_wait(&s_free[w], (js - 1) & 1)) {
+                        if (mbar_test_wait(&s_free[w], (js - 1) & 1)) {
                             bool kv_ok = js < kv_seen;
                             if (!kv_ok && js == kv_seen) {
                                 const int stg = js % ATT_STAGES;
-                                if (mbar_try_wait(&kv_full[stg], (js / ATT_STAGES) & 1)) {
+                                if (mbar_test_wait(&kv_full[stg], (js / ATT_STAGES) & 1)) {
                                     kv_seen = js + 1;
                                     kv_ok = true;
                                 }
@@ -218,7 +234,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                         }
                     }
                     const int jp = next_pv[w];
-                    if (jp < n_kv_tiles && mbar_try_wait(&p_ready[w], jp & 1)) {
+                    if (jp < n_kv_tiles && mbar_test_wait(&p_ready[w], jp & 1)) {
                         tc_fence_after();
                         issue_pv(w, jp % ATT_STAGES, jp);
                         tc_commit(&pv_done[w]);
@@ -230,40 +246,49 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
         }
     } else {
-        // softmax warpgroup w = 0 (warps 2-5) / 1 (warps 6-9); TMEM lane quarter = warp % 4
-        const int w = (warp - 2) >> 2;
+        // 16 softmax warps: query tile w (0/1) x column half h (0/1) x TMEM lane quarter (= warp % 4).
+        // Thread (w, h, row) owns 64 of the 128 score columns of its row: half the serial work per thread and
+        // twice the warps per scheduler to hide the TMEM / MUFU / barrier latencies.  The two halves of a row
+        // exchange their partial row maximum through shared memory once per key tile.
+        const int g = (warp - 2) >> 2;
+        const int w = g >> 1, h = g & 1;
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;                       // row within this 128-query tile
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-        const uint32_t tmem_S = tmem_base + w * 128;
-        const uint32_t tmem_O = tmem_base + 256 + w * 64;
-        uint8_t* sPw = sP + w * 2 * ATT_TILE_BYTES;
+        const uint32_t tmem_S = tmem_base + w * 128 + h * 64;
+        const uint32_t tmem_O = tmem_base + 256 + w * 64 + h * 32;
+        uint8_t* sPw = sP + w * 2 * ATT_TILE_BYTES + h * ATT_TILE_BYTES;   // this half's [128][64] sub-tile
+        float* mxw = mx_buf + w * 512;
+        const int bar_id = 1 + w;
         float m_used = -INFINITY, l_run = 0.f;
         for (int j = 0; j < n_kv_tiles; ++j) {
             mbar_wait(&s_full[w], j & 1);
             tc_fence_after();
-            const int kv_valid = min(ATT_BN, p.Nkv - j * ATT_BN);
-            // the whole S row (128 fp32) comes to registers in ONE TMEM round trip; the S buffer is then free
-            uint32_t sr[4][32];
-#pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld_32x32(tmem_S + lane_base + c * 32, sr[c]);
+            const int kv_valid = min(ATT_BN, p.Nkv - j * ATT_BN) - h * 64;   // valid columns within this half
+            uint32_t sr[2][32];
+            tmem_ld_32x32(tmem_S + lane_base, sr[0]);
+            tmem_ld_32x32(tmem_S + lane_base + 32, sr[1]);
             tmem_ld_wait();
             tc_fence_before();
             mbar_arrive(&s_free[w]);
-            if (kv_valid < ATT_BN) {
+            if (kv_valid < 64) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
+                for (int c = 0; c < 2; ++c)
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
                         if (c * 32 + i >= kv_valid) sr[c][i] = 0xff800000u;      // -inf: exp2 -> 0
             }
-            float mxs[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            float mxs[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+            for (int c = 0; c < 2; ++c)
 #pragma unroll
                 for (int i = 0; i < 32; i += 2)
                     mxs[c] = max3(mxs[c], __uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1]));
-            const float mx = fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3]));
+            float mx = fmaxf(mxs[0], mxs[1]);
+            float* slot = mxw + (j & 1) * 256;
+            slot[h * 128 + row] = mx;
+            asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+            mx = fmaxf(mx, slot[(h ^ 1) * 128 + row]);
             const float m_new = mx * p.scale_log2;
             const bool grow = m_new > m_used + ATT_RESCALE_THRESHOLD;      // first tile: m_used = -inf -> true
             const float alpha = (grow && j > 0) ? fast_exp2(m_used - m_new) : 1.0f;
@@ -272,9 +297,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
             const float2 nm2 = make_float2(-m_used, -m_used);
             float2 ps2 = make_float2(0.f, 0.f);
-            uint32_t pk[4][16];
+            uint32_t pk[2][16];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
                     const float2 x = ffma2(make_float2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), sc2, nm2);
@@ -289,42 +314,56 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 mbar_wait(&pv_done[w], (j - 1) & 1);
                 tc_fence_after();
                 if (__any_sync(0xffffffffu, alpha != 1.0f)) {
-#pragma unroll 1
-                    for (int c = 0; c < ATT_D / 32; ++c) {
-                        uint32_t r[32];
-                        tmem_ld_32x32(tmem_O + lane_base + c * 32, r);
-                        tmem_ld_wait();
+                    uint32_t r[32];
+                    tmem_ld_32x32(tmem_O + lane_base, r);
+                    tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-                        tmem_st_32x32(tmem_O + lane_base + c * 32, r);
-                    }
+                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                    tmem_st_32x32(tmem_O + lane_base, r);
                     tmem_st_wait();
                 }
             }
+#if FD_ATTN_P_TMEM
+            // P (bf16 pairs) goes to its own TMEM columns [384 + 64 w + 32 h, +32): no shared-memory round trip
+            {
+                uint32_t pflat[32];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint8_t* sub = sPw + (c >> 1) * ATT_TILE_BYTES + row * 128;
+                for (int i = 0; i < 16; ++i) {
+                    pflat[i] = pk[0][i];
+                    pflat[16 + i] = pk[1][i];
+                }
+                tmem_st_32x32(tmem_base + 384 + w * 64 + h * 32 + lane_base, pflat);
+                tmem_st_wait();
+            }
+#else
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint8_t* sub = sPw + row * 128;
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
-                    const int chunk = ((c & 1) * 4 + q4) ^ (row & 7);
+                    const int chunk = (c * 4 + q4) ^ (row & 7);
                     *reinterpret_cast<uint4*>(sub + chunk * 16) =
                         make_uint4(pk[c][4 * q4], pk[c][4 * q4 + 1], pk[c][4 * q4 + 2], pk[c][4 * q4 + 3]);
                 }
             }
             fence_proxy_async();
+#endif
             tc_fence_before();
             mbar_arrive(&p_ready[w]);
         }
-        // epilogue: O / l -> bf16
+        // epilogue: combine the two halves' row sums, then O / l -> bf16 (each half stores 32 of the 64 channels)
+        float* slot = mxw + (n_kv_tiles & 1) * 256;
+        slot[h * 128 + row] = l_run;
+        asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
+        l_run += slot[(h ^ 1) * 128 + row];
         mbar_wait(&pv_done[w], (n_kv_tiles - 1) & 1);
         tc_fence_after();
         const int q_row = q_blk * ATT_BM + w * 128 + row;
         const float inv_l = 1.f / l_run;
-        bf16* orow = p.o + (long long)batch * p.o_batch_stride + (long long)q_row * p.ldo + head * ATT_D;
-#pragma unroll 1
-        for (int c = 0; c < ATT_D / 32; ++c) {
+        bf16* orow = p.o + (long long)batch * p.o_batch_stride + (long long)q_row * p.ldo + head * ATT_D + h * 32;
+        {
             uint32_t r[32];
-            tmem_ld_32x32(tmem_O + lane_base + c * 32, r);
+            tmem_ld_32x32(tmem_O + lane_base, r);
             tmem_ld_wait();
             if (q_row < p.Nq) {
 #pragma unroll
@@ -334,11 +373,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     u.y = pack_bf16x2(__uint_as_float(r[8 * q4 + 2]) * inv_l, __uint_as_float(r[8 * q4 + 3]) * inv_l);
                     u.z = pack_bf16x2(__uint_as_float(r[8 * q4 + 4]) * inv_l, __uint_as_float(r[8 * q4 + 5]) * inv_l);
                     u.w = pack_bf16x2(__uint_as_float(r[8 * q4 + 6]) * inv_l, __uint_as_float(r[8 * q4 + 7]) * inv_l);
-                    *reinterpret_cast<uint4*>(orow + c * 32 + q4 * 8) = u;
+                    *reinterpret_cast<uint4*>(orow + q4 * 8) = u;
                 }
             }
         }
-        if (p.lse != nullptr && q_row < p.Nq)
+        if (h == 0 && p.lse != nullptr && q_row < p.Nq)
             p.lse[((long long)batch * p.H + head) * p.Nq + q_row] = (m_used + log2f(l_run)) * 0.69314718055994531f;
     }
 
