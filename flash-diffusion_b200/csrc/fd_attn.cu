@@ -90,6 +90,28 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
     return d;
 }
 
+// exp2 on the FMA pipe (Cody-Waite range reduction + cubic), two values at a time.  The MUFU (XU) pipe issues only
+// 16 ex2 per clock per SM and is the softmax bottleneck (ncu: mio_throttle is the top stall), so every
+// FD_ATTN_POLY_MOD-th pair of scores takes this path instead.  Relative error < 7e-4 (bf16 P has 2^-9 = 2e-3).
+#ifndef FD_ATTN_POLY_MOD
+#define FD_ATTN_POLY_MOD 4
+#endif
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+    const float kMagic = 12582912.0f;   // 1.5 * 2^23
+    x.x = fmaxf(x.x, -126.0f);
+    x.y = fmaxf(x.y, -126.0f);
+    const float2 t = fadd2(x, make_float2(kMagic, kMagic));
+    const float2 n = fadd2(t, make_float2(-kMagic, -kMagic));
+    const float2 f = fadd2(x, make_float2(-n.x, -n.y));
+    float2 pz = ffma2(f, make_float2(0.05550411f, 0.05550411f), make_float2(0.24022651f, 0.24022651f));
+    pz = ffma2(pz, f, make_float2(0.69314718f, 0.69314718f));
+    pz = ffma2(pz, f, make_float2(1.0f, 1.0f));
+    float2 r;
+    r.x = __int_as_float(__float_as_int(pz.x) + (__float_as_int(t.x) << 23));
+    r.y = __int_as_float(__float_as_int(pz.y) + (__float_as_int(t.y) << 23));
+    return r;
+}
+
 // Rescale threshold (log2 domain): O and l are only rescaled when the running row maximum grew by more
 // than this; otherwise the stale maximum keeps being used (P <= 2^8, exact in fp32 accumulation, and the
 // final O / l is invariant to the reference maximum).
@@ -257,7 +279,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         const uint32_t tmem_S = tmem_base + w * 128 + h * 64;
         const uint32_t tmem_O = tmem_base + 256 + w * 64 + h * 32;
+#if !FD_ATTN_P_TMEM
         uint8_t* sPw = sP + w * 2 * ATT_TILE_BYTES + h * ATT_TILE_BYTES;   // this half's [128][64] sub-tile
+#endif
         float* mxw = mx_buf + w * 512;
         const int bar_id = 1 + w;
         float m_used = -INFINITY, l_run = 0.f;
@@ -303,7 +327,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
                     const float2 x = ffma2(make_float2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), sc2, nm2);
-                    const float2 e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+                    float2 e;
+                    if (FD_ATTN_POLY_MOD > 0 && ((i >> 1) % (FD_ATTN_POLY_MOD > 0 ? FD_ATTN_POLY_MOD : 1)) == 1)
+                        e = exp2_poly2(x);
+                    else
+                        e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
                     ps2 = fadd2(ps2, e);
                     pk[c][i >> 1] = pack_bf16x2(e.x, e.y);
                 }
