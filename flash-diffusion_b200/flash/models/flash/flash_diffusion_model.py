@@ -211,9 +211,25 @@ class FlashDiffusion(BaseModel):
         else:
             noisy_sample_init = sched.add_noise(z, noise, start_timestep)
         student_in = sched.scale_model_input(noisy_sample_init, start_timestep)
+        start_t_host = int(sched.timesteps[int(start_idx)])          # host copy: no device sync for the return value
+
+        # guidance scale: drawn on the host exactly like the reference (`torch.rand(1).to(device)`, :284-286) but kept
+        # as a host float so that the fused rollout never has to read it back from the device
+        if "guidance" in draws:
+            guidance_host = float(draws["guidance"])
+        else:
+            guidance_host = float(torch.rand(1)) * (g_max - g_min) + g_min
 
         lean = (self.elide_unused_generator_pass and step % 2 == 1 and not self.use_teacher_as_real
                 and self.discriminator is not None)
+        # The frozen-teacher rollout (CUDA-graph replays: GPU-heavy, host-light) is ENQUEUED BEFORE the student
+        # forward (eager launches + autograd bookkeeping: host-heavy): the two are independent (:260-265 vs :288-324),
+        # so the host prepares the student's launches while the GPU is busy with the rollout.  Same values, same
+        # random-draw order.
+        teacher_output = None
+        if not lean:
+            teacher_output = self._teacher_rollout(noisy_sample_init, conditioning, unconditional_conditioning,
+                                                   int(start_idx), guidance_host)
         with torch.set_grad_enabled(torch.is_grad_enabled() and not lean):
             student_noise_pred = self.student_denoiser(sample=student_in, timestep=start_timestep,
                                                        conditioning=student_conditioning)
@@ -222,18 +238,11 @@ class FlashDiffusion(BaseModel):
         student_x0 = self._predicted_x_0(student_noise_pred, start_timestep.type(torch.int64), noisy_sample_init,
                                          "epsilon", self.sqrt_alpha_cumprod, self.sigmas, z)
 
-        if "guidance" in draws:
-            guidance_scale = torch.as_tensor([float(draws["guidance"])], device=z.device)
-        else:
-            guidance_scale = torch.rand(1).to(z.device) * (g_max - g_min) + g_min
-
         student_output = c_skip * noisy_sample_init + c_out * student_x0
         if lean:
             gan_loss = self._gan_loss(z, batch, student_output, None, conditioning, None, step=step, draws=draws)
             return {"loss": [None, gan_loss[1]], "teacher_output": None, "student_output": student_output,
-                    "noisy_sample": noisy_sample_init, "start_timestep": int(start_timestep[0])}
-        teacher_output = self._teacher_rollout(noisy_sample_init, conditioning, unconditional_conditioning,
-                                               int(start_idx), guidance_scale)
+                    "noisy_sample": noisy_sample_init, "start_timestep": start_t_host}
 
         loss = self._distill_loss(student_output, teacher_output) * self.distill_loss_scale[K_step]
         if self.use_dmd_loss:
@@ -242,7 +251,7 @@ class FlashDiffusion(BaseModel):
         gan_loss = self._gan_loss(z, batch, student_output, teacher_output, conditioning, None, step=step, draws=draws)
         loss = loss + self.adversarial_loss_scale[K_step] * gan_loss[0]
         return {"loss": [loss, gan_loss[1]], "teacher_output": teacher_output, "student_output": student_output,
-                "noisy_sample": noisy_sample_init, "start_timestep": int(start_timestep[0])}
+                "noisy_sample": noisy_sample_init, "start_timestep": start_t_host}
 
     @torch.no_grad()
     def _teacher_rollout(self, noisy_sample_init, conditioning, unconditional_conditioning, start_idx, guidance_scale):
@@ -250,10 +259,10 @@ class FlashDiffusion(BaseModel):
         x = noisy_sample_init.clone().detach()
         B = x.shape[0]
         fused = x.is_cuda and hasattr(sched, "fused_cfg_step")
+        w = float(guidance_scale)
         if fused:
             x = x.float().contiguous()
             x0_prev = torch.zeros_like(x)
-            w = float(guidance_scale)
         for t in sched.timesteps[start_idx:]:
             timestep = torch.tensor([t], device=x.device).repeat(B)
             x_in = sched.scale_model_input(x, t)
@@ -262,7 +271,7 @@ class FlashDiffusion(BaseModel):
             if fused:
                 sched.fused_cfg_step(eps_c.contiguous(), eps_u.contiguous(), w, t, x, x0_prev)
             else:
-                eps = guidance_scale * eps_c + (1 - guidance_scale) * eps_u
+                eps = w * eps_c + (1 - w) * eps_u
                 x = sched.step(eps, t, x, return_dict=False)[0]
         return x
 
