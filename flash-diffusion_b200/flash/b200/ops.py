@@ -313,8 +313,9 @@ class LinearPack:
         self.cache = cache_of(self.bases[0])
         self.N = sum(b.weight.shape[0] for b in self.bases)
         self.K = self.bases[0].weight.shape[1]
-        if head_pad is not None and head_pad[1] != head_pad[2] and (self.has_lora or geglu):
-            raise NotImplementedError("head padding with LoRA / GEGLU packs")
+        if head_pad is not None and head_pad[1] != head_pad[2] and geglu:
+            raise NotImplementedError("head padding with GEGLU packs")
+        self.N_packed = None
 
     def _w2d(self, b):
         w = b.weight.detach().reshape(b.weight.shape[0], -1)          # Linear or 1x1 Conv2d
@@ -395,16 +396,31 @@ class LinearPack:
             r = next(l.r for l in self.loras if l is not None)
             dev = self.bases[0].weight.device
             n = len(self.layers)
-            a_cat = torch.zeros((n * r, self.K), device=dev)
-            b_blk = torch.zeros((self.N, n * r), device=dev)
-            row = 0
+            padded = self.head_pad is not None and self.head_pad[1] != self.head_pad[2]
+            a_rows, b_rows = [], []
             for i, (l, b) in enumerate(zip(self.loras, self.bases)):
-                nout = b.weight.shape[0]
+                nout_true = b.weight.shape[0]
                 if l is not None:
-                    a_cat[i * r:(i + 1) * r] = l.lora_A["default"].weight.detach().float()
-                    b_blk[row:row + nout, i * r:(i + 1) * r] = l.lora_B["default"].weight.detach().float() * l.scaling
-                row += nout
-            return {"a": raw.cast_scale(a_cat, 1.0), "b": raw.cast_scale(b_blk, 1.0),
+                    A = l.lora_A["default"].weight.detach().float()              # [r, K]
+                    Bm = l.lora_B["default"].weight.detach().float() * l.scaling  # [Nout, r]
+                else:
+                    A = torch.zeros((r, b.weight.shape[1]), device=dev)
+                    Bm = torch.zeros((nout_true, r), device=dev)
+                if padded:
+                    H, d, dp = self.head_pad
+                    if self.pad_cols:       # out-projection: its INPUT columns (A's columns) are head-padded
+                        A = torch.nn.functional.pad(A.reshape(r, H, d), (0, dp - d)).reshape(r, H * dp)
+                    else:                   # q/k/v: OUTPUT rows (B's rows) are head-padded
+                        Bm = torch.nn.functional.pad(Bm.reshape(H, d, r), (0, 0, 0, dp - d)).reshape(H * dp, r)
+                a_rows.append(A)
+                b_rows.append(Bm)
+            a_cat = torch.cat(a_rows, dim=0)                                         # [n*r, K']
+            b_blk = torch.zeros((sum(x.shape[0] for x in b_rows), n * r), device=dev)
+            row = 0
+            for i, Bm in enumerate(b_rows):
+                b_blk[row:row + Bm.shape[0], i * r:(i + 1) * r] = Bm
+                row += Bm.shape[0]
+            return {"a": raw.cast_scale(a_cat.contiguous(), 1.0), "b": raw.cast_scale(b_blk, 1.0),
                     "a_t": raw.cast_scale(a_cat.t().contiguous(), 1.0),
                     "b_t": raw.cast_scale(b_blk.t().contiguous(), 1.0), "r": r}
         return self.cache.get("lora", self.lora_params(), build)
@@ -455,6 +471,8 @@ class _LinearFn(torch.autograd.Function):
 
 def _lora_weight_grads(pack, lp, x, t, dy, dt):
     """dA_i = dt_i^T x ; dB_i = s * dy_i^T t_i   (fp32, in the parameters' layout)."""
+    if pack.head_pad is not None and pack.head_pad[1] != pack.head_pad[2]:
+        raise NotImplementedError("LoRA gradients with head-padded packs (head dim != multiple of 16)")
     r = lp["r"]
     x_t = raw.transpose(x)                      # [K, M]
     dy_t = raw.transpose(dy)                    # [N, M]

@@ -31,6 +31,13 @@ SDXL_UNET_KWARGS = dict(
     cross_attention_dim=2048, transformer_layers_per_block=[1, 2, 10], attention_head_dim=[5, 10, 20],
     use_linear_projection=True, class_embed_type="projection", projection_class_embeddings_input_dim=2816)
 
+SD15_UNET_KWARGS = dict(          # examples/train_flash_sd.py:56-114
+    in_channels=4, out_channels=4,
+    down_block_types=["CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "DownBlock2D"],
+    up_block_types=["UpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D"],
+    block_out_channels=[320, 640, 1280, 1280], layers_per_block=2, cross_attention_dim=768,
+    transformer_layers_per_block=1, attention_head_dim=8, use_linear_projection=True, class_embed_type=None)
+
 TINY_UNET_KWARGS = dict(
     in_channels=4, out_channels=4, down_block_types=["DownBlock2D", "CrossAttnDownBlock2D"],
     up_block_types=["CrossAttnUpBlock2D", "UpBlock2D"], block_out_channels=[64, 128], layers_per_block=1,
@@ -70,6 +77,12 @@ def tiny_discriminator(color_dim=128):
                          nn.Conv2d(32, 1, 4, 1, 0, bias=False), nn.Flatten())
 
 
+def text_only_conditioner():
+    """SD1.5: cross-attention text embedding only (examples/train_flash_sd.py: one CLIP embedder, no vector)."""
+    return ConditionerWrapper([TorchNNEmbedder(TorchNNEmbedderConfig(
+        input_key="text_emb", nn_modules=["torch.nn.Identity"], nn_modules_kwargs=[{}]))])
+
+
 def synthetic_conditioner(fourier_channels=256):
     """text / pooled embeddings through Identity embedders, size/crop ids through
     TimestepsEmbedder — the same slots the CLIP embedders fill in examples/train_flash_sdxl.py:137-195."""
@@ -101,7 +114,7 @@ def synthetic_batch(B, latent_hw, ctx_tokens, ctx_dim, pooled_dim, seed, device=
 
 
 def build_distillation(unet_kwargs, discriminator, device, *, lora_rank=64, K=32, seed=1234, lora_b_std=0.01,
-                       fourier_channels=256, stage=2, lr=1e-5):
+                       fourier_channels=256, stage=2, lr=1e-5, conditioner=None, ucg_keys=("text_emb", "pooled_emb")):
     """teacher / student(LoRA) / discriminator / FlashDiffusion / TrainingPipeline on `device`."""
     with torch.device("meta"):
         teacher = DiffusersUNet2DCondWrapper(**unet_kwargs)
@@ -126,7 +139,7 @@ def build_distillation(unet_kwargs, discriminator, device, *, lora_rank=64, K=32
     probs = [[0.0, 0.0, 0.5, 0.5], [0.1, 0.3, 0.3, 0.3], [0.25, 0.25, 0.25, 0.25], [0.4, 0.2, 0.2, 0.2]][stage]
     cfg = FlashDiffusionConfig(
         K=[K], num_iterations_per_K=[10 ** 9], guidance_scale_min=3.0, guidance_scale_max=13.0,
-        distill_loss_type="l2", ucg_keys=["text_emb", "pooled_emb"], timestep_distribution="mixture",
+        distill_loss_type="l2", ucg_keys=list(ucg_keys), timestep_distribution="mixture",
         mixture_num_components=4, mixture_var=0.5, use_dmd_loss=True, dmd_loss_scale=dmd, distill_loss_scale=1.0,
         adversarial_loss_scale=adv, gan_loss_type="lsgan", mode_probs=[probs], use_teacher_as_real=False,
         use_empty_prompt=False, input_key="image")
@@ -135,7 +148,8 @@ def build_distillation(unet_kwargs, discriminator, device, *, lora_rank=64, K=32
     lcm = LCMScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", subfolder="scheduler",
                                        timestep_spacing="trailing")
     model = FlashDiffusion(cfg, student_denoiser=student, teacher_denoiser=teacher, teacher_noise_scheduler=sched,
-                           sampling_noise_scheduler=lcm, vae=None, conditioner=synthetic_conditioner(fourier_channels),
+                           sampling_noise_scheduler=lcm, vae=None,
+                           conditioner=conditioner if conditioner is not None else synthetic_conditioner(fourier_channels),
                            discriminator=discriminator).to(device)
     pipe = TrainingPipeline(model, TrainingConfig(
         optimizers_name=["AdamW", "AdamW"], learning_rates=[lr, lr],
@@ -146,6 +160,21 @@ def build_distillation(unet_kwargs, discriminator, device, *, lora_rank=64, K=32
 
 def build_sdxl_distillation(device, **kw):
     return build_distillation(SDXL_UNET_KWARGS, sdxl_discriminator(), device, **kw)
+
+
+def sd15_discriminator(color_dim=1280, d=64):
+    """examples/train_flash_sd.py:225-240"""
+    return nn.Sequential(nn.Conv2d(color_dim, d, 4, 2, 1, bias=False), nn.SiLU(True),
+                         nn.Conv2d(d, d * 2, 4, 2, 1, bias=False), nn.GroupNorm(4, d * 2), nn.SiLU(True),
+                         nn.Conv2d(d * 2, 1, 4, 1, 0, bias=False), nn.Flatten())
+
+
+def build_sd15_distillation(device, **kw):
+    """Config 1 objects (SD1.5, LoRA r=128).  Forward / sampling only on GPU this round: the attention backward is
+    built for head dim 64 (SD1.5 has 40/80/160)."""
+    kw.setdefault("lora_rank", 128)
+    return build_distillation(SD15_UNET_KWARGS, sd15_discriminator(), device, conditioner=text_only_conditioner(),
+                              ucg_keys=("text_emb",), **kw)
 
 
 def build_tiny_distillation(device, **kw):

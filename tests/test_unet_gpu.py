@@ -129,3 +129,13 @@ def test_cuda_graph_replay_matches_eager():
     prod.train()
     with torch.no_grad():
         assert not GraphedDenoiser.eligible(prod, x)          # training-mode LoRA module stays eager
+
+
+def test_sd15_lora_student_forward():
+    """SD1.5 student (LoRA r=128 on q/k/v/out, examples/train_flash_sd.py:193-200) with head-padded packs, forward."""
+    from oracle.unet import SD15_KWARGS
+    small15 = dict(SD15_KWARGS, block_out_channels=[64, 128, 256, 256], cross_attention_dim=96, norm_num_groups=32)
+    prod, ora = _pair(small15, lora=True, seed=3)       # heads = 8 -> head dims 8, 16, 32 (8 -> padded to 16)
+    x, t, cond = _inputs(2, 32, 32, 96, 0)
+    with torch.no_grad():
+        assert _rel(prod(x, t, cond), ora(x, t, cond)) < 2e-2

@@ -11,12 +11,18 @@ import torch
 from flash import recipes
 
 dev = torch.device("cuda:0")
-model, _ = recipes.build_sdxl_distillation(dev)
+which = sys.argv[1] if len(sys.argv) > 1 else "sdxl"
+if which == "sdxl":
+    model, _ = recipes.build_sdxl_distillation(dev)
+    hw, ctx, pooled, fwd_flops = 128, 2048, 1280, 6.76e12
+else:
+    model, _ = recipes.build_sd15_distillation(dev)
+    hw, ctx, pooled, fwd_flops = 64, 768, 0, 0.80e12
 model.eval()
 rows = []
 for B in [1, 2, 4, 8, 16, 32]:
-    batch = recipes.synthetic_batch(B, 128, 77, 2048, 1280, seed=B, device=dev)
-    z = torch.randn(B, 4, 128, 128, device=dev)
+    batch = recipes.synthetic_batch(B, hw, 77, ctx, pooled, seed=B, device=dev)
+    z = torch.randn(B, 4, hw, hw, device=dev)
     for _ in range(2):
         model.sample(z, num_steps=4, guidance_scale=1.0, conditioner_inputs=batch)
     torch.cuda.synchronize()
@@ -28,7 +34,7 @@ for B in [1, 2, 4, 8, 16, 32]:
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n
-    flops = 8 * B * 6.76e12          # 4 steps x (cond + uncond) student evaluations, as the reference does
+    flops = 8 * B * fwd_flops        # 4 steps x (cond + uncond) student evaluations, as the reference does
     rows.append({"batch": B, "latency_ms": ms, "images_per_s": B / ms * 1e3, "tflops": flops / ms / 1e9})
     print(rows[-1], flush=True)
-print(json.dumps({"metric": "4-NFE sample latency (SDXL student, LoRA r=64, CFG cond+uncond as reference)", "rows": rows}))
+print(json.dumps({"metric": f"4-NFE sample latency ({which} student, LoRA, CFG cond+uncond as reference)", "rows": rows}))
