@@ -58,6 +58,23 @@ __global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, long long ld, fl
     }
 }
 
+// x [NB*h*w, p*p*Cout] fp32 (columns ordered (pi, qi, c)) -> y [NB, Ckeep, h*p, w*p] fp32
+__global__ void unpatchify_kernel(const float* __restrict__ x, float* __restrict__ y, int NB, int h, int w, int p,
+                                  int Cout, int Ckeep) {
+    const int H = h * p, W = w * p;
+    const long long total = (long long)NB * Ckeep * H * W;
+    FD_GRID_STRIDE(i, total) {
+        const int X = (int)(i % W);
+        long long t = i / W;
+        const int Y = (int)(t % H);
+        t /= H;
+        const int c = (int)(t % Ckeep);
+        const int n = (int)(t / Ckeep);
+        const int hy = Y / p, pi = Y % p, wx = X / p, qi = X % p;
+        y[i] = x[(((long long)n * h + hy) * w + wx) * (p * p * Cout) + (pi * p + qi) * Cout + c];
+    }
+}
+
 // nearest 2x upsample, vectors of 8 channels
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int NB, int H,
                                   int W, int CV) {
@@ -276,6 +293,15 @@ extern "C" int fd_nhwc_to_nchw(const void* x, int32_t x_is_fp32, int64_t ld, flo
         nhwc_to_nchw_kernel<true><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, ld, y, NB, C, H * W);
     else
         nhwc_to_nchw_kernel<false><<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, ld, y, NB, C, H * W);
+    FD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int fd_unpatchify(const float* x, float* y, int32_t NB, int32_t h, int32_t w, int32_t p, int32_t Cout,
+                             int32_t Ckeep, void* stream) {
+    FD_CHECK_ARG(Ckeep <= Cout && p > 0, "fd_unpatchify: bad channels");
+    const long long total = (long long)NB * Ckeep * h * p * w * p;
+    unpatchify_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(x, y, NB, h, w, p, Cout, Ckeep);
     FD_CHECK_LAUNCH();
     return 0;
 }

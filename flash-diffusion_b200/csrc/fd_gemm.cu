@@ -42,6 +42,10 @@ struct GemmKParams {
     const float* ln_colsum;
     float ln_inv_c, ln_eps;
     float* rowstats_out;
+    int act;
+    const float* rowscale;
+    int rows_per_group_scale;
+    long long ldrs;
 };
 
 template <int BN>
@@ -164,6 +168,21 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int row, in
         }
     }
     if (!row_ok) return;
+
+    if (p.act == 1) {   // gelu (tanh approximation): 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const float x = v[j];
+            const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+            v[j] = 0.5f * x * (1.0f + tanhf(u));
+        }
+    }
+    if (p.rowscale != nullptr) {
+        const float* sv = p.rowscale + (long long)(row / p.rows_per_group_scale) * p.ldrs + col0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+            if (col0 + j < N) v[j] *= __ldg(sv + j);
+    }
 
     if (p.geglu) {
         // interleaved packing: cols [0,16) value, [16,32) gate -> 16 outputs at col0/2
@@ -739,6 +758,11 @@ extern "C" int fd_gemm(const FdGemmArgs* a, void* stream_) {
     p.ln_inv_c = a->ln_inv_c;
     p.ln_eps = a->ln_eps;
     p.rowstats_out = a->rowstats_out;
+    p.act = a->act;
+    p.rowscale = a->rowscale;
+    p.rows_per_group_scale = a->rows_per_group_scale;
+    p.ldrs = a->ldrs > 0 ? a->ldrs : a->N;
+    FD_CHECK_ARG(!a->rowscale || a->rows_per_group_scale > 0, "fd_gemm: rowscale needs rows_per_group_scale");
     FD_CHECK_ARG(!a->ln_stats || (a->ln_colsum && a->K2 == 0), "fd_gemm: LayerNorm fold needs ln_colsum and no K2 segment");
     FD_CHECK_ARG(!a->rowstats_out || !a->out_fp32, "fd_gemm: rowstats_out needs a bf16 output");
     if (a->rowstats_out) FD_CHECK_CUDA(cudaMemsetAsync(a->rowstats_out, 0, sizeof(float) * 2 * (size_t)a->M, stream));

@@ -253,6 +253,61 @@ __global__ void ln_fwd_kernel(const bf16* __restrict__ x, const float* __restric
     }
 }
 
+// y = LN(x) * (1 + scale[b]) + shift[b]   (AdaLN modulation, no affine), one warp per row
+__global__ void ln_modulate_kernel(const bf16* __restrict__ x, const float* __restrict__ scale,
+                                   const float* __restrict__ shift, long long ld_mod, bf16* __restrict__ y, int rows,
+                                   int C, int rows_per_batch, float eps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= rows) return;
+    const int nvec = C >> 3;
+    const bf16* xr = x + (long long)warp * C;
+    float v[LN_MAXV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nvec) {
+            load8(xr + vi * 8, v[i]);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += v[i][j];
+        }
+    }
+    const float mean = warp_sum(s) / C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nvec) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float d = v[i][j] - mean;
+                q += d * d;
+            }
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / C + eps);
+    const float* sc = scale + (long long)(warp / rows_per_batch) * ld_mod;
+    const float* sh = shift + (long long)(warp / rows_per_batch) * ld_mod;
+    bf16* yr = y + (long long)warp * C;
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int vi = lane + i * 32;
+        if (vi < nvec) {
+            const float4 a0 = __ldg(reinterpret_cast<const float4*>(sc + vi * 8));
+            const float4 a1 = __ldg(reinterpret_cast<const float4*>(sc + vi * 8 + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(sh + vi * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(sh + vi * 8 + 4));
+            const float sca[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float shf[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * (1.0f + sca[j]) + shf[j];
+            store8(yr + vi * 8, o);
+        }
+    }
+}
+
 __global__ void ln_bwd_kernel(const bf16* __restrict__ x, const float* __restrict__ stats,
                               const float* __restrict__ gamma, const bf16* __restrict__ dy,
                               bf16* __restrict__ dx, int rows, int C) {
@@ -365,6 +420,19 @@ extern "C" int fd_layernorm_fwd(const void* x, const float* gamma, const float* 
     const int blocks = (rows + warps_per_block - 1) / warps_per_block;
     ln_fwd_kernel<<<blocks, warps_per_block * 32, 0, stream>>>((const bf16*)x, gamma, beta, (bf16*)y,
                                                                stats, rows, C, eps);
+    FD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int fd_layernorm_modulate(const void* x, const float* scale, const float* shift, int64_t ld_mod, void* y,
+                                     int32_t rows, int32_t C, int32_t rows_per_batch, float eps, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FD_CHECK_ARG(C % 8 == 0 && C <= 8 * 32 * LN_MAXV && ld_mod % 4 == 0 && rows_per_batch > 0,
+                 "fd_layernorm_modulate: bad C=%d / ld_mod", C);
+    const int warps_per_block = 8;
+    const int blocks = (rows + warps_per_block - 1) / warps_per_block;
+    ln_modulate_kernel<<<blocks, warps_per_block * 32, 0, stream>>>((const bf16*)x, scale, shift, ld_mod, (bf16*)y,
+                                                                    rows, C, rows_per_batch, eps);
     FD_CHECK_LAUNCH();
     return 0;
 }

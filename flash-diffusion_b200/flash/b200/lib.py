@@ -34,6 +34,8 @@ class FdGemmArgs(Structure):
         ("force_bn", c_int32),
         ("ln_stats", c_void_p), ("ln_colsum", c_void_p), ("ln_inv_c", c_float), ("ln_eps", c_float),
         ("rowstats_out", c_void_p),
+        ("act", c_int32),
+        ("rowscale", c_void_p), ("rows_per_group_scale", c_int32), ("ldrs", c_int64),
     ]
 
 

@@ -26,7 +26,8 @@ def _req(t, dtype, name):
 
 
 def gemm(a1, b1, *, a2=None, b2=None, bias=None, rowvec=None, rows_per_group=0, geglu=False,
-         residual=None, out=None, out_fp32=False, conv=None, M=None, force_bn=0, ln=None, rowstats=None):
+         residual=None, out=None, out_fp32=False, conv=None, M=None, force_bn=0, ln=None, rowstats=None,
+         act=0, rowscale=None, rows_per_group_scale=0):
     """acc = a1 @ b1.T (+ a2 @ b2.T) with the fused epilogue of fd_gemm (include/flashb200.h).
 
     a1: [M, K1] bf16 (or, with conv=dict(NB_in,H,W,C,taps), an NHWC tensor), b1: [N, K1] bf16.
@@ -80,6 +81,12 @@ def gemm(a1, b1, *, a2=None, b2=None, bias=None, rowvec=None, rows_per_group=0, 
         assert st.dtype == torch.float32 and st.shape == (M, 2) and st.is_contiguous()
         assert colsum.dtype == torch.float32 and colsum.numel() == N and colsum.is_contiguous()
         args.ln_stats, args.ln_colsum, args.ln_inv_c, args.ln_eps = ptr(st), ptr(colsum), 1.0 / C, eps
+    args.act = act
+    if rowscale is not None:
+        # AdaLN gate: acc *= rowscale[row // rows_per_group_scale, :]
+        assert rowscale.dtype == torch.float32 and rowscale.dim() == 2 and rowscale.stride(1) == 1
+        assert rowscale.shape[1] == n_out and rows_per_group_scale > 0
+        args.rowscale, args.rows_per_group_scale, args.ldrs = ptr(rowscale), rows_per_group_scale, rowscale.stride(0)
     if rowstats is not None:
         assert rowstats.dtype == torch.float32 and rowstats.shape == (M, 2) and rowstats.is_contiguous()
         args.rowstats_out = ptr(rowstats)
@@ -124,6 +131,28 @@ def layernorm_fwd(x, gamma, beta, eps, save_stats=False):
     check(lib.fd_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(stats), c_int32(rows), c_int32(C),
                                c_float(eps), stream_ptr()), "fd_layernorm_fwd")
     return (y, stats) if save_stats else y
+
+
+def layernorm_modulate(x, scale, shift, rows_per_batch, eps):
+    """y = LayerNorm(x) * (1 + scale[b]) + shift[b]; scale/shift fp32 [B, C] views with equal row stride."""
+    lib = load(); _req(x, BF16, "x"); _req(scale, torch.float32, "scale"); _req(shift, torch.float32, "shift")
+    rows, C = x.shape
+    assert x.is_contiguous() and scale.stride(1) == 1 and shift.stride(1) == 1 and scale.stride(0) == shift.stride(0)
+    y = torch.empty_like(x)
+    check(lib.fd_layernorm_modulate(ptr(x), ptr(scale), ptr(shift), c_int64(scale.stride(0)), ptr(y), c_int32(rows),
+                                    c_int32(C), c_int32(rows_per_batch), c_float(eps), stream_ptr()),
+          "fd_layernorm_modulate")
+    return y
+
+
+def unpatchify(x, NB, h, w, p, Cout, Ckeep):
+    """x [NB*h*w, p*p*Cout] fp32 -> [NB, Ckeep, h*p, w*p] fp32"""
+    lib = load(); _req(x, torch.float32, "x")
+    assert x.is_contiguous() and x.shape == (NB * h * w, p * p * Cout)
+    y = torch.empty((NB, Ckeep, h * p, w * p), device=x.device, dtype=torch.float32)
+    check(lib.fd_unpatchify(ptr(x), ptr(y), c_int32(NB), c_int32(h), c_int32(w), c_int32(p), c_int32(Cout),
+                            c_int32(Ckeep), stream_ptr()), "fd_unpatchify")
+    return y
 
 
 def layernorm_bwd(x, stats, gamma, dy):

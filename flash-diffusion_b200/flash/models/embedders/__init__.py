@@ -5,8 +5,9 @@ fed synthetic embeddings through `TorchNNEmbedder` / `TimestepsEmbedder` (SURVEY
 """
 from .base import BaseConditioner, BaseConditionerConfig
 from .conditioners_wrapper import ConditionerWrapper
+from .precomputed import PrecomputedTextEmbedder, PrecomputedTextEmbedderConfig
 from .timesteps import TimestepsEmbedder, TimestepsEmbedderConfig
 from .torch_nn import TorchNNEmbedder, TorchNNEmbedderConfig
 
-__all__ = ["BaseConditioner", "BaseConditionerConfig", "ConditionerWrapper", "TimestepsEmbedder",
+__all__ = ["PrecomputedTextEmbedder", "PrecomputedTextEmbedderConfig", "BaseConditioner", "BaseConditionerConfig", "ConditionerWrapper", "TimestepsEmbedder",
            "TimestepsEmbedderConfig", "TorchNNEmbedder", "TorchNNEmbedderConfig"]

@@ -1,0 +1,295 @@
+"""B200-native `DiffusersTransformer2DWrapper` — PixArt-alpha DiT (reference src/flash/models/transformers/tranformers.py:9-100
+with the custom `AdaLayerNormSingle`, src/flash/models/transformers/utils.py:8-102; constructor kwargs as at
+examples/train_flash_pixart.py:65-86).
+
+Round-1 scope: FORWARD (teacher evaluation, LoRA student evaluation, `FlashDiffusion.sample`) on the hand-written
+kernels; the backward of this block type (AdaLN-modulate / gate kernels, attention backward for head dim 72 with a
+key-padding mask) is the next row, so a call that needs gradients raises.
+
+Kernel mapping (UPSTREAM diffusers math, restated in oracle/dit.py):
+  PatchEmbed conv 2x2/2    space-to-depth + 4-tap implicit-GEMM (fd_gemm conv mode) with the sin-cos position table added
+                           as the residual of the same epilogue
+  adaLN-single MLPs        small fd_gemm launches (M = batch)
+  caption projection       fd_gemm with the gelu-tanh epilogue, then fd_gemm
+  LN * (1+scale) + shift   fd_layernorm_modulate
+  attention (d = 72)       q/k/v packs zero-padded to 80 channels per head -> fd_attn_fwd_generic (T5 key-padding mask
+                           as per-sample valid lengths)
+  gate * f(x) + x          fd_gemm epilogue: bias -> (gelu-tanh) -> per-sample gate vector -> residual
+  un-patchify              fd_unpatchify (keeps the first `in_channels` channels, as the reference slices them)
+"""
+from typing import Dict, Optional, Union
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from ...b200 import ops, raw
+from ...b200.ops import LinearPack, cache_of
+from ..lora import inject_lora
+from ..unets.unet import TimestepEmbedding, _Container
+
+
+def _sincos_1d(embed_dim, pos):
+    omega = 1.0 / 10000 ** (np.arange(embed_dim // 2, dtype=np.float64) / (embed_dim / 2.0))
+    out = np.einsum("m,d->md", pos.reshape(-1), omega)
+    return np.concatenate([np.sin(out), np.cos(out)], axis=1)
+
+
+def sincos_2d(embed_dim, grid_size, base_size, interpolation_scale):
+    """UPSTREAM diffusers `get_2d_sincos_pos_embed` (PixArt position table; not a parameter, not in the state dict)."""
+    g = np.arange(grid_size, dtype=np.float32) / (grid_size / base_size) / interpolation_scale
+    grid = np.stack(np.meshgrid(g, g), axis=0).reshape(2, 1, grid_size, grid_size)
+    return np.concatenate([_sincos_1d(embed_dim // 2, grid[0]), _sincos_1d(embed_dim // 2, grid[1])], axis=1)
+
+
+class PatchEmbed(_Container):
+    def __init__(self, sample_size, patch_size, in_channels, embed_dim):
+        super().__init__()
+        self.proj = nn.Conv2d(in_channels, embed_dim, patch_size, stride=patch_size)
+        grid = sample_size // patch_size
+        pe = sincos_2d(embed_dim, grid, base_size=grid, interpolation_scale=max(sample_size // 64, 1))
+        self.register_buffer("pos_embed", torch.from_numpy(pe).float()[None], persistent=False)
+
+
+class AdaLayerNormSingle(_Container):
+    """reference src/flash/models/transformers/utils.py:8-102 (same attribute / key names)."""
+
+    def __init__(self, time_embed_dim, timesteps_embedding_num_channels=256, projection_class_embeddings_input_dim=None,
+                 use_concat_conditioning=False, num_vector_conditionings=None):
+        super().__init__()
+        self.num_channels = timesteps_embedding_num_channels
+        self.timestep_embedder = TimestepEmbedding(timesteps_embedding_num_channels, time_embed_dim)
+        self.projection_class_embeddings_input_dim = projection_class_embeddings_input_dim
+        self.use_concat_conditioning = use_concat_conditioning
+        self.num_vector_conditionings = num_vector_conditionings
+        if projection_class_embeddings_input_dim is not None:
+            if not use_concat_conditioning:
+                self.add_embedding = TimestepEmbedding(projection_class_embeddings_input_dim, time_embed_dim)
+            else:
+                assert num_vector_conditionings is not None, \
+                    "num_vector_conditionings must be provided if use_concat_conditioning is True"
+                self.add_embedding = nn.ModuleList(
+                    [TimestepEmbedding(projection_class_embeddings_input_dim, time_embed_dim // num_vector_conditionings)
+                     for _ in range(num_vector_conditionings)])
+        self.linear = nn.Linear(time_embed_dim, 6 * time_embed_dim, bias=True)
+
+
+class TextProjection(_Container):
+    def __init__(self, in_features, hidden):
+        super().__init__()
+        self.linear_1 = nn.Linear(in_features, hidden)
+        self.linear_2 = nn.Linear(hidden, hidden)
+
+
+class Attention(_Container):
+    def __init__(self, dim, cross_dim, heads, dim_head, bias):
+        super().__init__()
+        inner = heads * dim_head
+        self.heads, self.dim_head, self.is_cross = heads, dim_head, cross_dim is not None
+        self.to_q = nn.Linear(dim, inner, bias=bias)
+        self.to_k = nn.Linear(cross_dim or dim, inner, bias=bias)
+        self.to_v = nn.Linear(cross_dim or dim, inner, bias=bias)
+        self.to_out = nn.ModuleList([nn.Linear(inner, dim), nn.Dropout(0.0)])
+
+
+class GELUProj(_Container):
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out)
+
+
+class FeedForward(_Container):
+    def __init__(self, dim, mult=4):
+        super().__init__()
+        self.net = nn.ModuleList([GELUProj(dim, dim * mult), nn.Dropout(0.0), nn.Linear(dim * mult, dim)])
+
+
+class AdaBlock(_Container):
+    def __init__(self, dim, heads, dim_head, cross_dim, bias):
+        super().__init__()
+        self.scale_shift_table = nn.Parameter(torch.randn(6, dim) / dim ** 0.5)
+        self.attn1 = Attention(dim, None, heads, dim_head, bias)
+        self.attn2 = Attention(dim, cross_dim, heads, dim_head, bias)
+        self.ff = FeedForward(dim)
+
+
+class DiffusersTransformer2DWrapper(nn.Module):
+    def __init__(self, time_embed_dim: int = 256, timesteps_embedding_num_channels: int = 256,
+                 projection_class_embeddings_input_dim: Optional[int] = None,
+                 use_concat_vector_conditioning: bool = False, num_vector_conditionings: Optional[int] = None,
+                 sample_size=128, num_layers=28, attention_head_dim=72, in_channels=4, out_channels=8, patch_size=2,
+                 attention_bias=True, num_attention_heads=16, cross_attention_dim=1152,
+                 activation_fn="gelu-approximate", norm_type="ada_norm_single", norm_elementwise_affine=False,
+                 norm_eps=1e-6, caption_channels=4096, **unused):
+        super().__init__()
+        if norm_type != "ada_norm_single" or activation_fn != "gelu-approximate" or norm_elementwise_affine \
+                or patch_size != 2:
+            raise NotImplementedError("only the PixArt-alpha Transformer2DModel variant of the examples is built")
+        D = num_attention_heads * attention_head_dim
+        self.patch_size, self.out_channels, self.in_channels, self.norm_eps = patch_size, out_channels, in_channels, norm_eps
+        self.inner_dim, self.sample_size = D, sample_size
+        self.pos_embed = PatchEmbed(sample_size, patch_size, in_channels, D)
+        self.adaln_single = AdaLayerNormSingle(time_embed_dim, timesteps_embedding_num_channels,
+                                               projection_class_embeddings_input_dim, use_concat_vector_conditioning,
+                                               num_vector_conditionings)
+        self.caption_projection = TextProjection(caption_channels, D)
+        self.transformer_blocks = nn.ModuleList(
+            [AdaBlock(D, num_attention_heads, attention_head_dim, cross_attention_dim, attention_bias)
+             for _ in range(num_layers)])
+        self.scale_shift_table = nn.Parameter(torch.randn(2, D) / D ** 0.5)
+        self.proj_out = nn.Linear(D, patch_size * patch_size * out_channels)
+        self.__dict__["_packs"] = {}
+
+    # ------------------------------------------------------------------------------------ helpers
+    def _pack(self, key, make):
+        packs = self.__dict__.setdefault("_packs", {})
+        if key not in packs:
+            packs[key] = make()
+        return packs[key]
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = {} if k == "_packs" else copy.deepcopy(v, memo)
+        for m in new.modules():
+            m.__dict__.pop("_fd_cache", None)
+        return new
+
+    def freeze(self):
+        self.eval()
+        for p in self.parameters():
+            p.requires_grad = False
+
+    def add_adapter(self, lora_config):
+        """LoRA on the nn.Linear targets (peft would also wrap the Conv2d `pos_embed.proj`, which this round does not)."""
+        inject_lora(self, lora_config)
+        self.__dict__["_packs"] = {}
+        return self
+
+    @staticmethod
+    def _lin(x, pack: LinearPack, *, residual=None, act=0, rowscale=None, rows_per_group_scale=0, out_fp32=False):
+        """(LoRA-aware) GEMM with the DiT epilogue: bias -> act -> gate -> residual."""
+        p = pack.pack()
+        a2 = b2 = None
+        if pack.has_lora:
+            lp = pack.pack_lora()
+            a2, b2 = raw.gemm(x, lp["a"]), lp["b"]
+        return raw.gemm(x, p["w"], a2=a2, b2=b2, bias=p["b"], residual=residual, act=act, rowscale=rowscale,
+                        rows_per_group_scale=rows_per_group_scale, out_fp32=out_fp32)
+
+    def _mlp_rows(self, x_bf16, te: TimestepEmbedding, key):
+        """TimestepEmbedding on [B, in] rows: linear_1 -> SiLU -> linear_2, fp32 out."""
+        l1 = self._pack((key, 1), lambda: LinearPack(te.linear_1))
+        l2 = self._pack((key, 2), lambda: LinearPack(te.linear_2))
+        h = raw.silu_f32_to_bf16(self._lin(x_bf16, l1, out_fp32=True))
+        return self._lin(h, l2, out_fp32=True)
+
+    def _adaln(self, timestep, vector, B, dev):
+        ad = self.adaln_single
+        t_emb = raw.timestep_embedding(timestep, ad.num_channels)
+        emb = self._mlp_rows(t_emb, ad.timestep_embedder, "te")
+        if ad.projection_class_embeddings_input_dim is not None:
+            if vector is None:
+                raise ValueError("vector conditioning is required by this adaln_single configuration")
+            v = raw.cast_scale(vector.detach().float().contiguous(), 1.0)
+            if isinstance(ad.add_embedding, nn.ModuleList):
+                n = ad.num_vector_conditionings
+                w = v.shape[1] // n
+                parts = [self._mlp_rows(v[:, i * w:(i + 1) * w].contiguous(), ad.add_embedding[i], ("ae", i))
+                         for i in range(n)]
+                emb = emb + torch.cat(parts, dim=1)
+            else:
+                emb = emb + self._mlp_rows(v, ad.add_embedding, "ae")
+        t6 = self._lin(raw.silu_f32_to_bf16(emb), self._pack("adaln_linear", lambda: LinearPack(ad.linear)), out_fp32=True)
+        return t6, emb
+
+    def _attention(self, a: Attention, x, ctx, B, kv_len, **epi):
+        H, d = a.heads, a.dim_head
+        dp = (d + 15) // 16 * 16
+        hp = (H, d, dp) if dp != d else None
+        inner = H * dp
+        if not a.is_cross:
+            qkv = self._lin(x, self._pack(("qkv", id(a)), lambda: LinearPack([a.to_q, a.to_k, a.to_v], head_pad=hp)))
+            o = ops.attention_self(qkv.view(B, -1, 3 * inner), H, head_dim=dp, scale=d ** -0.5)
+        else:
+            q = self._lin(x, self._pack(("q", id(a)), lambda: LinearPack(a.to_q, head_pad=hp)))
+            kv = self._lin(ctx, self._pack(("kv", id(a)), lambda: LinearPack([a.to_k, a.to_v], head_pad=hp)))
+            o = ops.attention_cross(q.view(B, -1, inner), kv.view(B, -1, 2 * inner), H, head_dim=dp, scale=d ** -0.5,
+                                    kv_len=kv_len)
+        return self._lin(o.view(-1, inner),
+                         self._pack(("o", id(a)), lambda: LinearPack(a.to_out[0], head_pad=hp, pad_cols=True)), **epi)
+
+    # ------------------------------------------------------------------------------------ forward
+    def forward(self, sample: torch.Tensor, timestep: Union[torch.Tensor, float, int],
+                conditioning: Dict[str, torch.Tensor], hidden_states_masks: Optional[torch.Tensor] = None,
+                *args, **kwargs):
+        assert isinstance(conditioning, dict), "conditionings must be a dictionary"
+        if not sample.is_cuda:
+            raise RuntimeError("DiffusersTransformer2DWrapper runs only on CUDA (B200) tensors: there is no CPU fallback")
+        if torch.is_grad_enabled() and (sample.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError("PixArt DiT backward (AdaLN / gate kernels, attention backward for d=72 + mask) is "
+                                      "the next row; call under torch.no_grad()")
+        cond = conditioning["cond"]
+        vector, crossattn, concat = cond.get("vector"), cond.get("crossattn"), cond.get("concat")
+        mask = cond.get("attention_mask")
+        c_keep = sample.shape[1]
+        if concat is not None:
+            sample = torch.cat([sample, concat], dim=1)
+        B, Cin, H, W = sample.shape
+        dev, p, D = sample.device, self.patch_size, self.inner_dim
+        hh, ww = H // p, W // p
+        N = hh * ww
+        with torch.no_grad():
+            if not torch.is_tensor(timestep):
+                timestep = torch.tensor([float(timestep)], dtype=torch.float32, device=dev)
+            timestep = timestep.to(device=dev, dtype=torch.float32).reshape(-1)
+            if timestep.numel() == 1 and B > 1:
+                timestep = timestep.expand(B)
+            timestep = timestep.contiguous()
+            t6, emb = self._adaln(timestep, vector, B, dev)
+            # caption projection (gelu-tanh in the epilogue of linear_1)
+            cp = self.caption_projection
+            T = crossattn.shape[1]
+            c0 = raw.cast_scale(crossattn.detach().float().contiguous().view(B * T, -1), 1.0)
+            c1 = self._lin(c0, self._pack("cp1", lambda: LinearPack(cp.linear_1)), act=1)
+            ctx = self._lin(c1, self._pack("cp2", lambda: LinearPack(cp.linear_2)))
+            kv_len = None
+            if mask is not None:      # T5 padding mask (ones then zeros): per-sample number of valid keys
+                kv_len = mask.to(device=dev).reshape(B, T).sum(dim=1).to(torch.int32).contiguous()
+            # patch embedding: 2x2 stride-2 conv == 4-tap implicit GEMM over the space-to-depth image (+ position table)
+            cpad = (Cin + 7) // 8 * 8
+            x = raw.nchw_to_nhwc(sample.float(), cpad).view(B * H * W, cpad)
+            x = raw.space_to_depth(x, B, H, W, cpad)
+            pe = self.pos_embed
+
+            def build_patch():
+                wt = pe.proj.weight.detach().float()                      # [D, Cin, 2, 2]
+                buf = torch.zeros((D, 4, 64), device=dev)
+                buf[:, :, :Cin] = wt.permute(0, 2, 3, 1).reshape(D, 4, Cin)
+                pos = pe.pos_embed[0, :N].to(dev)
+                return {"w": raw.cast_scale(buf.reshape(D, 256), 1.0), "b": pe.proj.bias.detach().float().contiguous(),
+                        "pos": raw.cast_scale(pos.contiguous(), 1.0)}
+            pk = cache_of(pe.proj).get(("patch", N), [pe.proj.weight, pe.proj.bias], build_patch)
+            pos_b = self._pack(("pos_tiled", B, N), lambda: pk["pos"].repeat(B, 1).contiguous())
+            taps = [(ph * B, 0, 0) for ph in range(4)]
+            h = raw.gemm(x, pk["w"], bias=pk["b"], residual=pos_b, M=B * N,
+                         conv=dict(NB_in=4 * B, H=hh, W=ww, C=cpad, taps=taps))
+            # AdaLN parameters of every block in one small op: [L, B, 6, D]
+            tables = self._pack("tables", lambda: torch.stack([b.scale_shift_table.detach().float()
+                                                               for b in self.transformer_blocks]))
+            mods = (tables[:, None] + t6.view(1, B, 6, D)).contiguous()
+            for li, blk in enumerate(self.transformer_blocks):
+                m = mods[li]                                              # [B, 6, D]: shift/scale/gate msa, mlp
+                n1 = raw.layernorm_modulate(h, m[:, 1], m[:, 0], N, self.norm_eps)
+                h = self._attention(blk.attn1, n1, None, B, None, residual=h, rowscale=m[:, 2], rows_per_group_scale=N)
+                h = self._attention(blk.attn2, h, ctx, B, kv_len, residual=h)
+                n2 = raw.layernorm_modulate(h, m[:, 4], m[:, 3], N, self.norm_eps)
+                f = self._lin(n2, self._pack(("ff1", id(blk)), lambda: LinearPack(blk.ff.net[0].proj)), act=1)
+                h = self._lin(f, self._pack(("ff2", id(blk)), lambda: LinearPack(blk.ff.net[2])), residual=h,
+                              rowscale=m[:, 5], rows_per_group_scale=N)
+            fin = (self.scale_shift_table.detach().float()[None] + emb[:, None]).contiguous()     # [B, 2, D]
+            nf = raw.layernorm_modulate(h, fin[:, 1], fin[:, 0], N, self.norm_eps)
+            out = self._lin(nf, self._pack("proj_out", lambda: LinearPack(self.proj_out)), out_fp32=True)
+            return raw.unpatchify(out, B, hh, ww, p, self.out_channels, c_keep)

@@ -177,6 +177,53 @@ def build_sd15_distillation(device, **kw):
                               ucg_keys=("text_emb",), **kw)
 
 
+PIXART_KWARGS = dict(   # examples/train_flash_pixart.py:65-86
+    sample_size=128, num_layers=28, attention_head_dim=72, in_channels=4, out_channels=8, patch_size=2,
+    attention_bias=True, num_attention_heads=16, cross_attention_dim=1152, activation_fn="gelu-approximate",
+    num_embeds_ada_norm=1000, norm_type="ada_norm_single", norm_elementwise_affine=False, norm_eps=1e-6,
+    caption_channels=4096, projection_class_embeddings_input_dim=256, time_embed_dim=1152,
+    timesteps_embedding_num_channels=256, use_concat_vector_conditioning=True, num_vector_conditionings=3)
+
+
+def build_pixart_sampler(device, lora_rank=64, seed=1234):
+    """PixArt-alpha student (LoRA on the Linear targets of examples/train_flash_pixart.py:237-256) inside a
+    FlashDiffusion for the few-step sampler (config 5).  Training for this backbone is the next row."""
+    from .models.embedders import PrecomputedTextEmbedder, PrecomputedTextEmbedderConfig
+    from .models.transformers import DiffusersTransformer2DWrapper
+    with torch.device("meta"):
+        teacher = DiffusersTransformer2DWrapper(**PIXART_KWARGS)
+    teacher = teacher.to_empty(device=device)
+    init_random_(teacher, seed)
+    from .models.transformers.transformers import sincos_2d
+    teacher.pos_embed.pos_embed = torch.from_numpy(sincos_2d(1152, 64, 64, 2)).float()[None].to(device)
+    student = copy.deepcopy(teacher)
+    student.add_adapter(LoraConfig(r=lora_rank, lora_alpha=8, target_modules=[
+        "to_k", "to_q", "to_v", "to_out.0", "net.2", "linear", "linear_1", "linear_2"]))
+    teacher.freeze()
+    conditioner = ConditionerWrapper([
+        PrecomputedTextEmbedder(PrecomputedTextEmbedderConfig(input_key="text_emb", mask_key="text_mask")),
+        TimestepsEmbedder(TimestepsEmbedderConfig(input_key="resolution", num_channels=256)),
+        TimestepsEmbedder(TimestepsEmbedderConfig(input_key="aspect_ratio", num_channels=256))])
+    cfg = FlashDiffusionConfig(K=[32], num_iterations_per_K=[10 ** 9], distill_loss_type="l2", ucg_keys=["text_emb"],
+                               use_dmd_loss=False, gan_loss_type="lsgan", input_key="image")
+    sched = DPMSolverMultistepScheduler.from_pretrained("PixArt-alpha/PixArt-XL-2-1024-MS", subfolder="scheduler",
+                                                        timestep_spacing="trailing")
+    lcm = LCMScheduler.from_pretrained("PixArt-alpha/PixArt-XL-2-1024-MS", subfolder="scheduler",
+                                       timestep_spacing="trailing")
+    disc = nn.Sequential(nn.Conv2d(4, 8, 4, 2, 1, bias=False), nn.Flatten())
+    model = FlashDiffusion(cfg, student_denoiser=student, teacher_denoiser=teacher, teacher_noise_scheduler=sched,
+                           sampling_noise_scheduler=lcm, vae=None, conditioner=conditioner, discriminator=disc).to(device)
+    return model
+
+
+def pixart_batch(B, seed, device, tokens=120, valid=77):
+    g = torch.Generator().manual_seed(seed)
+    batch = {"image": torch.randn(B, 4, 128, 128, generator=g), "text_emb": torch.randn(B, tokens, 4096, generator=g),
+             "text_mask": (torch.arange(tokens)[None] < valid).long().repeat(B, 1),
+             "resolution": torch.tensor([[1024., 1024.]] * B), "aspect_ratio": torch.tensor([[1.0]] * B)}
+    return {k: v.to(device) for k, v in batch.items()}
+
+
 def build_tiny_distillation(device, **kw):
     kw.setdefault("lora_rank", 64)
     kw.setdefault("K", 4)

@@ -88,6 +88,11 @@ typedef struct {
     /* LayerNorm fold */
     const float* ln_stats; const float* ln_colsum; float ln_inv_c; float ln_eps;
     float* rowstats_out;
+    /* DiT epilogue: act (0 none, 1 gelu-tanh) after the bias, then acc *= rowscale[row / rows_per_group_scale, :N]
+     * (fp32, row stride ldrs) before the residual add — the AdaLN gate of PixArt / SD3 blocks
+     * (UPSTREAM BasicTransformerBlock(ada_norm_single): hidden = gate * attn(...) + hidden). */
+    int32_t act;
+    const float* rowscale; int32_t rows_per_group_scale; int64_t ldrs;
 } FdGemmArgs;
 int fd_gemm(const FdGemmArgs* args, void* stream);
 
@@ -115,6 +120,11 @@ int fd_layernorm_fwd(const void* x, const float* gamma, const float* beta, void*
                      void* stream);
 int fd_layernorm_bwd(const void* x, const float* stats, const float* gamma, const void* dy,
                      void* dx, int32_t rows, int32_t C, void* stream);
+/* AdaLN modulation: y = LayerNorm(x) (no affine) * (1 + scale[b]) + shift[b], b = row / rows_per_batch;
+ * scale / shift fp32 with row stride ld_mod.  UPSTREAM BasicTransformerBlock(norm_type="ada_norm_single") and
+ * Transformer2DModel output norm (reference src/flash/models/transformers/tranformers.py:83-92). */
+int fd_layernorm_modulate(const void* x, const float* scale, const float* shift, int64_t ld_mod, void* y,
+                          int32_t rows, int32_t C, int32_t rows_per_batch, float eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Attention (softmax(Q K^T / sqrt(d)) V), d = 64, bf16, fp32 softmax.
@@ -157,6 +167,10 @@ int fd_nchw_to_nhwc(const float* x, void* y, int32_t NB, int32_t C, int32_t H, i
 /* NHWC (fp32 or bf16 rows of ld elements, first C valid) -> NCHW fp32. */
 int fd_nhwc_to_nchw(const void* x, int32_t x_is_fp32, int64_t ld, float* y, int32_t NB, int32_t C,
                     int32_t H, int32_t W, void* stream);
+/* DiT un-patchify: x [NB*h*w, p*p*Cout] fp32 (token rows, columns ordered (p, q, c)) -> y NCHW fp32
+ * [NB, Ckeep, h*p, w*p] keeping the first Ckeep channels (reference tranformers.py:92 slices `[:, :in_channels]`). */
+int fd_unpatchify(const float* x, float* y, int32_t NB, int32_t h, int32_t w, int32_t p, int32_t Cout, int32_t Ckeep,
+                  void* stream);
 /* nearest-neighbour 2x upsample, NHWC bf16 (UPSTREAM Upsample2D) */
 int fd_upsample2x(const void* x, void* y, int32_t NB, int32_t H, int32_t W, int32_t C,
                   void* stream);

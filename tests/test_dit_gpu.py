@@ -1,0 +1,122 @@
+"""GPU parity of the PixArt-alpha DiT path (DiffusersTransformer2DWrapper, forward) against the fp32 oracle DiT."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(sample_size=32, num_layers=2, attention_head_dim=24, in_channels=4, out_channels=8, patch_size=2,
+             attention_bias=True, num_attention_heads=4, cross_attention_dim=96, activation_fn="gelu-approximate",
+             norm_type="ada_norm_single", norm_elementwise_affine=False, norm_eps=1e-6, caption_channels=64,
+             projection_class_embeddings_input_dim=8, time_embed_dim=96, timesteps_embedding_num_channels=32,
+             use_concat_vector_conditioning=True, num_vector_conditionings=3)
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+def _pair(kwargs, seed=0):
+    from flash.models.transformers import DiffusersTransformer2DWrapper
+    from oracle.dit import PixArtTransformerOracle
+    torch.manual_seed(seed)
+    ora = PixArtTransformerOracle(**kwargs)
+    with torch.no_grad():
+        for n, p in ora.named_parameters():
+            if p.dim() >= 2 and "scale_shift_table" not in n:
+                p.normal_(0, 1.0 / p[0].numel() ** 0.5)
+            elif n.endswith("bias"):
+                p.normal_(0, 0.05)
+    with torch.device("meta"):
+        prod = DiffusersTransformer2DWrapper(**kwargs)
+    prod = prod.to_empty(device="cuda")
+    ora = ora.cuda()
+    prod.load_state_dict(ora.state_dict())
+    prod.pos_embed.pos_embed = ora.pos_embed.pos_embed.clone()       # non-persistent buffer (deterministic table)
+    return prod, ora
+
+
+def _inputs(B, hw, T, cap, vec, seed=1, masked=True):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(B, 4, hw, hw, device="cuda", generator=g)
+    t = torch.randint(0, 1000, (B,), device="cuda", generator=g).float()
+    cond = {"cond": {"crossattn": torch.randn(B, T, cap, device="cuda", generator=g),
+                     "vector": torch.randn(B, vec, device="cuda", generator=g)}}
+    if masked:
+        lens = torch.tensor([T - 3 * (i + 1) for i in range(B)], device="cuda")
+        cond["cond"]["attention_mask"] = (torch.arange(T, device="cuda")[None, :] < lens[:, None]).long()
+    return x, t, cond
+
+
+def test_dit_kernels():
+    from flash.b200 import raw
+    torch.manual_seed(0)
+    B, N, C = 3, 200, 96
+    x = (torch.randn(B * N, C, device="cuda") * 1.5 + 0.2).bfloat16()
+    mod = torch.randn(B, 6, C, device="cuda")
+    y = raw.layernorm_modulate(x, mod[:, 1], mod[:, 0], N, 1e-6)
+    ref = F.layer_norm(x.float().view(B, N, C), (C,), eps=1e-6) * (1 + mod[:, 1:2]) + mod[:, 0:1]
+    assert _rel(y, ref.view(B * N, C)) < 6e-3
+    # gated residual + gelu-tanh epilogues
+    w = (torch.randn(160, C, device="cuda") / C ** 0.5).bfloat16()
+    bias = torch.randn(160, device="cuda")
+    res = torch.randn(B * N, 160, device="cuda").bfloat16()
+    gate = torch.randn(B, 160, device="cuda")
+    out = raw.gemm(x, w, bias=bias, residual=res, rowscale=gate, rows_per_group_scale=N, out_fp32=True)
+    ref = (x.float() @ w.float().t() + bias).view(B, N, 160) * gate[:, None] + res.float().view(B, N, 160)
+    assert _rel(out, ref.view(B * N, 160)) < 1e-5
+    out = raw.gemm(x, w, bias=bias, act=1, out_fp32=True)
+    assert _rel(out, F.gelu(x.float() @ w.float().t() + bias, approximate="tanh")) < 1e-5
+    # un-patchify
+    tok = torch.randn(2 * 4 * 4, 2 * 2 * 8, device="cuda")
+    ref = torch.einsum("nhwpqc->nchpwq", tok.view(2, 4, 4, 2, 2, 8)).reshape(2, 8, 8, 8)[:, :4]
+    assert torch.equal(raw.unpatchify(tok, 2, 4, 4, 2, 8, 4), ref)
+
+
+@pytest.mark.parametrize("masked", [False, True])
+def test_small_pixart_forward(masked):
+    prod, ora = _pair(SMALL)
+    prod.freeze(); ora.freeze()
+    x, t, cond = _inputs(2, 32, 20, 64, 24, masked=masked)
+    with torch.no_grad():
+        ref = ora(x, t, cond)
+        out = prod(x, t, cond)
+    assert out.shape == ref.shape == (2, 4, 32, 32)
+    assert _rel(out, ref) < 2e-2, _rel(out, ref)
+    with pytest.raises(NotImplementedError):
+        prod(x.requires_grad_(True), t, cond)
+
+
+def test_small_pixart_lora_student_forward():
+    from flash.models.lora import LoraConfig
+    from oracle.unet import LoraConfig as OLoraConfig
+    from oracle.unet import UNet2DConditionOracle
+    prod, ora = _pair(SMALL, seed=3)
+    targets = ["to_k", "to_q", "to_v", "to_out.0", "net.2", "linear", "linear_1", "linear_2"]    # Linear targets of
+    cfg = dict(r=8, lora_alpha=8, target_modules=targets)                                        # train_flash_pixart.py:237-256
+    UNet2DConditionOracle.add_adapter(ora, OLoraConfig(**cfg))
+    prod.add_adapter(LoraConfig(**cfg))
+    with torch.no_grad():
+        for n, p in ora.named_parameters():
+            if "lora_B" in n:
+                p.normal_(0, 0.05)
+    ora = ora.cuda()
+    prod.load_state_dict(ora.state_dict())
+    prod.eval(); ora.eval()
+    x, t, cond = _inputs(2, 32, 20, 64, 24)
+    with torch.no_grad():
+        assert _rel(prod(x, t, cond), ora(x, t, cond)) < 2e-2
+
+
+def test_pixart_xl_forward_full_size():
+    """BASELINE config 3 architecture (examples/train_flash_pixart.py:65-86) at 1024x1024, B=1, masked T5 context."""
+    from oracle.dit import PIXART_KWARGS
+    prod, ora = _pair(PIXART_KWARGS, seed=11)
+    prod.freeze(); ora.freeze()
+    x, t, cond = _inputs(1, 128, 120, 4096, 768)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        out = prod(x, t, cond)
+        ref = ora(x, t, cond)
+    assert torch.isfinite(out).all()
+    assert _rel(out, ref) < 2e-2, _rel(out, ref)

@@ -15,13 +15,17 @@ which = sys.argv[1] if len(sys.argv) > 1 else "sdxl"
 if which == "sdxl":
     model, _ = recipes.build_sdxl_distillation(dev)
     hw, ctx, pooled, fwd_flops = 128, 2048, 1280, 6.76e12
+elif which == "pixart":
+    model = recipes.build_pixart_sampler(dev)
+    hw, ctx, pooled, fwd_flops = 128, 4096, 0, 6.51e12
 else:
     model, _ = recipes.build_sd15_distillation(dev)
     hw, ctx, pooled, fwd_flops = 64, 768, 0, 0.80e12
 model.eval()
 rows = []
 for B in [1, 2, 4, 8, 16, 32]:
-    batch = recipes.synthetic_batch(B, hw, 77, ctx, pooled, seed=B, device=dev)
+    batch = (recipes.pixart_batch(B, B, dev) if which == "pixart"
+             else recipes.synthetic_batch(B, hw, 77, ctx, pooled, seed=B, device=dev))
     z = torch.randn(B, 4, hw, hw, device=dev)
     for _ in range(2):
         model.sample(z, num_steps=4, guidance_scale=1.0, conditioner_inputs=batch)
