@@ -120,3 +120,60 @@ def test_pixart_xl_forward_full_size():
         ref = ora(x, t, cond)
     assert torch.isfinite(out).all()
     assert _rel(out, ref) < 2e-2, _rel(out, ref)
+
+
+SD3_SMALL = dict(sample_size=16, patch_size=2, in_channels=16, num_layers=3, attention_head_dim=64,
+                 num_attention_heads=2, joint_attention_dim=48, caption_projection_dim=128, pooled_projection_dim=40,
+                 out_channels=16, pos_embed_max_size=12)
+
+
+def _sd3_pair(kwargs, seed=0):
+    from flash.models.transformers import DiffusersSD3Transformer2DWrapper
+    from oracle.sd3 import SD3TransformerOracle
+    torch.manual_seed(seed)
+    ora = SD3TransformerOracle(**kwargs)
+    with torch.no_grad():
+        for n, p in ora.named_parameters():
+            if p.dim() >= 2:
+                p.normal_(0, 1.0 / p[0].numel() ** 0.5)
+            else:
+                p.normal_(0, 0.05)
+    with torch.device("meta"):
+        prod = DiffusersSD3Transformer2DWrapper(**kwargs)
+    prod = prod.to_empty(device="cuda")
+    ora = ora.cuda()
+    prod.load_state_dict(ora.state_dict())          # includes the persistent position table
+    prod.freeze(); ora.freeze()
+    return prod, ora
+
+
+def _sd3_inputs(B, hw, T, joint, pooled, seed=1):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn(B, 16, hw, hw, device="cuda", generator=g)
+    t = torch.randint(0, 1000, (B,), device="cuda", generator=g).float()
+    cond = {"cond": {"crossattn": torch.randn(B, T, joint, device="cuda", generator=g),
+                     "vector": torch.randn(B, pooled, device="cuda", generator=g)}}
+    return x, t, cond
+
+
+def test_small_sd3_forward():
+    prod, ora = _sd3_pair(SD3_SMALL)
+    x, t, cond = _sd3_inputs(2, 16, 10, 48, 40)
+    with torch.no_grad():
+        ref = ora(x, t, cond)
+        out = prod(x, t, cond)
+    assert out.shape == ref.shape == (2, 16, 16, 16)
+    assert _rel(out, ref) < 2e-2, _rel(out, ref)
+
+
+def test_sd3_medium_forward_full_size():
+    """BASELINE config 4 architecture (examples/train_flash_sd3.py:65-77) at 1024x1024, B=1, 154 text tokens."""
+    from oracle.sd3 import SD3_KWARGS
+    prod, ora = _sd3_pair(SD3_KWARGS, seed=5)
+    x, t, cond = _sd3_inputs(1, 128, 154, 4096, 2048)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        out = prod(x, t, cond)
+        ref = ora(x, t, cond)
+    assert torch.isfinite(out).all()
+    assert _rel(out, ref) < 2e-2, _rel(out, ref)
