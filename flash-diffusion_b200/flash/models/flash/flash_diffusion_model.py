@@ -339,8 +339,13 @@ class FlashDiffusion(BaseModel):
             feats = self._call_frozen(self.disc_backbone, noisy_sample, torch.cat([timesteps, timesteps], dim=0),
                                       cond2, return_intermediate=True)
         f_fake, f_real = feats.chunk(2, dim=0)
+        return self._gan_objective(f_fake, f_real, B, generator_turn)
+
+    def _gan_objective(self, f_fake, f_real, B, generator_turn):
+        """[loss_G, loss_D] of the configured GAN type on backbone features (reference :571-667; the SD3 variant
+        flash_sd3/flash_diffusion_model.py:571-658 is the same table)."""
         D = self.discriminator
-        dev = student_output.device
+        dev = f_fake.device
         valid = torch.ones(B, 1, device=dev)
         fake_t = torch.zeros(B, 1, device=dev)
         t = self.gan_loss_type

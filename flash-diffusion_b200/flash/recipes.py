@@ -229,3 +229,65 @@ def build_tiny_distillation(device, **kw):
     kw.setdefault("K", 4)
     kw.setdefault("fourier_channels", 8)
     return build_distillation(TINY_UNET_KWARGS, tiny_discriminator(), device, **kw)
+
+
+SD3_KWARGS = dict(   # examples/train_flash_sd3.py:65-77
+    sample_size=128, patch_size=2, in_channels=16, num_layers=24, attention_head_dim=64, num_attention_heads=24,
+    joint_attention_dim=4096, caption_projection_dim=1536, pooled_projection_dim=2048, out_channels=16,
+    pos_embed_max_size=192)
+
+# examples/train_flash_sd3.py:104-117
+SD3_LORA_TARGETS = ["to_q", "to_k", "to_v", "to_out.0", "proj_in", "proj_out", "ff.net.0.proj", "ff.net.2", "proj",
+                    "linear", "linear_1", "linear_2"]
+
+
+def sd3_discriminator(color_dim=16, d=64):
+    """examples/train_flash_sd3.py:143-181 (on the 16-channel backbone output)."""
+    return nn.Sequential(nn.Conv2d(color_dim, d, 4, 2, 1, bias=False), nn.SiLU(True),
+                         nn.Conv2d(d, d * 2, 4, 2, 1, bias=False), nn.GroupNorm(4, d * 2), nn.SiLU(True),
+                         nn.Conv2d(d * 2, d * 4, 4, 2, 1, bias=False), nn.GroupNorm(4, d * 4), nn.SiLU(True),
+                         nn.Conv2d(d * 4, d * 8, 4, 2, 1, bias=False), nn.GroupNorm(4, d * 8), nn.SiLU(True),
+                         nn.Conv2d(d * 8, 1, 4, 1, 0, bias=False), nn.Flatten())
+
+
+def build_sd3(device, kwargs=None, lora_rank=64, seed=1234, K=32):
+    """Config 4 objects (SD3-medium MMDiT, LoRA r=64 on the reference's targets, flow-matching schedulers) inside a
+    `FlashDiffusionSD3`.  On CUDA the MMDiT is forward-only: teacher rollout, DMD/GAN teacher evaluations and the
+    few-step sampler run; the student backward is the next row."""
+    from .models.flash_sd3 import FlashDiffusionSD3, FlashDiffusionSD3Config
+    from .models.transformers import DiffusersSD3Transformer2DWrapper
+    from .schedulers import FlashFlowMatchEulerDiscreteScheduler, FlowMatchEulerDiscreteScheduler
+    kwargs = kwargs or SD3_KWARGS
+    with torch.device("meta"):
+        teacher = DiffusersSD3Transformer2DWrapper(**kwargs)
+    teacher = teacher.to_empty(device=device)
+    init_random_(teacher, seed)
+    pe = teacher.pos_embed
+    fresh = type(pe)(kwargs["sample_size"], kwargs["patch_size"], kwargs["in_channels"], teacher.inner_dim,
+                     kwargs["pos_embed_max_size"])
+    pe.pos_embed = fresh.pos_embed.to(device)
+    student = copy.deepcopy(teacher)
+    if lora_rank:
+        student.add_adapter(LoraConfig(r=lora_rank, lora_alpha=lora_rank, target_modules=SD3_LORA_TARGETS))
+    teacher.freeze()
+    cfg = FlashDiffusionSD3Config(K=[K], num_iterations_per_K=[10 ** 9], guidance_scale_min=7.0,
+                                  guidance_scale_max=13.0, distill_loss_type="l2", use_dmd_loss=True,
+                                  gan_loss_type="lsgan", input_key="image")
+    mk = lambda cls, **kw: cls.from_pretrained("stabilityai/stable-diffusion-3-medium", subfolder="scheduler", **kw)
+    return FlashDiffusionSD3(cfg, student_denoiser=student, teacher_denoiser=teacher,
+                             teacher_noise_scheduler=mk(FlowMatchEulerDiscreteScheduler, timestep_spacing="trailing"),
+                             sampling_noise_scheduler=mk(FlashFlowMatchEulerDiscreteScheduler, timestep_spacing="trailing"),
+                             teacher_sampling_noise_scheduler=mk(FlowMatchEulerDiscreteScheduler),
+                             discriminator=sd3_discriminator(kwargs["out_channels"])).to(device)
+
+
+def sd3_batch(B, seed, device, kwargs=None, tokens=154, hw=None):
+    kwargs = kwargs or SD3_KWARGS
+    hw = hw or kwargs["sample_size"]
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g)
+    j, p = kwargs["joint_attention_dim"], kwargs["pooled_projection_dim"]
+    batch = {"image": r(B, kwargs["in_channels"], hw, hw), "prompt_embeds": r(B, tokens, j),
+             "negative_prompt_embeds": r(B, tokens, j), "pooled_prompt_embeds": r(B, p),
+             "negative_pooled_prompt_embeds": r(B, p)}
+    return {k: v.to(device) for k, v in batch.items()}

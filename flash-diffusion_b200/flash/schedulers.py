@@ -277,3 +277,112 @@ class LCMScheduler(_SchedulerBase):
             prev = denoised
         self._step_index += 1
         return (prev, denoised)
+
+
+class FlowMatchEulerDiscreteScheduler:
+    """Rectified-flow Euler scheduler used by the SD3 recipe (reference examples/train_flash_sd3.py:123-141,
+    consumed at src/flash/models/flash_sd3/flash_diffusion_model.py:253-324 and :1043-1060).
+
+    Restated from upstream diffusers' published `FlowMatchEulerDiscreteScheduler` (v0.29): training grid
+    sigma_i = shift*s/(1+(shift-1)*s), s = i/N for i = N..1, timesteps = sigma*N; `set_timesteps(K)` takes K values
+    linearly spaced between sigma_max*N and sigma_min*N and applies the shift map to them AGAIN (upstream v0.29
+    behaviour, kept); `step` is x + (sigma_next - sigma) * v with a trailing sigma of 0.
+
+    `timestep_spacing="trailing"` exists only in the authors' diffusers fork, which is not available: it is read here
+    as the trailing grid of the other schedulers (raw timesteps N, N-N/K, ..., N/K, shift map applied once).  That
+    reading is an ASSUMPTION and is stated in DESIGN.md; the default spacing follows upstream.
+    """
+    order = 1
+
+    def __init__(self, num_train_timesteps=1000, shift=1.0, timestep_spacing="linspace", **extra):
+        self.config = SimpleNamespace(num_train_timesteps=num_train_timesteps, shift=shift,
+                                      timestep_spacing=timestep_spacing, **extra)
+        n = num_train_timesteps
+        sig = torch.from_numpy(np.linspace(1, n, n, dtype=np.float32)[::-1].copy()) / n
+        sig = self._shift(sig)
+        self.timesteps = sig * n
+        self.sigmas = sig.clone()
+        self.sigma_min, self.sigma_max = float(sig[-1]), float(sig[0])
+        self.num_inference_steps = None
+        self._step_index = None
+
+    def _shift(self, s):
+        k = self.config.shift
+        return k * s / (1 + (k - 1) * s)
+
+    @classmethod
+    def from_pretrained(cls, repo: str = None, subfolder: str = None, revision: str = None, **overrides):
+        cfg = dict(num_train_timesteps=1000, shift=3.0)          # stabilityai/stable-diffusion-3-medium scheduler
+        cfg.update(overrides)
+        return cls(**cfg)
+
+    @classmethod
+    def from_config(cls, config, **overrides):
+        cfg = dict(vars(config)) if not isinstance(config, dict) else dict(config)
+        cfg.update(overrides)
+        return cls(**cfg)
+
+    def set_timesteps(self, num_inference_steps=None, device=None):
+        n = self.config.num_train_timesteps
+        self.num_inference_steps = num_inference_steps
+        if self.config.timestep_spacing == "trailing":
+            raw = np.arange(n, 0, -n / num_inference_steps, dtype=np.float64)[:num_inference_steps]
+            sig = self._shift(torch.from_numpy((raw / n).astype(np.float32)))
+        else:
+            raw = np.linspace(self.sigma_max * n, self.sigma_min * n, num_inference_steps, dtype=np.float32)
+            sig = self._shift(torch.from_numpy(raw / n))
+        self.timesteps = (sig * n).to(device) if device is not None else sig * n
+        self.sigmas = torch.cat([sig, torch.zeros(1)])
+        self._step_index = None
+
+    def scale_model_input(self, sample, timestep=None):
+        return sample
+
+    def index_for(self, timestep) -> int:
+        hits = (self.timesteps == float(timestep)).nonzero()
+        if hits.numel() == 0:
+            raise ValueError(f"timestep {float(timestep)} is not on the current schedule")
+        return int(hits[0])
+
+    def scale_noise(self, sample, timestep, noise):
+        s = float(self.sigmas[self.index_for(timestep)])
+        return s * noise + (1.0 - s) * sample
+
+    def step(self, model_output, timestep, sample, return_dict=False, **kw):
+        i = self.index_for(timestep)
+        s, s_next = float(self.sigmas[i]), float(self.sigmas[i + 1])
+        prev = sample + (s_next - s) * model_output
+        self._step_index = i + 1
+        return (prev,)
+
+    def fused_cfg_step(self, v_c, v_u, guidance_scale: float, timestep, sample, scratch):
+        """CUDA path: v = w v_c + (1-w) v_u and the Euler update in ONE kernel (fd_step_cfg_dpm), in place on `sample`
+        (fp32).  The kernel computes x0 = (x - s v)/a and x' = c_x x - c_d0 x0 - c_d1r (x0 - x0_prev); with a = 1,
+        s = sigma it is the flow's x0 read-out, and x + (sigma' - sigma) v = (sigma'/sigma) x + (1 - sigma'/sigma) x0."""
+        from .b200 import raw
+        i = self.index_for(timestep)
+        s, s_next = float(self.sigmas[i]), float(self.sigmas[i + 1])
+        r = s_next / s
+        raw.step_cfg_dpm(v_c, v_u, sample, scratch, (guidance_scale, 1.0, s, r, -(1.0 - r), 0.0))
+        self._step_index = i + 1
+        return sample
+
+
+class FlashFlowMatchEulerDiscreteScheduler(FlowMatchEulerDiscreteScheduler):
+    """Few-step student sampler of the SD3 recipe (reference examples/configs/flash_sd3.yaml `SAMPLING_SCHEDULER`,
+    consumed at flash_sd3/flash_diffusion_model.py:694-790).  The class exists only in the authors' diffusers fork;
+    it is read here as the flow-matching analogue of the LCM sampler the other recipes use: the student's velocity
+    gives x0 = x - sigma*v (exactly the `student_output` the objective trains, :324), which is re-noised to the next
+    level, x' = (1 - sigma')*x0 + sigma'*noise.  ASSUMPTION, stated in DESIGN.md."""
+
+    def step(self, model_output, timestep, sample, generator=None, return_dict=False, **kw):
+        i = self.index_for(timestep)
+        s, s_next = float(self.sigmas[i]), float(self.sigmas[i + 1])
+        x0 = sample - s * model_output
+        if s_next > 0:
+            noise = torch.randn(sample.shape, generator=generator, device=sample.device, dtype=sample.dtype)
+            prev = (1.0 - s_next) * x0 + s_next * noise
+        else:
+            prev = x0
+        self._step_index = i + 1
+        return (prev, x0)

@@ -177,3 +177,69 @@ def test_sd3_medium_forward_full_size():
         ref = ora(x, t, cond)
     assert torch.isfinite(out).all()
     assert _rel(out, ref) < 2e-2, _rel(out, ref)
+
+
+def _sd3_objective_pair(lora_rank, seed=0):
+    """Product FlashDiffusionSD3 (B200 MMDiT wrappers) and the same class around fp32 oracle MMDiTs with equal weights
+    (LoRA merged into the oracle student's weights)."""
+    import copy
+    from flash.models.lora import LoRALinear
+    from flash.recipes import build_sd3
+    from oracle.sd3 import SD3TransformerOracle
+    prod = build_sd3("cuda", kwargs=SD3_SMALL, lora_rank=lora_rank, seed=seed, K=4)
+    if lora_rank:
+        g = torch.Generator(device="cuda").manual_seed(seed + 7)
+        with torch.no_grad():
+            for n, p in prod.student_denoiser.named_parameters():
+                if "lora_B" in n:
+                    p.normal_(0, 0.05, generator=g)
+    t_ora = SD3TransformerOracle(**SD3_SMALL).cuda()
+    t_ora.load_state_dict(prod.teacher_denoiser.state_dict())
+    s_ora = copy.deepcopy(t_ora)
+    with torch.no_grad():
+        for name, m in prod.student_denoiser.named_modules():
+            if isinstance(m, LoRALinear):
+                s_ora.get_submodule(name).weight += m.scaling * (m.lora_B["default"].weight @ m.lora_A["default"].weight)
+    t_ora.freeze(); s_ora.freeze()
+    ora = copy.copy(prod)
+    ora.__dict__ = dict(prod.__dict__)
+    ora._modules = dict(prod._modules)
+    ora._modules["student_denoiser"], ora._modules["teacher_denoiser"] = s_ora, t_ora
+    ora.disc_backbone = t_ora
+    ora.teacher_noise_scheduler = copy.deepcopy(prod.teacher_noise_scheduler)
+    ora.sampling_noise_scheduler = copy.deepcopy(prod.sampling_noise_scheduler)
+    ora.use_cuda_graphs = False
+    ora.__dict__["_graphed"] = {}
+    return prod, ora
+
+
+@pytest.mark.parametrize("lora_rank", [0, 4])
+def test_sd3_objective_teacher_rollout_and_sampler(lora_rank):
+    """Teacher CFG Euler rollout (one 2B call + fused CFG/Euler kernel, graph replay) and the 4-step student sampler of
+    FlashDiffusionSD3 against the same host class around the fp32 oracle MMDiT."""
+    from flash.recipes import sd3_batch
+    prod, ora = _sd3_objective_pair(lora_rank)
+    batch = sd3_batch(2, 3, "cuda", kwargs=SD3_SMALL, tokens=9, hw=16)
+    cond, unc = prod._conditionings(batch, "cuda")
+    x = torch.randn(2, 16, 16, 16, device="cuda")
+    prod.teacher_noise_scheduler.set_timesteps(4)
+    ora.teacher_noise_scheduler.set_timesteps(4)
+    a = prod._teacher_rollout(x, cond, unc, 1, 9.5)
+    b = ora._teacher_rollout(x, cond, unc, 1, 9.5)
+    assert torch.isfinite(a).all() and _rel(a, b) < 3e-2, _rel(a, b)
+    prod.eval()
+    z = torch.randn(2, 16, 16, 16, device="cuda")
+    for w in (1.0, 2.0):
+        ga, gb = torch.Generator(device="cuda").manual_seed(5), torch.Generator(device="cuda").manual_seed(5)
+        sa, ta = prod.sample(z, num_steps=4, guidance_scale=w, conditioner_inputs=batch, log_teacher_samples=True,
+                             generator=ga)
+        sb, tb = ora.sample(z, num_steps=4, guidance_scale=w, conditioner_inputs=batch, log_teacher_samples=True,
+                            generator=gb)
+        assert _rel(sa, sb) < 3e-2 and _rel(ta, tb) < 3e-2, (_rel(sa, sb), _rel(ta, tb))
+
+
+def test_sd3_objective_training_forward_raises_on_cuda_student():
+    from flash.recipes import sd3_batch
+    prod, _ = _sd3_objective_pair(4)
+    with pytest.raises(NotImplementedError, match="backward"):
+        prod(sd3_batch(2, 3, "cuda", kwargs=SD3_SMALL, tokens=9, hw=16), draws={"start_idx": 1})
