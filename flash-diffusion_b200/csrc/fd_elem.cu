@@ -236,6 +236,46 @@ __global__ void geglu_bwd_kernel(const bf16* __restrict__ acc, const bf16* __res
     }
 }
 
+// dacc = dout * d/dx gelu_tanh(acc)   (the activation the GEMM epilogue applies with act = 1)
+__global__ void gelu_tanh_bwd_kernel(const bf16* __restrict__ acc, const bf16* __restrict__ dout,
+                                     bf16* __restrict__ dacc, long long nvec) {
+    FD_GRID_STRIDE(i, nvec) {
+        float a[8], d[8], o[8];
+        ld8(acc + i * 8, a);
+        ld8(dout + i * 8, d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float x = a[j];
+            const float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+            const float t = tanhf(u);
+            const float du = 0.7978845608028654f * (1.0f + 3.0f * 0.044715f * x * x);
+            o[j] = d[j] * (0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du);
+        }
+        st8(dacc + i * 8, o);
+    }
+}
+
+// inverse of unpatchify_kernel for the gradient: dy [NB, Ckeep, h*p, w*p] fp32 -> dx [NB*h*w, p*p*Cout] bf16
+// (columns ordered (pi, qi, c); channels >= Ckeep get zero)
+__global__ void patchify_kernel(const float* __restrict__ dy, bf16* __restrict__ dx, int NB, int h, int w, int p,
+                                int Cout, int Ckeep) {
+    const int H = h * p, W = w * p, cols = p * p * Cout;
+    const long long total = (long long)NB * h * w * cols;
+    FD_GRID_STRIDE(i, total) {
+        const int col = (int)(i % cols);
+        long long t = i / cols;
+        const int wx = (int)(t % w);
+        t /= w;
+        const int hy = (int)(t % h);
+        const int n = (int)(t / h);
+        const int c = col % Cout, pq = col / Cout;
+        const int pi = pq / p, qi = pq % p;
+        float v = 0.f;
+        if (c < Ckeep) v = dy[(((long long)n * Ckeep + c) * H + hy * p + pi) * W + wx * p + qi];
+        dx[i] = __float2bfloat16(v);
+    }
+}
+
 // ------------------------------------------------------------------ distillation-step kernels
 __global__ void add_noise_kernel(const float* __restrict__ z, const float* __restrict__ noise,
                                  const float* __restrict__ sa, const float* __restrict__ sg,
@@ -421,6 +461,23 @@ extern "C" int fd_step_student_output(const float* x_t, const float* eps, const 
                                       const float* c_skip, const float* c_out, float* out, int32_t B,
                                       int64_t n, void* stream) {
     student_output_kernel<<<grid_for((long long)B * n), 256, 0, (cudaStream_t)stream>>>(x_t, eps, sa, sg, c_skip, c_out, out, B, n);
+    FD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int fd_gelu_tanh_bwd(const void* acc, const void* dout, void* dacc, int64_t n, void* stream) {
+    FD_CHECK_ARG(n % 8 == 0, "fd_gelu_tanh_bwd: n %% 8");
+    gelu_tanh_bwd_kernel<<<grid_for(n / 8), 256, 0, (cudaStream_t)stream>>>((const bf16*)acc, (const bf16*)dout,
+                                                                            (bf16*)dacc, n / 8);
+    FD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int fd_patchify(const float* dy, void* dx, int32_t NB, int32_t h, int32_t w, int32_t p, int32_t Cout,
+                           int32_t Ckeep, void* stream) {
+    FD_CHECK_ARG(Ckeep <= Cout && p > 0, "fd_patchify: bad channels");
+    const long long total = (long long)NB * h * w * p * p * Cout;
+    patchify_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(dy, (bf16*)dx, NB, h, w, p, Cout, Ckeep);
     FD_CHECK_LAUNCH();
     return 0;
 }

@@ -355,6 +355,163 @@ __global__ void ln_bwd_kernel(const bf16* __restrict__ x, const float* __restric
     }
 }
 
+
+// Backward of y = LN(x) * (1 + scale[b]) + shift[b] (no affine): recomputes the row statistics from x,
+//   dx = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * (1 + scale[b]),
+//   dscale[b, c] += sum_rows dy * xhat,   dshift[b, c] += sum_rows dy.
+// grid (chunks, B): a block owns a contiguous run of rows of ONE sample, accumulates the two column sums in shared
+// memory (2*C floats) and adds them to global memory once at the end.
+__global__ void ln_modulate_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                       const float* __restrict__ scale, long long ld_mod, bf16* __restrict__ dx,
+                                       float* __restrict__ dscale, float* __restrict__ dshift, int C,
+                                       int rows_per_batch, int rows_per_block, float eps) {
+    extern __shared__ float ln_acc[];            // [2][C]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int b = blockIdx.y;
+    const int nvec = C >> 3;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) ln_acc[i] = 0.f;
+    __syncthreads();
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(r0 + rows_per_block, rows_per_batch);
+    const float* sc = scale + (long long)b * ld_mod;
+    for (int r = r0 + warp; r < r1; r += nwarps) {
+        const long long row = (long long)b * rows_per_batch + r;
+        const bf16* xr = x + row * C;
+        const bf16* dr = dy + row * C;
+        float xh[LN_MAXV][8], dg[LN_MAXV][8];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            const int vi = lane + i * 32;
+            if (vi < nvec) {
+                load8(xr + vi * 8, xh[i]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s += xh[i][j];
+            }
+        }
+        const float mean = warp_sum(s) / C;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            const int vi = lane + i * 32;
+            if (vi < nvec) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    xh[i][j] -= mean;
+                    q += xh[i][j] * xh[i][j];
+                }
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(q) / C + eps);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            const int vi = lane + i * 32;
+            if (vi < nvec) {
+                load8(dr + vi * 8, dg[i]);
+                const float4 a0 = __ldg(reinterpret_cast<const float4*>(sc + vi * 8));
+                const float4 a1 = __ldg(reinterpret_cast<const float4*>(sc + vi * 8 + 4));
+                const float sca[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    xh[i][j] *= rstd;
+                    atomicAdd(&ln_acc[vi * 8 + j], dg[i][j] * xh[i][j]);
+                    atomicAdd(&ln_acc[C + vi * 8 + j], dg[i][j]);
+                    dg[i][j] *= 1.0f + sca[j];
+                    s1 += dg[i][j];
+                    s2 += dg[i][j] * xh[i][j];
+                }
+            }
+        }
+        s1 = warp_sum(s1) / C;
+        s2 = warp_sum(s2) / C;
+        bf16* dxr = dx + row * C;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            const int vi = lane + i * 32;
+            if (vi < nvec) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = rstd * (dg[i][j] - s1 - xh[i][j] * s2);
+                store8(dxr + vi * 8, o);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) {
+        atomicAdd(dscale + (long long)b * C + i, ln_acc[i]);
+        atomicAdd(dshift + (long long)b * C + i, ln_acc[C + i]);
+    }
+}
+
+// out = res + gate[b] * h ; backward dh = gate[b] * dout, dgate[b, c] += sum_rows dout * h   (AdaLN-Zero gates)
+__global__ void gate_residual_kernel(const bf16* __restrict__ h, const float* __restrict__ gate, long long ld_gate,
+                                     const bf16* __restrict__ res, bf16* __restrict__ out, long long rows, int C,
+                                     int rows_per_batch) {
+    const int cv = C >> 3;
+    const long long total = rows * cv;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / cv;
+        const int v = (int)(i - row * cv);
+        const float* g = gate + (row / rows_per_batch) * ld_gate + v * 8;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(g));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(g + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        float a[8], r[8];
+        load8(h + row * C + v * 8, a);
+        load8(res + row * C + v * 8, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] += gg[j] * a[j];
+        store8(out + row * C + v * 8, r);
+    }
+}
+
+__global__ void gate_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ h,
+                                const float* __restrict__ gate, long long ld_gate, bf16* __restrict__ dh,
+                                float* __restrict__ dgate, int C, int rows_per_batch, int rows_per_block) {
+    extern __shared__ float ln_acc[];            // [C]
+    const int b = blockIdx.y;
+    const int cv = C >> 3;
+    for (int i = threadIdx.x; i < C; i += blockDim.x) ln_acc[i] = 0.f;
+    __syncthreads();
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(r0 + rows_per_block, rows_per_batch);
+    const float* gp = gate + (long long)b * ld_gate;
+    // a thread keeps the same 8 columns for all its rows when blockDim.x is a multiple of cv; otherwise it just
+    // walks the (row, vector) space: the shared-memory adds make either correct
+    const long long total = (long long)(r1 - r0) * cv;
+    for (long long i = threadIdx.x; i < total; i += blockDim.x) {
+        const int r = (int)(i / cv);
+        const int v = (int)(i - (long long)r * cv);
+        const long long row = (long long)b * rows_per_batch + r0 + r;
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp + v * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gp + v * 8 + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        float d[8], a[8], o[8];
+        load8(dout + row * C + v * 8, d);
+        load8(h + row * C + v * 8, a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            o[j] = gg[j] * d[j];
+            atomicAdd(&ln_acc[v * 8 + j], d[j] * a[j]);
+        }
+        store8(dh + row * C + v * 8, o);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += blockDim.x) atomicAdd(dgate + (long long)b * C + i, ln_acc[i]);
+}
+
+static void per_sample_geometry(int B, int rows_per_batch, int min_rows, dim3& grid, int& rows_per_block) {
+    int chunks = (num_sms() * 4 + B - 1) / B;
+    const int max_chunks = (rows_per_batch + min_rows - 1) / min_rows;
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    rows_per_block = (rows_per_batch + chunks - 1) / chunks;
+    chunks = (rows_per_batch + rows_per_block - 1) / rows_per_block;
+    grid = dim3(chunks, B);
+}
+
 }  // namespace fd
 
 using namespace fd;
@@ -445,6 +602,55 @@ extern "C" int fd_layernorm_bwd(const void* x, const float* stats, const float* 
     const int blocks = (rows + warps_per_block - 1) / warps_per_block;
     ln_bwd_kernel<<<blocks, warps_per_block * 32, 0, stream>>>((const bf16*)x, stats, gamma,
                                                                (const bf16*)dy, (bf16*)dx, rows, C);
+    FD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int fd_layernorm_modulate_bwd(const void* x, const void* dy, const float* scale, int64_t ld_mod, void* dx,
+                                         float* dscale, float* dshift, int32_t rows, int32_t C,
+                                         int32_t rows_per_batch, float eps, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FD_CHECK_ARG(C % 8 == 0 && C <= 8 * 32 * LN_MAXV && ld_mod % 4 == 0 && rows_per_batch > 0 &&
+                     rows % rows_per_batch == 0,
+                 "fd_layernorm_modulate_bwd: bad C=%d / ld_mod / rows", C);
+    const int B = rows / rows_per_batch;
+    FD_CHECK_CUDA(cudaMemsetAsync(dscale, 0, sizeof(float) * (size_t)B * C, stream));
+    FD_CHECK_CUDA(cudaMemsetAsync(dshift, 0, sizeof(float) * (size_t)B * C, stream));
+    dim3 grid;
+    int rpb;
+    per_sample_geometry(B, rows_per_batch, 16, grid, rpb);
+    ln_modulate_bwd_kernel<<<grid, 256, 2 * C * sizeof(float), stream>>>(
+        (const bf16*)x, (const bf16*)dy, scale, ld_mod, (bf16*)dx, dscale, dshift, C, rows_per_batch, rpb, eps);
+    FD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int fd_gate_residual(const void* h, const float* gate, int64_t ld_gate, const void* res, void* out,
+                                int32_t rows, int32_t C, int32_t rows_per_batch, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FD_CHECK_ARG(C % 8 == 0 && ld_gate % 4 == 0 && rows_per_batch > 0, "fd_gate_residual: bad C=%d / ld_gate", C);
+    const long long total = (long long)rows * (C / 8);
+    long long g = (total + 255) / 256;
+    const long long cap = (long long)num_sms() * 16;
+    if (g > cap) g = cap;
+    gate_residual_kernel<<<(int)g, 256, 0, stream>>>((const bf16*)h, gate, ld_gate, (const bf16*)res, (bf16*)out,
+                                                     rows, C, rows_per_batch);
+    FD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int fd_gate_bwd(const void* dout, const void* h, const float* gate, int64_t ld_gate, void* dh,
+                           float* dgate, int32_t rows, int32_t C, int32_t rows_per_batch, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FD_CHECK_ARG(C % 8 == 0 && ld_gate % 4 == 0 && rows_per_batch > 0 && rows % rows_per_batch == 0,
+                 "fd_gate_bwd: bad C=%d / ld_gate / rows", C);
+    const int B = rows / rows_per_batch;
+    FD_CHECK_CUDA(cudaMemsetAsync(dgate, 0, sizeof(float) * (size_t)B * C, stream));
+    dim3 grid;
+    int rpb;
+    per_sample_geometry(B, rows_per_batch, 16, grid, rpb);
+    gate_bwd_kernel<<<grid, 256, C * sizeof(float), stream>>>((const bf16*)dout, (const bf16*)h, gate, ld_gate,
+                                                              (bf16*)dh, dgate, C, rows_per_batch, rpb);
     FD_CHECK_LAUNCH();
     return 0;
 }

@@ -426,7 +426,7 @@ class LinearPack:
         return self.cache.get("lora", self.lora_params(), build)
 
 
-def _linear_fwd_raw(x, pack: LinearPack, residual, out=None):
+def _linear_fwd_raw(x, pack: LinearPack, residual, out=None, act=0, out_fp32=False):
     p = pack.pack()
     a2 = b2 = None
     t = None
@@ -434,17 +434,21 @@ def _linear_fwd_raw(x, pack: LinearPack, residual, out=None):
         lp = pack.pack_lora()
         t = raw.gemm(x, lp["a"])
         a2, b2 = t, lp["b"]
-    y = raw.gemm(x, p["w"], a2=a2, b2=b2, bias=p["b"], geglu=pack.geglu, residual=residual, out=out)
+    y = raw.gemm(x, p["w"], a2=a2, b2=b2, bias=p["b"], geglu=pack.geglu, residual=residual, out=out, act=act,
+                 out_fp32=out_fp32)
     return y, t
 
 
 class _LinearFn(torch.autograd.Function):
-    """y = x W^T + b (+ LoRA) (+ residual); GEGLU handled by _GegluFn."""
+    """y = act(x W^T + b (+ LoRA)) (+ residual); GEGLU handled by _GegluFn.  act = 1 is the tanh-GELU of the GEMM
+    epilogue: its backward recomputes the pre-activation (one extra GEMM) instead of storing it.  out_fp32 returns
+    fp32 (the incoming gradient is rounded to bf16 for the tensor-core backward)."""
 
     @staticmethod
-    def forward(ctx, x, residual, pack, *lora_params):
-        y, t = _linear_fwd_raw(x, pack, residual)
+    def forward(ctx, x, residual, pack, act, out_fp32, *lora_params):
+        y, t = _linear_fwd_raw(x, pack, residual, act=act, out_fp32=out_fp32)
         ctx.pack = pack
+        ctx.act = act
         ctx.has_res = residual is not None
         ctx.save_for_backward(x, t)
         return y
@@ -454,7 +458,15 @@ class _LinearFn(torch.autograd.Function):
         pack = ctx.pack
         x, t = ctx.saved_tensors
         dy = dy.contiguous()
-        dx = dres = None
+        if dy.dtype != BF16:
+            dy = raw.cast_scale(dy.float(), 1.0)
+        dres = dy if (ctx.has_res and ctx.needs_input_grad[1]) else None
+        if ctx.act:
+            p = pack.pack()
+            lp = pack.pack_lora() if pack.has_lora else None
+            pre = raw.gemm(x, p["w"], a2=t, b2=lp["b"] if lp else None, bias=p["b"])
+            dy = raw.gelu_tanh_bwd(pre, dy)
+        dx = None
         grads = [None] * len(pack.lora_params())
         if pack.has_lora:
             lp = pack.pack_lora()
@@ -464,9 +476,7 @@ class _LinearFn(torch.autograd.Function):
             grads = _lora_weight_grads(pack, lp, x, t, dy, dt)
         elif ctx.needs_input_grad[0]:
             dx = raw.gemm(dy, pack.pack_t())
-        if ctx.has_res and ctx.needs_input_grad[1]:
-            dres = dy
-        return (dx, dres, None, *grads)
+        return (dx, dres, None, None, None, *grads)
 
 
 def _lora_weight_grads(pack, lp, x, t, dy, dt):
@@ -491,19 +501,19 @@ def _lora_weight_grads(pack, lp, x, t, dy, dt):
     return grads
 
 
-def linear(x, pack: LinearPack, residual=None, want_stats=None):
-    """y = x W^T + b (+LoRA) (+residual).  want_stats None: return y.  True/False: return (y, stats) where stats are
-    the [M,2] row statistics of y (fused into the GEMM epilogue) when requested and the no-grad, LoRA-free path is
+def linear(x, pack: LinearPack, residual=None, want_stats=None, act=0, out_fp32=False):
+    """y = act(x W^T + b (+LoRA)) (+residual).  want_stats None: return y.  True/False: return (y, stats) where stats
+    are the [M,2] row statistics of y (fused into the GEMM epilogue) when requested and the no-grad, LoRA-free path is
     taken, else None."""
     lora_params = pack.lora_params() if pack.has_lora else []
     if _grad_on(x, residual, *lora_params):
-        y = _LinearFn.apply(x, residual, pack, *lora_params)
+        y = _LinearFn.apply(x, residual, pack, act, out_fp32, *lora_params)
         return y if want_stats is None else (y, None)
     if want_stats and not pack.has_lora:
         p = pack.pack()
         stats = torch.empty((x.shape[0], 2), device=x.device, dtype=torch.float32)
-        return raw.gemm(x, p["w"], bias=p["b"], residual=residual, rowstats=stats), stats
-    y = _linear_fwd_raw(x, pack, residual)[0]
+        return raw.gemm(x, p["w"], bias=p["b"], residual=residual, rowstats=stats, act=act), stats
+    y = _linear_fwd_raw(x, pack, residual, act=act, out_fp32=out_fp32)[0]
     return y if want_stats is None else (y, None)
 
 
@@ -542,6 +552,84 @@ def geglu(x, pack: LinearPack):
         return _GegluFn.apply(x, pack)
     p = pack.pack()
     return raw.gemm(x, p["w"], bias=p["b"], geglu=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# DiT / MMDiT blocks: AdaLN modulation and AdaLN-Zero gates (gradients flow to scale / shift / gate because the
+# reference's SD3 LoRA targets include every AdaLN linear, examples/train_flash_sd3.py:104-117)
+# ------------------------------------------------------------------------------------------------
+class _ModulateFn(torch.autograd.Function):
+    """y = LN(x) * (1 + scale[b]) + shift[b]; scale / shift fp32 [B, C] (views of the AdaLN projection)."""
+
+    @staticmethod
+    def forward(ctx, x, scale, shift, rows_per_batch, eps):
+        ctx.save_for_backward(x, scale)
+        ctx.meta = (rows_per_batch, eps)
+        return raw.layernorm_modulate(x, scale, shift, rows_per_batch, eps)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, scale = ctx.saved_tensors
+        rows_per_batch, eps = ctx.meta
+        dx, dscale, dshift = raw.layernorm_modulate_bwd(x, dy.contiguous(), scale, rows_per_batch, eps)
+        return dx, dscale, dshift, None, None
+
+
+def modulate(x, scale, shift, rows_per_batch, eps=1e-6):
+    if _grad_on(x, scale, shift):
+        return _ModulateFn.apply(x, scale, shift, rows_per_batch, eps)
+    return raw.layernorm_modulate(x, scale, shift, rows_per_batch, eps)
+
+
+class _GateResidualFn(torch.autograd.Function):
+    """out = res + gate[b] * h; gate fp32 [B, C]."""
+
+    @staticmethod
+    def forward(ctx, h, gate, res, rows_per_batch):
+        ctx.save_for_backward(h, gate)
+        ctx.rows_per_batch = rows_per_batch
+        return raw.gate_residual(h, gate, res, rows_per_batch)
+
+    @staticmethod
+    def backward(ctx, dout):
+        h, gate = ctx.saved_tensors
+        dout = dout.contiguous()
+        dh, dgate = raw.gate_bwd(dout, h, gate, ctx.rows_per_batch)
+        return dh, dgate, dout, None
+
+
+def gated_linear(x, pack: LinearPack, gate, res, rows_per_batch, act=0):
+    """res + gate[b] * act(x W^T + b (+LoRA)).  Without gradients the gate and the residual ride in the GEMM
+    epilogue; with gradients the branch output is kept for the gate gradient."""
+    lora_params = pack.lora_params() if pack.has_lora else []
+    if _grad_on(x, gate, res, *lora_params):
+        h = linear(x, pack, act=act)
+        return _GateResidualFn.apply(h, gate, res, rows_per_batch)
+    p = pack.pack()
+    a2 = b2 = None
+    if pack.has_lora:
+        lp = pack.pack_lora()
+        a2, b2 = raw.gemm(x, lp["a"]), lp["b"]
+    return raw.gemm(x, p["w"], a2=a2, b2=b2, bias=p["b"], act=act, residual=res, rowscale=gate,
+                    rows_per_group_scale=rows_per_batch)
+
+
+class _UnpatchifyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, NB, h, w, p, Cout, Ckeep):
+        ctx.meta = (h, w, p, Cout)
+        return raw.unpatchify(x, NB, h, w, p, Cout, Ckeep)
+
+    @staticmethod
+    def backward(ctx, dy):
+        h, w, p, Cout = ctx.meta
+        return raw.patchify(dy.contiguous().float(), h, w, p, Cout).float(), None, None, None, None, None, None
+
+
+def unpatchify(x, NB, h, w, p, Cout, Ckeep):
+    if _grad_on(x):
+        return _UnpatchifyFn.apply(x, NB, h, w, p, Cout, Ckeep)
+    return raw.unpatchify(x, NB, h, w, p, Cout, Ckeep)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -145,6 +145,63 @@ def layernorm_modulate(x, scale, shift, rows_per_batch, eps):
     return y
 
 
+def layernorm_modulate_bwd(x, dy, scale, rows_per_batch, eps):
+    """-> dx [rows, C] bf16, dscale [B, C] fp32, dshift [B, C] fp32 (see fd_layernorm_modulate_bwd)."""
+    lib = load(); _req(x, BF16, "x"); _req(dy, BF16, "dy"); _req(scale, torch.float32, "scale")
+    rows, C = x.shape
+    assert x.is_contiguous() and dy.is_contiguous() and scale.stride(1) == 1 and rows % rows_per_batch == 0
+    B = rows // rows_per_batch
+    dx = torch.empty_like(x)
+    dscale = torch.empty((B, C), device=x.device, dtype=torch.float32)
+    dshift = torch.empty((B, C), device=x.device, dtype=torch.float32)
+    check(lib.fd_layernorm_modulate_bwd(ptr(x), ptr(dy), ptr(scale), c_int64(scale.stride(0)), ptr(dx), ptr(dscale),
+                                        ptr(dshift), c_int32(rows), c_int32(C), c_int32(rows_per_batch), c_float(eps),
+                                        stream_ptr()), "fd_layernorm_modulate_bwd")
+    return dx, dscale, dshift
+
+
+def gate_residual(h, gate, res, rows_per_batch):
+    """out = res + gate[b] * h; gate fp32 [B, C] view (unit column stride)."""
+    lib = load(); _req(h, BF16, "h"); _req(res, BF16, "res"); _req(gate, torch.float32, "gate")
+    rows, C = h.shape
+    assert h.is_contiguous() and res.is_contiguous() and res.shape == h.shape and gate.stride(1) == 1
+    out = torch.empty_like(h)
+    check(lib.fd_gate_residual(ptr(h), ptr(gate), c_int64(gate.stride(0)), ptr(res), ptr(out), c_int32(rows),
+                               c_int32(C), c_int32(rows_per_batch), stream_ptr()), "fd_gate_residual")
+    return out
+
+
+def gate_bwd(dout, h, gate, rows_per_batch):
+    """-> dh [rows, C] bf16 = gate[b] * dout, dgate [B, C] fp32 = per-sample column sums of dout * h."""
+    lib = load(); _req(dout, BF16, "dout"); _req(h, BF16, "h"); _req(gate, torch.float32, "gate")
+    rows, C = h.shape
+    assert h.is_contiguous() and dout.is_contiguous() and gate.stride(1) == 1 and rows % rows_per_batch == 0
+    dh = torch.empty_like(h)
+    dgate = torch.empty((rows // rows_per_batch, C), device=h.device, dtype=torch.float32)
+    check(lib.fd_gate_bwd(ptr(dout), ptr(h), ptr(gate), c_int64(gate.stride(0)), ptr(dh), ptr(dgate), c_int32(rows),
+                          c_int32(C), c_int32(rows_per_batch), stream_ptr()), "fd_gate_bwd")
+    return dh, dgate
+
+
+def gelu_tanh_bwd(acc, dout):
+    lib = load(); _req(acc, BF16, "acc"); _req(dout, BF16, "dout")
+    assert acc.is_contiguous() and dout.is_contiguous() and acc.shape == dout.shape and acc.numel() % 8 == 0
+    dacc = torch.empty_like(acc)
+    check(lib.fd_gelu_tanh_bwd(ptr(acc), ptr(dout), ptr(dacc), c_int64(acc.numel()), stream_ptr()), "fd_gelu_tanh_bwd")
+    return dacc
+
+
+def patchify(dy, h, w, p, Cout):
+    """gradient of unpatchify: dy [NB, Ckeep, h*p, w*p] fp32 -> [NB*h*w, p*p*Cout] bf16"""
+    lib = load(); _req(dy, torch.float32, "dy")
+    NB, Ckeep = dy.shape[:2]
+    assert dy.is_contiguous() and dy.shape[2:] == (h * p, w * p)
+    dx = torch.empty((NB * h * w, p * p * Cout), device=dy.device, dtype=BF16)
+    check(lib.fd_patchify(ptr(dy), ptr(dx), c_int32(NB), c_int32(h), c_int32(w), c_int32(p), c_int32(Cout),
+                          c_int32(Ckeep), stream_ptr()), "fd_patchify")
+    return dx
+
+
 def unpatchify(x, NB, h, w, p, Cout, Ckeep):
     """x [NB*h*w, p*p*Cout] fp32 -> [NB, Ckeep, h*p, w*p] fp32"""
     lib = load(); _req(x, torch.float32, "x")

@@ -1,6 +1,8 @@
 """B200-native `DiffusersSD3Transformer2DWrapper` — SD3 MMDiT (reference src/flash/models/transformers/tranformers.py:103-163;
-constructor kwargs as at examples/train_flash_sd3.py:65-77).  FORWARD only this round (teacher / student evaluation and
-sampling); the joint-block backward and `FlashDiffusionSD3` are the next rows.
+constructor kwargs as at examples/train_flash_sd3.py:65-77).  Forward and backward: activation gradients (incl. the
+input gradient the GAN generator turn needs through the frozen backbone) and LoRA gradients for every Linear the
+reference's target list names (attention, feed-forward, AdaLN and embedding linears).  Not wrapped: the 2x2 patch
+convolution, which peft would also give a LoRA (its name ends in "proj").
 
 Kernel mapping (UPSTREAM diffusers `SD3Transformer2DModel` math, restated in oracle/sd3.py):
   PatchEmbed conv 2x2/2 + cropped sin-cos table   space-to-depth + 4-tap implicit GEMM, table added as the epilogue residual
@@ -8,8 +10,11 @@ Kernel mapping (UPSTREAM diffusers `SD3Transformer2DModel` math, restated in ora
   every AdaLN-Zero / AdaLN-continuous `linear`     ONE fd_gemm over the concatenated weights of all 24 blocks
   LN * (1+scale) + shift (image and text streams)  fd_layernorm_modulate
   joint attention (24 heads x 64)                  fused q|k|v GEMMs per stream, token concat, fd_attn_fwd (tuned d=64 kernel)
-  gate * f(x) + x                                  fd_gemm epilogue (bias -> gelu-tanh -> per-sample gate -> residual)
-  un-patchify                                      fd_unpatchify
+  gate * f(x) + x                                  fd_gemm epilogue (bias -> gelu-tanh -> per-sample gate -> residual);
+                                                   with gradients: fd_gemm, then fd_gate_residual (keeps f(x) for d gate)
+  un-patchify                                      fd_unpatchify / fd_patchify
+  backward                                         fd_layernorm_modulate_bwd, fd_gate_bwd, fd_gelu_tanh_bwd (pre-activation
+                                                   recomputed), fd_attn_bwd, fd_gemm for every dX / LoRA dA, dB
 """
 from typing import Dict, Optional, Union
 
@@ -141,14 +146,40 @@ class DiffusersSD3Transformer2DWrapper(nn.Module):
             mods += [blk.norm1, blk.norm1_context]
         return mods + [self.norm_out]
 
+    @staticmethod
+    def _silu_bf16(x):
+        """silu(fp32) -> bf16 on a [B, D] embedding; with a gradient it is three torch ops on B rows."""
+        if torch.is_grad_enabled() and x.requires_grad:
+            return torch.nn.functional.silu(x).to(torch.bfloat16)
+        return raw.silu_f32_to_bf16(x)
+
+    def _patch_embed(self, sample, B, Cin, H, W):
+        pe, D, dev = self.pos_embed, self.inner_dim, sample.device
+        hh, ww = H // 2, W // 2
+        N = hh * ww
+        cpad = (Cin + 7) // 8 * 8
+
+        def build_patch():
+            wt = pe.proj.weight.detach().float()
+            buf = torch.zeros((D, 4, 64), device=dev)
+            buf[:, :, :Cin] = wt.permute(0, 2, 3, 1).reshape(D, 4, Cin)
+            w = raw.cast_scale(buf.reshape(D, 256), 1.0)
+            return {"w": w, "w_t": raw.cast_scale(buf.reshape(D, 256).t().contiguous(), 1.0),
+                    "b": pe.proj.bias.detach().float().contiguous(),
+                    "pos": raw.cast_scale(pe.cropped(hh, ww).to(dev).contiguous(), 1.0)}
+        pk = cache_of(pe.proj).get(("patch", hh, ww), [pe.proj.weight, pe.proj.bias], build_patch)
+        pos_b = self._pack(("pos_tiled", B, N), lambda: pk["pos"].repeat(B, 1).contiguous())
+        geom = (B, Cin, H, W, cpad)
+        if torch.is_grad_enabled() and sample.requires_grad:
+            return _PatchEmbedFn.apply(sample.float(), pk, pos_b, geom)
+        return _patch_embed_fwd(sample.float(), pk, pos_b, geom)
+
     def forward(self, sample: torch.Tensor, timestep: Union[torch.Tensor, float, int],
                 conditioning: Dict[str, torch.Tensor], hidden_states_masks: Optional[torch.Tensor] = None,
                 *args, **kwargs):
         assert isinstance(conditioning, dict), "conditionings must be a dictionary"
         if not sample.is_cuda:
             raise RuntimeError("DiffusersSD3Transformer2DWrapper runs only on CUDA (B200) tensors: there is no CPU fallback")
-        if torch.is_grad_enabled() and (sample.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError("SD3 MMDiT backward is the next row; call under torch.no_grad()")
         cond = conditioning["cond"]
         pooled, crossattn, concat = cond.get("vector"), cond.get("crossattn"), cond.get("concat")
         c_keep = sample.shape[1]
@@ -158,84 +189,113 @@ class DiffusersSD3Transformer2DWrapper(nn.Module):
         dev, p, D, Hh = sample.device, self.patch_size, self.inner_dim, self.heads
         hh, ww = H // p, W // p
         N, T = hh * ww, crossattn.shape[1]
-        with torch.no_grad():
-            if not torch.is_tensor(timestep):
-                timestep = torch.tensor([float(timestep)], dtype=torch.float32, device=dev)
-            timestep = timestep.to(device=dev, dtype=torch.float32).reshape(-1)
-            if timestep.numel() == 1 and B > 1:
-                timestep = timestep.expand(B)
-            timestep = timestep.contiguous()
-            # temb = timestep_embedder(sinusoid(t)) + text_embedder(pooled): both second Linears as ONE two-segment GEMM
-            tt = self.time_text_embed
-            te1 = self._pack("te1", lambda: LinearPack(tt.timestep_embedder.linear_1))
-            te2 = self._pack("te2", lambda: LinearPack(tt.timestep_embedder.linear_2))
-            tx1 = self._pack("tx1", lambda: LinearPack(tt.text_embedder.linear_1))
-            tx2 = self._pack("tx2", lambda: LinearPack(tt.text_embedder.linear_2))
-            ht = raw.silu_f32_to_bf16(self._lin(raw.timestep_embedding(timestep, 256), te1, out_fp32=True))
-            hp_ = raw.silu_f32_to_bf16(self._lin(raw.cast_scale(pooled.detach().float().contiguous(), 1.0), tx1, out_fp32=True))
+        if not torch.is_tensor(timestep):
+            timestep = torch.tensor([float(timestep)], dtype=torch.float32, device=dev)
+        timestep = timestep.detach().to(device=dev, dtype=torch.float32).reshape(-1)
+        if timestep.numel() == 1 and B > 1:
+            timestep = timestep.expand(B)
+        timestep = timestep.contiguous()
+        tt = self.time_text_embed
+        te1 = self._pack("te1", lambda: LinearPack(tt.timestep_embedder.linear_1))
+        te2 = self._pack("te2", lambda: LinearPack(tt.timestep_embedder.linear_2))
+        tx1 = self._pack("tx1", lambda: LinearPack(tt.text_embedder.linear_1))
+        tx2 = self._pack("tx2", lambda: LinearPack(tt.text_embedder.linear_2))
+        ada = self._all_ada()
+        ada_pack = self._pack("ada_all", lambda: LinearPack([m.linear for m in ada]))
+        # `tuning` = the embedding / AdaLN linears carry trainable adapters (the reference's SD3 LoRA targets do): their
+        # gradients need per-module products, so the one-GEMM fusions below are used only without them
+        tuning = torch.is_grad_enabled() and any(q.requires_grad for pk in (te1, te2, tx1, tx2, ada_pack)
+                                                 for q in pk.lora_params())
+        t_in = raw.timestep_embedding(timestep, 256)
+        p_in = raw.cast_scale(pooled.detach().float().contiguous(), 1.0)
+        ht = self._silu_bf16(ops.linear(t_in, te1, out_fp32=True))
+        hp_ = self._silu_bf16(ops.linear(p_in, tx1, out_fp32=True))
+        if tuning:
+            temb = ops.linear(ht, te2, out_fp32=True) + ops.linear(hp_, tx2, out_fp32=True)
+            s_temb = self._silu_bf16(temb)
+            mods = [ops.linear(s_temb, self._pack(("ada", id(m)), lambda m=m: LinearPack(m.linear)), out_fp32=True)
+                    .view(B, -1, D) for m in ada]
+            mod = lambda idx: mods[idx]
+        else:
+            # temb = timestep_embedder(sinusoid(t)) + text_embedder(pooled): both second Linears as ONE two-segment
+            # GEMM, then every AdaLN linear of the network in one GEMM
             p2, q2 = te2.pack(), tx2.pack()
             bsum = self._pack("temb_bias", lambda: (p2["b"] + q2["b"]).contiguous())
-            temb = raw.gemm(ht, p2["w"], a2=hp_, b2=q2["w"], bias=bsum, out_fp32=True)
-            # all AdaLN linears of the network in one GEMM
-            ada = self._all_ada()
-            ada_pack = self._pack("ada_all", lambda: LinearPack([m.linear for m in ada]))
+            if te2.has_lora or tx2.has_lora:
+                temb = self._lin(ht, te2, out_fp32=True) + self._lin(hp_, tx2, out_fp32=True)
+            else:
+                temb = raw.gemm(ht, p2["w"], a2=hp_, b2=q2["w"], bias=bsum, out_fp32=True)
             mod_all = self._lin(raw.silu_f32_to_bf16(temb), ada_pack, out_fp32=True)          # [B, sum(chunks)*D]
             offs, off = [], 0
             for m in ada:
                 n_out = m.linear.weight.shape[0]
                 offs.append((off, n_out // D))
                 off += n_out
-            # context + patch embedding
-            c = self._lin(raw.cast_scale(crossattn.detach().float().contiguous().view(B * T, -1), 1.0),
-                          self._pack("ctx", lambda: LinearPack(self.context_embedder)))
-            cpad = (Cin + 7) // 8 * 8
-            x = raw.space_to_depth(raw.nchw_to_nhwc(sample.float(), cpad).view(B * H * W, cpad), B, H, W, cpad)
-            pe = self.pos_embed
-
-            def build_patch():
-                wt = pe.proj.weight.detach().float()
-                buf = torch.zeros((D, 4, 64), device=dev)
-                buf[:, :, :Cin] = wt.permute(0, 2, 3, 1).reshape(D, 4, Cin)
-                return {"w": raw.cast_scale(buf.reshape(D, 256), 1.0), "b": pe.proj.bias.detach().float().contiguous(),
-                        "pos": raw.cast_scale(pe.cropped(hh, ww).to(dev).contiguous(), 1.0)}
-            pk = cache_of(pe.proj).get(("patch", hh, ww), [pe.proj.weight, pe.proj.bias], build_patch)
-            pos_b = self._pack(("pos_tiled", B, N), lambda: pk["pos"].repeat(B, 1).contiguous())
-            h = raw.gemm(x, pk["w"], bias=pk["b"], residual=pos_b, M=B * N,
-                         conv=dict(NB_in=4 * B, H=hh, W=ww, C=cpad, taps=[(ph * B, 0, 0) for ph in range(4)]))
 
             def mod(idx):
                 o, k = offs[idx]
                 return mod_all[:, o:o + k * D].view(B, k, D)
 
-            inner = Hh * 64
-            for li, blk in enumerate(self.transformer_blocks):
-                mx, mc = mod(2 * li), mod(2 * li + 1)        # image: shift,scale,gate (msa), shift,scale,gate (mlp)
-                a = blk.attn
-                nx = raw.layernorm_modulate(h, mx[:, 1], mx[:, 0], N, 1e-6)
-                if blk.pre_only:
-                    nc = raw.layernorm_modulate(c, mc[:, 0], mc[:, 1], T, 1e-6)       # AdaLN-continuous: (scale, shift)
-                else:
-                    nc = raw.layernorm_modulate(c, mc[:, 1], mc[:, 0], T, 1e-6)
-                qkv_x = self._lin(nx, self._pack(("qkv", id(a)), lambda: LinearPack([a.to_q, a.to_k, a.to_v])))
-                qkv_c = self._lin(nc, self._pack(("aqkv", id(a)), lambda: LinearPack([a.add_q_proj, a.add_k_proj, a.add_v_proj])))
-                joint = torch.cat([qkv_x.view(B, N, 3 * inner), qkv_c.view(B, T, 3 * inner)], dim=1)
-                o = ops.attention_self(joint, Hh)
-                ox = o[:, :N].reshape(B * N, inner)
-                h = self._lin(ox, self._pack(("o", id(a)), lambda: LinearPack(a.to_out[0])), residual=h,
-                              rowscale=mx[:, 2], rows_per_group_scale=N)
-                n2 = raw.layernorm_modulate(h, mx[:, 4], mx[:, 3], N, 1e-6)
-                f = self._lin(n2, self._pack(("ff1", id(blk)), lambda: LinearPack(blk.ff.net[0].proj)), act=1)
-                h = self._lin(f, self._pack(("ff2", id(blk)), lambda: LinearPack(blk.ff.net[2])), residual=h,
-                              rowscale=mx[:, 5], rows_per_group_scale=N)
-                if not blk.pre_only:
-                    oc = o[:, N:].reshape(B * T, inner)
-                    c = self._lin(oc, self._pack(("ao", id(a)), lambda: LinearPack(a.to_add_out)), residual=c,
-                                  rowscale=mc[:, 2], rows_per_group_scale=T)
-                    nc2 = raw.layernorm_modulate(c, mc[:, 4], mc[:, 3], T, 1e-6)
-                    fc = self._lin(nc2, self._pack(("cff1", id(blk)), lambda: LinearPack(blk.ff_context.net[0].proj)), act=1)
-                    c = self._lin(fc, self._pack(("cff2", id(blk)), lambda: LinearPack(blk.ff_context.net[2])), residual=c,
-                                  rowscale=mc[:, 5], rows_per_group_scale=T)
-            mo = mod(len(ada) - 1)                                                          # (scale, shift)
-            nf = raw.layernorm_modulate(h, mo[:, 0], mo[:, 1], N, 1e-6)
-            out = self._lin(nf, self._pack("proj_out", lambda: LinearPack(self.proj_out)), out_fp32=True)
-            return raw.unpatchify(out, B, hh, ww, p, self.out_channels, c_keep)
+        c = ops.linear(raw.cast_scale(crossattn.detach().float().contiguous().view(B * T, -1), 1.0),
+                       self._pack("ctx", lambda: LinearPack(self.context_embedder)))
+        h = self._patch_embed(sample, B, Cin, H, W)
+
+        inner = Hh * 64
+        for li, blk in enumerate(self.transformer_blocks):
+            mx, mc = mod(2 * li), mod(2 * li + 1)        # image: shift,scale,gate (msa), shift,scale,gate (mlp)
+            a = blk.attn
+            nx = ops.modulate(h, mx[:, 1], mx[:, 0], N)
+            if blk.pre_only:
+                nc = ops.modulate(c, mc[:, 0], mc[:, 1], T)           # AdaLN-continuous: (scale, shift)
+            else:
+                nc = ops.modulate(c, mc[:, 1], mc[:, 0], T)
+            qkv_x = ops.linear(nx, self._pack(("qkv", id(a)), lambda: LinearPack([a.to_q, a.to_k, a.to_v])))
+            qkv_c = ops.linear(nc, self._pack(("aqkv", id(a)), lambda: LinearPack([a.add_q_proj, a.add_k_proj, a.add_v_proj])))
+            joint = torch.cat([qkv_x.view(B, N, 3 * inner), qkv_c.view(B, T, 3 * inner)], dim=1)
+            o = ops.attention_self(joint, Hh)
+            ox = o[:, :N].reshape(B * N, inner)
+            h = ops.gated_linear(ox, self._pack(("o", id(a)), lambda: LinearPack(a.to_out[0])), mx[:, 2], h, N)
+            n2 = ops.modulate(h, mx[:, 4], mx[:, 3], N)
+            f = ops.linear(n2, self._pack(("ff1", id(blk)), lambda: LinearPack(blk.ff.net[0].proj)), act=1)
+            h = ops.gated_linear(f, self._pack(("ff2", id(blk)), lambda: LinearPack(blk.ff.net[2])), mx[:, 5], h, N)
+            if not blk.pre_only:
+                oc = o[:, N:].reshape(B * T, inner)
+                c = ops.gated_linear(oc, self._pack(("ao", id(a)), lambda: LinearPack(a.to_add_out)), mc[:, 2], c, T)
+                nc2 = ops.modulate(c, mc[:, 4], mc[:, 3], T)
+                fc = ops.linear(nc2, self._pack(("cff1", id(blk)), lambda: LinearPack(blk.ff_context.net[0].proj)), act=1)
+                c = ops.gated_linear(fc, self._pack(("cff2", id(blk)), lambda: LinearPack(blk.ff_context.net[2])),
+                                     mc[:, 5], c, T)
+        mo = mod(len(ada) - 1)                                                          # (scale, shift)
+        nf = ops.modulate(h, mo[:, 0], mo[:, 1], N)
+        out = ops.linear(nf, self._pack("proj_out", lambda: LinearPack(self.proj_out)), out_fp32=True)
+        return ops.unpatchify(out, B, hh, ww, p, self.out_channels, c_keep)
+
+
+def _patch_embed_fwd(sample, pk, pos_b, geom):
+    """2x2/2 patch convolution + position table: space-to-depth, then a 4-tap implicit GEMM whose taps are the four
+    phase images; the table rides in the epilogue as the residual."""
+    B, Cin, H, W, cpad = geom
+    hh, ww = H // 2, W // 2
+    x = raw.space_to_depth(raw.nchw_to_nhwc(sample, cpad).view(B * H * W, cpad), B, H, W, cpad)
+    return raw.gemm(x, pk["w"], bias=pk["b"], residual=pos_b, M=B * hh * ww,
+                    conv=dict(NB_in=4 * B, H=hh, W=ww, C=cpad, taps=[(ph * B, 0, 0) for ph in range(4)]))
+
+
+class _PatchEmbedFn(torch.autograd.Function):
+    """Input gradient of the patch embedding (the GAN generator turn differentiates the frozen backbone with respect
+    to its input, reference flash_sd3/flash_diffusion_model.py:560-565): d(tokens) W gives the four phase images,
+    depth-to-space and NHWC->NCHW undo the forward re-layout."""
+
+    @staticmethod
+    def forward(ctx, sample, pk, pos_b, geom):
+        ctx.pk, ctx.geom = pk, geom
+        return _patch_embed_fwd(sample, pk, pos_b, geom)
+
+    @staticmethod
+    def backward(ctx, dh):
+        B, Cin, H, W, cpad = ctx.geom
+        hh, ww = H // 2, W // 2
+        d = raw.gemm(dh.contiguous(), ctx.pk["w_t"])                                  # [B*N, 4*64], column = tap*64 + c
+        phases = d.view(B * hh * ww, 4, 64)[:, :, :cpad].permute(1, 0, 2).contiguous().view(4 * B * hh * ww, cpad)
+        dx = raw.depth_to_space(phases, B, H, W, cpad)
+        return raw.nhwc_to_nchw(dx, B, Cin, H, W), None, None, None

@@ -125,6 +125,20 @@ int fd_layernorm_bwd(const void* x, const float* stats, const float* gamma, cons
  * Transformer2DModel output norm (reference src/flash/models/transformers/tranformers.py:83-92). */
 int fd_layernorm_modulate(const void* x, const float* scale, const float* shift, int64_t ld_mod, void* y,
                           int32_t rows, int32_t C, int32_t rows_per_batch, float eps, void* stream);
+/* Backward of fd_layernorm_modulate (student LoRA backward through the MMDiT AdaLN blocks; reference autograd of
+ * tranformers.py:103-150 under examples/train_flash_sd3.py:101-120, whose LoRA targets include every AdaLN linear):
+ * dx [rows, C] bf16; dscale / dshift [rows/rows_per_batch, C] fp32 (dense, overwritten) = per-sample column sums of
+ * dy * xhat and dy. */
+int fd_layernorm_modulate_bwd(const void* x, const void* dy, const float* scale, int64_t ld_mod, void* dx,
+                              float* dscale, float* dshift, int32_t rows, int32_t C, int32_t rows_per_batch,
+                              float eps, void* stream);
+/* AdaLN-Zero gate: out = res + gate[b] * h (training-time form of the fd_gemm rowscale + residual epilogue, which
+ * keeps h for the gate gradient), and its backward dh = gate[b] * dout, dgate[b, c] = sum_rows dout * h
+ * ([rows/rows_per_batch, C] fp32, overwritten).  gate fp32 with row stride ld_gate. */
+int fd_gate_residual(const void* h, const float* gate, int64_t ld_gate, const void* res, void* out, int32_t rows,
+                     int32_t C, int32_t rows_per_batch, void* stream);
+int fd_gate_bwd(const void* dout, const void* h, const float* gate, int64_t ld_gate, void* dh, float* dgate,
+                int32_t rows, int32_t C, int32_t rows_per_batch, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Attention (softmax(Q K^T / sqrt(d)) V), d = 64, bf16, fp32 softmax.
@@ -171,6 +185,9 @@ int fd_nhwc_to_nchw(const void* x, int32_t x_is_fp32, int64_t ld, float* y, int3
  * [NB, Ckeep, h*p, w*p] keeping the first Ckeep channels (reference tranformers.py:92 slices `[:, :in_channels]`). */
 int fd_unpatchify(const float* x, float* y, int32_t NB, int32_t h, int32_t w, int32_t p, int32_t Cout, int32_t Ckeep,
                   void* stream);
+/* gradient of fd_unpatchify: dy NCHW fp32 [NB, Ckeep, h*p, w*p] -> dx [NB*h*w, p*p*Cout] bf16 (zero for c >= Ckeep) */
+int fd_patchify(const float* dy, void* dx, int32_t NB, int32_t h, int32_t w, int32_t p, int32_t Cout, int32_t Ckeep,
+                void* stream);
 /* nearest-neighbour 2x upsample, NHWC bf16 (UPSTREAM Upsample2D) */
 int fd_upsample2x(const void* x, void* y, int32_t NB, int32_t H, int32_t W, int32_t C,
                   void* stream);
@@ -205,6 +222,9 @@ int fd_timestep_embedding(const float* t, void* y, int32_t NB, int32_t dim, void
 /* GEGLU backward: given pre-activation acc (interleaved layout as written by fd_gemm with
  * geglu=0) [M, N] bf16 and dout [M, N/2], produce dacc [M, N] bf16 */
 int fd_geglu_bwd(const void* acc, const void* dout, void* dacc, int64_t M, int32_t N, void* stream);
+/* backward of the tanh-GELU the fd_gemm epilogue applies with act = 1 (UPSTREAM FeedForward "gelu-approximate"):
+ * acc = recomputed pre-activation, n elements (multiple of 8), all bf16 */
+int fd_gelu_tanh_bwd(const void* acc, const void* dout, void* dacc, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Distillation-step elementwise kernels (fp32 latents NCHW [B, C, H, W], n = C*H*W per sample)

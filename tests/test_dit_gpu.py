@@ -213,7 +213,7 @@ def _sd3_objective_pair(lora_rank, seed=0):
     return prod, ora
 
 
-@pytest.mark.parametrize("lora_rank", [0, 4])
+@pytest.mark.parametrize("lora_rank", [0, 8])
 def test_sd3_objective_teacher_rollout_and_sampler(lora_rank):
     """Teacher CFG Euler rollout (one 2B call + fused CFG/Euler kernel, graph replay) and the 4-step student sampler of
     FlashDiffusionSD3 against the same host class around the fp32 oracle MMDiT."""
@@ -238,8 +238,125 @@ def test_sd3_objective_teacher_rollout_and_sampler(lora_rank):
         assert _rel(sa, sb) < 3e-2 and _rel(ta, tb) < 3e-2, (_rel(sa, sb), _rel(ta, tb))
 
 
-def test_sd3_objective_training_forward_raises_on_cuda_student():
+# ------------------------------------------------------------------------------------------- MMDiT backward
+def test_dit_backward_kernels():
+    from flash.b200 import raw
+    g = torch.Generator(device="cuda").manual_seed(0)
+    B, N, C = 3, 70, 192
+    x = torch.randn(B * N, C, device="cuda", generator=g).bfloat16()
+    dy = torch.randn(B * N, C, device="cuda", generator=g).bfloat16()
+    mod = 0.3 * torch.randn(B, 3, C, device="cuda", generator=g)
+    scale, shift, gate = mod[:, 0], mod[:, 1], mod[:, 2]
+    # AdaLN modulation backward vs autograd of the fp32 formula
+    xr = x.float().requires_grad_(True)
+    sc, sh = scale.clone().requires_grad_(True), shift.clone().requires_grad_(True)
+    y = F.layer_norm(xr, (C,), eps=1e-6).view(B, N, C) * (1 + sc[:, None]) + sh[:, None]
+    y.backward(dy.float().view(B, N, C))
+    dx, dsc, dsh = raw.layernorm_modulate_bwd(x, dy, scale, N, 1e-6)
+    assert _rel(dx, xr.grad) < 1e-2 and _rel(dsc, sc.grad) < 1e-3 and _rel(dsh, sh.grad) < 1e-3
+    # gate: out = res + gate * h
+    h = torch.randn(B * N, C, device="cuda", generator=g).bfloat16()
+    res = torch.randn(B * N, C, device="cuda", generator=g).bfloat16()
+    out = raw.gate_residual(h, gate, res, N)
+    ref = res.float().view(B, N, C) + gate[:, None] * h.float().view(B, N, C)
+    assert _rel(out, ref.view(B * N, C)) < 5e-3
+    dh, dg = raw.gate_bwd(dy, h, gate, N)
+    assert _rel(dh, (gate[:, None] * dy.float().view(B, N, C)).view(B * N, C)) < 5e-3
+    assert _rel(dg, (dy.float() * h.float()).view(B, N, C).sum(1)) < 1e-3
+    # tanh-GELU backward
+    a = torch.randn(B * N, C, device="cuda", generator=g).bfloat16()
+    ar = a.float().requires_grad_(True)
+    F.gelu(ar, approximate="tanh").backward(dy.float())
+    assert _rel(raw.gelu_tanh_bwd(a, dy), ar.grad) < 5e-3
+    # patchify = gradient of un-patchify
+    tok = torch.randn(2 * 4 * 5, 2 * 2 * 8, device="cuda", generator=g).requires_grad_(True)
+    img = torch.einsum("nhwpqc->nchpwq", tok.view(2, 4, 5, 2, 2, 8)).reshape(2, 8, 8, 10)[:, :6]
+    d_img = torch.randn(2, 6, 8, 10, device="cuda", generator=g)
+    img.backward(d_img)
+    assert _rel(raw.patchify(d_img.contiguous(), 4, 5, 2, 8), tok.grad) < 5e-3
+    assert torch.equal(raw.unpatchify(tok.detach().contiguous(), 2, 4, 5, 2, 8, 6), img.detach())
+
+
+def _sd3_lora_pair(seed=0, rank=8):
+    from flash.models.lora import LoraConfig
+    from flash.recipes import SD3_LORA_TARGETS
+    from oracle.unet import LoraConfig as OLoraConfig
+    from oracle.unet import UNet2DConditionOracle
+    prod, ora = _sd3_pair(SD3_SMALL, seed=seed)
+    cfg = dict(r=rank, lora_alpha=rank, target_modules=SD3_LORA_TARGETS)
+    ora = ora.cpu()
+    UNet2DConditionOracle.add_adapter(ora, OLoraConfig(**cfg))
+    prod.add_adapter(LoraConfig(**cfg))
+    with torch.no_grad():
+        for n, p in ora.named_parameters():
+            if "lora_B" in n:
+                p.normal_(0, 0.05)
+    ora = ora.cuda()
+    prod.load_state_dict(ora.state_dict())
+    prod.train(); ora.train()
+    return prod, ora
+
+
+def test_small_sd3_lora_backward_matches_oracle():
+    """Student LoRA backward through the MMDiT (reference autograd of tranformers.py:103-150 under the LoRA targets of
+    examples/train_flash_sd3.py:104-117): every LoRA gradient and the input gradient against fp32 autograd."""
+    prod, ora = _sd3_lora_pair()
+    x, t, cond = _sd3_inputs(2, 16, 9, 48, 40)
+    w = torch.randn(2, 16, 16, 16, device="cuda")
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya, yb = prod(xa, t, cond), ora(xb, t, cond)
+    assert _rel(ya, yb) < 2e-2, _rel(ya, yb)
+    (ya * w).sum().backward()
+    (yb * w).sum().backward()
+    assert _rel(xa.grad, xb.grad) < 3e-2, _rel(xa.grad, xb.grad)
+    ga = {n: p.grad for n, p in prod.named_parameters() if p.requires_grad}
+    gb = {n: p.grad for n, p in ora.named_parameters() if p.requires_grad}
+    assert set(ga) == set(gb) and len(ga) > 40
+    assert all(g is not None for g in ga.values())
+    worst = max((_rel(ga[n], gb[n]), n) for n in ga if gb[n].norm() > 1e-6 * max(v.norm() for v in gb.values()))
+    assert worst[0] < 6e-2, worst
+    tot_a = torch.cat([ga[n].flatten() for n in sorted(ga)])
+    tot_b = torch.cat([gb[n].flatten() for n in sorted(ga)])
+    assert _rel(tot_a, tot_b) < 3e-2, _rel(tot_a, tot_b)
+
+
+def test_small_sd3_frozen_backbone_input_gradient():
+    """GAN generator turn: gradient with respect to the INPUT of the frozen backbone (no parameter gradients)."""
+    prod, ora = _sd3_pair(SD3_SMALL, seed=2)
+    x, t, cond = _sd3_inputs(2, 16, 9, 48, 40)
+    w = torch.randn(2, 16, 16, 16, device="cuda")
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    (prod(xa, t, cond) * w).sum().backward()
+    (ora(xb, t, cond) * w).sum().backward()
+    assert _rel(xa.grad, xb.grad) < 3e-2, _rel(xa.grad, xb.grad)
+
+
+def test_sd3_objective_training_step_on_gpu():
+    """FlashDiffusionSD3.forward on the B200 kernels (generator and discriminator turns) against the same host class
+    around the fp32 oracle MMDiT: losses, student output and the LoRA gradient of the generator objective."""
     from flash.recipes import sd3_batch
-    prod, _ = _sd3_objective_pair(4)
-    with pytest.raises(NotImplementedError, match="backward"):
-        prod(sd3_batch(2, 3, "cuda", kwargs=SD3_SMALL, tokens=9, hw=16), draws={"start_idx": 1})
+    prod, ora = _sd3_objective_pair(8)
+    torch.manual_seed(4)       # the recipe's discriminator is sized for 128x128 latents; 16x16 here
+    disc = torch.nn.Sequential(torch.nn.Conv2d(16, 8, 4, 2, 1, bias=False), torch.nn.SiLU(True),
+                               torch.nn.Conv2d(8, 1, 4, 1, 0, bias=False), torch.nn.Flatten()).cuda()
+    prod.discriminator = disc
+    ora._modules["discriminator"] = disc
+    batch = sd3_batch(2, 3, "cuda", kwargs=SD3_SMALL, tokens=9, hw=16)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    r = lambda: torch.randn(2, 16, 16, 16, device="cuda", generator=g)
+    draws = {"noise": r(), "start_idx": 1, "guidance": 9.5, "dmd_noise": r(), "dmd_index": torch.tensor([137, 902]),
+             "dmd_guidance": 11.0, "gan_noise": r(), "gan_choice": torch.tensor([2, 0])}
+    for step in (0, 1):
+        a = prod(batch, step=step, draws=draws)
+        b = ora(batch, step=step, draws=draws)
+        assert _rel(a["student_output"], b["student_output"]) < 3e-2
+        assert _rel(a["teacher_output"], b["teacher_output"]) < 3e-2
+        assert abs(float(a["loss"][0]) - float(b["loss"][0])) < 5e-2 * abs(float(b["loss"][0]))
+        if step == 1:
+            assert abs(float(a["loss"][1]) - float(b["loss"][1])) < 5e-2 * abs(float(b["loss"][1]))
+    out = prod(batch, step=0, draws=draws)
+    out["loss"][0].backward()
+    grads = [p.grad for n, p in prod.student_denoiser.named_parameters() if p.requires_grad]
+    assert all(g_ is not None and torch.isfinite(g_).all() for g_ in grads)
+    assert sum(float(g_.norm()) for g_ in grads) > 0
+    assert all(p.grad is None for p in prod.teacher_denoiser.parameters())
