@@ -7,7 +7,7 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -cudart static"
 OBJS=""
 pids=()
-for f in fd_api fd_gemm fd_norm fd_elem fd_attn fd_attn_bwd fd_attn_generic; do
+for f in fd_api fd_gemm fd_norm fd_elem fd_attn fd_attn_bwd fd_attn_generic fd_attn_bwd_generic; do
   [ -f $f.cu ] || continue
   if [ ! -f ../lib/$f.o ] || [ $f.cu -nt ../lib/$f.o ] || [ fd_common.cuh -nt ../lib/$f.o ] || [ fd_host.h -nt ../lib/$f.o ] || [ ../../include/flashb200.h -nt ../lib/$f.o ]; then
     $NVCC $FLAGS ${PTXAS_V:+-Xptxas -v} -c $f.cu -o ../lib/$f.o &

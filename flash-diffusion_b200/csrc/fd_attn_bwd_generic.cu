@@ -7,8 +7,8 @@
 //    TMA box reads past d belong to the next head and are never multiplied), the products whose N dimension is d use
 //    instruction N = d over MN-major descriptors that span the sub-tiles.  TMEM: S [0,128), dP [128,256),
 //    dV [256,256+d), dK [384,384+d); dQ re-uses the S columns [0,d) once the softmax warps have consumed S.
-//  * attn_bwd_small_kernel: CUDA-core kernel for short sequences (Nq, Nkv <= 128) at any head dim (SD1.5's deepest
-//    level: d = 160 at 8x8 = 64 queries, 64 / 77 keys — 0.02% of the step's attention FLOPs); one CTA per (head, batch).
+//  * attn_bwd_small_*: three CUDA-core passes (P / dS into a global scratch, then dK|dV and dQ) for larger head dims at
+//    short sequences — SD1.5's d = 160 levels: 16x16 and 8x8 tokens, 77 text keys, ~1% of that UNet's attention FLOPs.
 //
 // UPSTREAM math: autograd of F.scaled_dot_product_attention(q, k, v, attn_mask=key padding) under the student LoRA
 // backward (reference src/flash/models/unets/unet.py:108-119, transformers/tranformers.py:58-92).
@@ -347,78 +347,92 @@ __device__ __forceinline__ float dot_bf16(const bf16* a, const bf16* b, int d) {
     return acc;
 }
 
-// one CTA per (head, batch); P and dS [Nq][Nkv] fp32 live in shared memory
+// pass 1: P and dS [B,H,Nq,Nkv] fp32 into global scratch, one (query, key) pair per thread
 __global__ void __launch_bounds__(256)
-attn_bwd_small_kernel(const AttnBwdSParams p) {
-    extern __shared__ float sm[];
-    const int head = blockIdx.x, batch = blockIdx.y;
+attn_bwd_small_p_kernel(const AttnBwdSParams p, float* __restrict__ gP, float* __restrict__ gDS) {
+    const int head = blockIdx.y, batch = blockIdx.z;
     const int Nq = p.Nq, Nkv = p.Nkv, d = p.d;
-    float* sP = sm;
-    float* sDS = sm + Nq * Nkv;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)Nq * Nkv) return;
+    const int i = (int)(e / Nkv), j = (int)(e - (long long)i * Nkv);
     const bf16* q = p.q + (long long)batch * p.q_bs + head * d;
     const bf16* k = p.k + (long long)batch * p.k_bs + head * d;
     const bf16* v = p.v + (long long)batch * p.v_bs + head * d;
     const bf16* dO = p.d_o + (long long)batch * p.do_bs + head * d;
-    const float* lse = p.lse + ((long long)batch * p.H + head) * Nq;
-    const float* delta = p.delta + ((long long)batch * p.H + head) * Nq;
+    const long long bh = (long long)batch * p.H + head;
     const int nkv = p.kv_len != nullptr ? min(Nkv, max(1, p.kv_len[batch])) : Nkv;
-    for (int e = threadIdx.x; e < Nq * Nkv; e += blockDim.x) {
-        const int i = e / Nkv, j = e - i * Nkv;
-        float pr = 0.f, ds = 0.f;
-        if (j < nkv) {
-            const float s = dot_bf16(q + (long long)i * p.ldq, k + (long long)j * p.ldk, d) * p.scale;
-            pr = __expf(s - lse[i]);
-            const float dp = dot_bf16(dO + (long long)i * p.lddo, v + (long long)j * p.ldv, d);
-            ds = pr * (dp - delta[i]) * p.scale;
-        }
-        sP[e] = pr;
-        sDS[e] = ds;
+    float pr = 0.f, ds = 0.f;
+    if (j < nkv) {
+        const float s = dot_bf16(q + (long long)i * p.ldq, k + (long long)j * p.ldk, d) * p.scale;
+        pr = __expf(s - p.lse[bh * Nq + i]);
+        const float dp = dot_bf16(dO + (long long)i * p.lddo, v + (long long)j * p.ldv, d);
+        ds = pr * (dp - p.delta[bh * Nq + i]) * p.scale;
     }
-    __syncthreads();
-    const int dv8 = d / 8;
-    // dV[j, c] = sum_i P[i, j] dO[i, c] ; dK[j, c] = sum_i dS[i, j] Q[i, c]
-    for (int e = threadIdx.x; e < Nkv * dv8; e += blockDim.x) {
-        const int j = e / dv8, c = (e - j * dv8) * 8;
-        float av[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ak[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int i = 0; i < Nq; ++i) {
-            const float pr = sP[i * Nkv + j], ds = sDS[i * Nkv + j];
-            const uint4 x = *reinterpret_cast<const uint4*>(dO + (long long)i * p.lddo + c);
-            const uint4 y = *reinterpret_cast<const uint4*>(q + (long long)i * p.ldq + c);
-            const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
+    gP[bh * Nq * Nkv + e] = pr;
+    gDS[bh * Nq * Nkv + e] = ds;
+}
+
+// pass 2: dV[j, c] = sum_i P[i, j] dO[i, c] ; dK[j, c] = sum_i dS[i, j] Q[i, c]   (8 channels per thread)
+__global__ void __launch_bounds__(128)
+attn_bwd_small_kv_kernel(const AttnBwdSParams p, const float* __restrict__ gP, const float* __restrict__ gDS) {
+    const int head = blockIdx.y, batch = blockIdx.z;
+    const int Nq = p.Nq, Nkv = p.Nkv, d = p.d, dv8 = d / 8;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= Nkv * dv8) return;
+    const int j = e / dv8, c = (e - j * dv8) * 8;
+    const bf16* q = p.q + (long long)batch * p.q_bs + head * d;
+    const bf16* dO = p.d_o + (long long)batch * p.do_bs + head * d;
+    const long long bh = (long long)batch * p.H + head;
+    const float* P = gP + bh * Nq * Nkv;
+    const float* DS = gDS + bh * Nq * Nkv;
+    float av[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ak[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < Nq; ++i) {
+        const float pr = P[(long long)i * Nkv + j], ds = DS[(long long)i * Nkv + j];
+        const uint4 x = *reinterpret_cast<const uint4*>(dO + (long long)i * p.lddo + c);
+        const uint4 y = *reinterpret_cast<const uint4*>(q + (long long)i * p.ldq + c);
+        const uint32_t xs[4] = {x.x, x.y, x.z, x.w}, ys[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const float2 a = unpack_bf16x2(xs[t]), b = unpack_bf16x2(ys[t]);
-                av[2 * t] += pr * a.x; av[2 * t + 1] += pr * a.y;
-                ak[2 * t] += ds * b.x; ak[2 * t + 1] += ds * b.y;
-            }
+        for (int t = 0; t < 4; ++t) {
+            const float2 a = unpack_bf16x2(xs[t]), b = unpack_bf16x2(ys[t]);
+            av[2 * t] += pr * a.x; av[2 * t + 1] += pr * a.y;
+            ak[2 * t] += ds * b.x; ak[2 * t + 1] += ds * b.y;
         }
-        uint4 u, w;
-        u.x = pack_bf16x2(av[0], av[1]); u.y = pack_bf16x2(av[2], av[3]);
-        u.z = pack_bf16x2(av[4], av[5]); u.w = pack_bf16x2(av[6], av[7]);
-        w.x = pack_bf16x2(ak[0], ak[1]); w.y = pack_bf16x2(ak[2], ak[3]);
-        w.z = pack_bf16x2(ak[4], ak[5]); w.w = pack_bf16x2(ak[6], ak[7]);
-        *reinterpret_cast<uint4*>(p.dv + (long long)batch * p.dv_bs + (long long)j * p.lddv + head * d + c) = u;
-        *reinterpret_cast<uint4*>(p.dk + (long long)batch * p.dk_bs + (long long)j * p.lddk + head * d + c) = w;
     }
-    // dQ[i, c] = sum_j dS[i, j] K[j, c]
-    for (int e = threadIdx.x; e < Nq * dv8; e += blockDim.x) {
-        const int i = e / dv8, c = (e - i * dv8) * 8;
-        float aq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        for (int j = 0; j < nkv; ++j) {
-            const float ds = sDS[i * Nkv + j];
-            const uint4 y = *reinterpret_cast<const uint4*>(k + (long long)j * p.ldk + c);
-            const uint32_t ys[4] = {y.x, y.y, y.z, y.w};
+    uint4 u, w;
+    u.x = pack_bf16x2(av[0], av[1]); u.y = pack_bf16x2(av[2], av[3]);
+    u.z = pack_bf16x2(av[4], av[5]); u.w = pack_bf16x2(av[6], av[7]);
+    w.x = pack_bf16x2(ak[0], ak[1]); w.y = pack_bf16x2(ak[2], ak[3]);
+    w.z = pack_bf16x2(ak[4], ak[5]); w.w = pack_bf16x2(ak[6], ak[7]);
+    *reinterpret_cast<uint4*>(p.dv + (long long)batch * p.dv_bs + (long long)j * p.lddv + head * d + c) = u;
+    *reinterpret_cast<uint4*>(p.dk + (long long)batch * p.dk_bs + (long long)j * p.lddk + head * d + c) = w;
+}
+
+// pass 3: dQ[i, c] = sum_j dS[i, j] K[j, c]
+__global__ void __launch_bounds__(128)
+attn_bwd_small_q_kernel(const AttnBwdSParams p, const float* __restrict__ gDS) {
+    const int head = blockIdx.y, batch = blockIdx.z;
+    const int Nq = p.Nq, Nkv = p.Nkv, d = p.d, dv8 = d / 8;
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= Nq * dv8) return;
+    const int i = e / dv8, c = (e - i * dv8) * 8;
+    const bf16* k = p.k + (long long)batch * p.k_bs + head * d;
+    const long long bh = (long long)batch * p.H + head;
+    const float* DS = gDS + bh * Nq * Nkv + (long long)i * Nkv;
+    float aq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int j = 0; j < Nkv; ++j) {
+        const float ds = DS[j];
+        const uint4 y = *reinterpret_cast<const uint4*>(k + (long long)j * p.ldk + c);
+        const uint32_t ys[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                const float2 b = unpack_bf16x2(ys[t]);
-                aq[2 * t] += ds * b.x; aq[2 * t + 1] += ds * b.y;
-            }
+        for (int t = 0; t < 4; ++t) {
+            const float2 b = unpack_bf16x2(ys[t]);
+            aq[2 * t] += ds * b.x; aq[2 * t + 1] += ds * b.y;
         }
-        uint4 u;
-        u.x = pack_bf16x2(aq[0], aq[1]); u.y = pack_bf16x2(aq[2], aq[3]);
-        u.z = pack_bf16x2(aq[4], aq[5]); u.w = pack_bf16x2(aq[6], aq[7]);
-        *reinterpret_cast<uint4*>(p.dq + (long long)batch * p.dq_bs + (long long)i * p.lddq + head * d + c) = u;
     }
+    uint4 u;
+    u.x = pack_bf16x2(aq[0], aq[1]); u.y = pack_bf16x2(aq[2], aq[3]);
+    u.z = pack_bf16x2(aq[4], aq[5]); u.w = pack_bf16x2(aq[6], aq[7]);
+    *reinterpret_cast<uint4*>(p.dq + (long long)batch * p.dq_bs + (long long)i * p.lddq + head * d + c) = u;
 }
 
 static int gb_tmap(CUtensorMap* m, const void* base, int HD, int N, int B, int64_t ld, int64_t bs) {
@@ -465,9 +479,11 @@ extern "C" int fd_attn_bwd_generic(const FdAttnBwdArgs* a, int32_t head_dim, con
     FD_CHECK_LAUNCH();
 
     if (d > 80) {
-        // CUDA-core kernel for short sequences
-        FD_CHECK_ARG(f.Nq <= 128 && f.Nkv <= 128,
-                     "fd_attn_bwd_generic: head_dim %d > 80 is supported for Nq, Nkv <= 128 (got %d, %d)", d, f.Nq, f.Nkv);
+        // CUDA-core path for short sequences; dq_accum is the P / dS scratch (2 * B*H*Nq*Nkv floats)
+        FD_CHECK_ARG(a->dq_accum != nullptr, "fd_attn_bwd_generic: scratch required");
+        FD_CHECK_ARG((long long)f.Nq * f.Nkv <= (1LL << 20),
+                     "fd_attn_bwd_generic: head_dim %d > 80 runs the short-sequence kernel (Nq*Nkv <= 2^20, got %d x %d)",
+                     d, f.Nq, f.Nkv);
         AttnBwdSParams s;
         s.Nq = f.Nq; s.Nkv = f.Nkv; s.H = f.H; s.d = d; s.scale = f.scale;
         s.q = (const bf16*)f.q; s.k = (const bf16*)f.k; s.v = (const bf16*)f.v; s.d_o = (const bf16*)a->d_o;
@@ -477,15 +493,15 @@ extern "C" int fd_attn_bwd_generic(const FdAttnBwdArgs* a, int32_t head_dim, con
         s.dq = (bf16*)a->dq; s.dk = (bf16*)a->dk; s.dv = (bf16*)a->dv;
         s.lddq = a->lddq; s.dq_bs = a->dq_batch_stride; s.lddk = a->lddk; s.dk_bs = a->dk_batch_stride;
         s.lddv = a->lddv; s.dv_bs = a->dv_batch_stride;
-        const int smem = 2 * f.Nq * f.Nkv * (int)sizeof(float);
-        static bool attr_set = false;
-        if (!attr_set) {
-            FD_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               2 * 128 * 128 * (int)sizeof(float)));
-            attr_set = true;
-        }
+        float* gP = a->dq_accum;
+        float* gDS = gP + (size_t)f.B * f.H * f.Nq * f.Nkv;
         ProfScope prof(stream, PROF_ATTN_BWD, 10.0 * (double)f.B * f.H * (double)f.Nq * (double)f.Nkv * d);
-        attn_bwd_small_kernel<<<dim3(f.H, f.B), 256, smem, stream>>>(s);
+        const long long pairs = (long long)f.Nq * f.Nkv;
+        attn_bwd_small_p_kernel<<<dim3((unsigned)((pairs + 255) / 256), f.H, f.B), 256, 0, stream>>>(s, gP, gDS);
+        FD_CHECK_LAUNCH();
+        attn_bwd_small_kv_kernel<<<dim3((f.Nkv * (d / 8) + 127) / 128, f.H, f.B), 128, 0, stream>>>(s, gP, gDS);
+        FD_CHECK_LAUNCH();
+        attn_bwd_small_q_kernel<<<dim3((f.Nq * (d / 8) + 127) / 128, f.H, f.B), 128, 0, stream>>>(s, gDS);
         FD_CHECK_LAUNCH();
         return 0;
     }

@@ -480,9 +480,9 @@ class _LinearFn(torch.autograd.Function):
 
 
 def _lora_weight_grads(pack, lp, x, t, dy, dt):
-    """dA_i = dt_i^T x ; dB_i = s * dy_i^T t_i   (fp32, in the parameters' layout)."""
-    if pack.head_pad is not None and pack.head_pad[1] != pack.head_pad[2]:
-        raise NotImplementedError("LoRA gradients with head-padded packs (head dim != multiple of 16)")
+    """dA_i = dt_i^T x ; dB_i = s * dy_i^T t_i   (fp32, in the parameters' layout).  With head-padded packs the zero
+    channels the kernels see are dropped again: rows of dB for q/k/v projections, columns of dA for the attention
+    out-projection."""
     r = lp["r"]
     x_t = raw.transpose(x)                      # [K, M]
     dy_t = raw.transpose(dy)                    # [N, M]
@@ -490,14 +490,27 @@ def _lora_weight_grads(pack, lp, x, t, dy, dt):
     dt_t = raw.transpose(dt)                    # [n*r, M]
     d_a = raw.gemm(dt_t, x_t, out_fp32=True)    # [n*r, K]
     d_b = raw.gemm(dy_t, t_t, out_fp32=True)    # [N, n*r]  (block-diagonal part is what we keep)
+    padded = pack.head_pad is not None and pack.head_pad[1] != pack.head_pad[2]
     grads = []
     row = 0
     for i, (l, b) in enumerate(zip(pack.loras, pack.bases)):
         nout = b.weight.shape[0]
+        rows_here = nout
+        if padded and not pack.pad_cols:
+            H, d, dp = pack.head_pad
+            rows_here = H * dp
         if l is not None:
-            grads.append(d_a[i * r:(i + 1) * r])
-            grads.append(d_b[row:row + nout, i * r:(i + 1) * r] * l.scaling)
-        row += nout
+            ga = d_a[i * r:(i + 1) * r]
+            gb = d_b[row:row + rows_here, i * r:(i + 1) * r]
+            if padded:
+                H, d, dp = pack.head_pad
+                if pack.pad_cols:
+                    ga = ga.reshape(r, H, dp)[:, :, :d].reshape(r, H * d)
+                else:
+                    gb = gb.reshape(H, dp, r)[:, :d].reshape(H * d, r)
+            grads.append(ga)
+            grads.append(gb * l.scaling)
+        row += rows_here
     return grads
 
 
@@ -636,64 +649,56 @@ def unpatchify(x, NB, h, w, p, Cout, Ckeep):
 # attention
 # ------------------------------------------------------------------------------------------------
 class _AttnSelfFn(torch.autograd.Function):
-    """Self-attention on the fused projection output qkv [B, N, 3*H*64] (q | k | v)."""
+    """Self-attention on the fused projection output qkv [B, N, 3*H*d] (q | k | v)."""
 
     @staticmethod
-    def forward(ctx, qkv, H):
-        inner = H * 64
+    def forward(ctx, qkv, H, head_dim, scale):
+        inner = H * head_dim
         q, k, v = qkv[..., :inner], qkv[..., inner:2 * inner], qkv[..., 2 * inner:]
-        o, lse = raw.attention_fwd(q, k, v, H, need_lse=True)
+        o, lse = raw.attention_fwd(q, k, v, H, scale=scale, need_lse=True, head_dim=head_dim)
         ctx.save_for_backward(qkv, o, lse)
-        ctx.H = H
+        ctx.meta = (H, head_dim, scale)
         return o
 
     @staticmethod
     def backward(ctx, do):
         qkv, o, lse = ctx.saved_tensors
-        H = ctx.H
-        inner = H * 64
+        H, head_dim, scale = ctx.meta
+        inner = H * head_dim
         q, k, v = qkv[..., :inner], qkv[..., inner:2 * inner], qkv[..., 2 * inner:]
         dqkv = torch.empty_like(qkv)
-        raw.attention_bwd(q, k, v, o, lse, do.contiguous(), H, dq=dqkv[..., :inner], dk=dqkv[..., inner:2 * inner],
-                          dv=dqkv[..., 2 * inner:])
-        return dqkv, None
+        raw.attention_bwd(q, k, v, o, lse, do.contiguous(), H, scale=scale, dq=dqkv[..., :inner],
+                          dk=dqkv[..., inner:2 * inner], dv=dqkv[..., 2 * inner:], head_dim=head_dim)
+        return dqkv, None, None, None
 
 
 class _AttnCrossFn(torch.autograd.Function):
-    """Cross-attention: q [B, Nq, H*64], fused kv [B, Nkv, 2*H*64] (k | v)."""
+    """Cross-attention: q [B, Nq, H*d], fused kv [B, Nkv, 2*H*d] (k | v), optional key-padding mask kv_len [B]."""
 
     @staticmethod
-    def forward(ctx, q, kv, H):
-        inner = H * 64
-        o, lse = raw.attention_fwd(q, kv[..., :inner], kv[..., inner:], H, need_lse=True)
+    def forward(ctx, q, kv, H, head_dim, scale, kv_len):
+        inner = H * head_dim
+        o, lse = raw.attention_fwd(q, kv[..., :inner], kv[..., inner:], H, scale=scale, need_lse=True,
+                                   head_dim=head_dim, kv_len=kv_len)
         ctx.save_for_backward(q, kv, o, lse)
-        ctx.H = H
+        ctx.meta = (H, head_dim, scale, kv_len)
         return o
 
     @staticmethod
     def backward(ctx, do):
         q, kv, o, lse = ctx.saved_tensors
-        H = ctx.H
-        inner = H * 64
+        H, head_dim, scale, kv_len = ctx.meta
+        inner = H * head_dim
         dkv = torch.empty_like(kv)
-        dq, _, _ = raw.attention_bwd(q, kv[..., :inner], kv[..., inner:], o, lse, do.contiguous(), H,
-                                     dk=dkv[..., :inner], dv=dkv[..., inner:])
-        return dq, dkv, None
-
-
-def _no_grad_generic(name, *ts):
-    if _grad_on(*ts):
-        raise NotImplementedError(f"{name}: the attention backward kernel is built for head dim 64 without masks; "
-                                  "other head dims / key-padding masks are forward-only this round")
+        dq, _, _ = raw.attention_bwd(q, kv[..., :inner], kv[..., inner:], o, lse, do.contiguous(), H, scale=scale,
+                                     dk=dkv[..., :inner], dv=dkv[..., inner:], head_dim=head_dim, kv_len=kv_len)
+        return dq, dkv, None, None, None, None
 
 
 def attention_self(qkv, H, head_dim=64, scale=None):
     """qkv [B, N, 3*H*d] -> [B, N, H*d]"""
-    if head_dim == 64:
-        if _grad_on(qkv):
-            return _AttnSelfFn.apply(qkv, H)
-    else:
-        _no_grad_generic("attention_self", qkv)
+    if _grad_on(qkv):
+        return _AttnSelfFn.apply(qkv, H, head_dim, scale)
     inner = H * head_dim
     return raw.attention_fwd(qkv[..., :inner], qkv[..., inner:2 * inner], qkv[..., 2 * inner:], H, scale=scale,
                              head_dim=head_dim)
@@ -701,11 +706,8 @@ def attention_self(qkv, H, head_dim=64, scale=None):
 
 def attention_cross(q, kv, H, head_dim=64, scale=None, kv_len=None):
     """q [B, Nq, H*d], kv [B, Nkv, 2*H*d] -> [B, Nq, H*d]; kv_len [B] int32 masks padded keys."""
-    if head_dim == 64 and kv_len is None:
-        if _grad_on(q, kv):
-            return _AttnCrossFn.apply(q, kv, H)
-    else:
-        _no_grad_generic("attention_cross", q, kv)
+    if _grad_on(q, kv):
+        return _AttnCrossFn.apply(q, kv, H, head_dim, scale, kv_len)
     inner = H * head_dim
     return raw.attention_fwd(q, kv[..., :inner], kv[..., inner:], H, scale=scale, head_dim=head_dim, kv_len=kv_len)
 

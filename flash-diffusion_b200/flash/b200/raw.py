@@ -250,18 +250,22 @@ def attention_fwd(q, k, v, H, scale=None, need_lse=False, head_dim=64, kv_len=No
     return (o, lse) if need_lse else o
 
 
-def attention_bwd(q, k, v, o, lse, do, H, scale=None, dq=None, dk=None, dv=None):
+def attention_bwd(q, k, v, o, lse, do, H, scale=None, dq=None, dk=None, dv=None, head_dim=64, kv_len=None):
     """Gradients of attention_fwd.  dq/dk/dv may be given as (strided) output views, e.g. slices of one fused
-    [B, N, 3*H*64] buffer; otherwise contiguous tensors are allocated."""
+    [B, N, 3*H*d] buffer; otherwise contiguous tensors are allocated.  d = 64 without a mask runs the tuned kernel
+    (fd_attn_bwd), everything else fd_attn_bwd_generic."""
     lib = load(); _req(do, BF16, "do")
     B, Nq, HD = q.shape
     Nkv = k.shape[1]
-    assert do.stride(2) == 1 and o.stride(2) == 1
+    assert HD == H * head_dim and do.stride(2) == 1 and o.stride(2) == 1
     dq = torch.empty((B, Nq, HD), device=q.device, dtype=BF16) if dq is None else dq
     dk = torch.empty((B, Nkv, HD), device=q.device, dtype=BF16) if dk is None else dk
     dv = torch.empty((B, Nkv, HD), device=q.device, dtype=BF16) if dv is None else dv
     delta = torch.empty((B, H, Nq), device=q.device, dtype=torch.float32)
-    dq_accum = torch.empty((B, Nq, HD), device=q.device, dtype=torch.float32)
+    if head_dim <= 80 or (head_dim == 64 and kv_len is None):
+        dq_accum = torch.empty((B, Nq, HD), device=q.device, dtype=torch.float32)
+    else:       # short-sequence kernel: scratch for P and dS
+        dq_accum = torch.empty((2 * B * H * Nq * Nkv,), device=q.device, dtype=torch.float32)
     a = _l.FdAttnBwdArgs()
     f = a.f
     f.q, f.ldq, f.q_batch_stride = ptr(q), q.stride(1), q.stride(0)
@@ -270,13 +274,18 @@ def attention_bwd(q, k, v, o, lse, do, H, scale=None, dq=None, dk=None, dv=None)
     f.o, f.ldo, f.o_batch_stride = ptr(o), o.stride(1), o.stride(0)
     f.lse = ptr(lse)
     f.B, f.H, f.Nq, f.Nkv = B, H, Nq, Nkv
-    f.scale = scale if scale is not None else 64 ** -0.5
+    f.scale = scale if scale is not None else head_dim ** -0.5
     a.d_o, a.lddo, a.do_batch_stride = ptr(do), do.stride(1), do.stride(0)
     a.dq, a.lddq, a.dq_batch_stride = ptr(dq), dq.stride(1), dq.stride(0)
     a.dk, a.lddk, a.dk_batch_stride = ptr(dk), dk.stride(1), dk.stride(0)
     a.dv, a.lddv, a.dv_batch_stride = ptr(dv), dv.stride(1), dv.stride(0)
     a.delta, a.dq_accum = ptr(delta), ptr(dq_accum)
-    check(lib.fd_attn_bwd(byref(a), stream_ptr()), "fd_attn_bwd")
+    if head_dim == 64 and kv_len is None:
+        check(lib.fd_attn_bwd(byref(a), stream_ptr()), "fd_attn_bwd")
+    else:
+        if kv_len is not None:
+            assert kv_len.dtype == torch.int32 and kv_len.numel() == B and kv_len.is_cuda
+        check(lib.fd_attn_bwd_generic(byref(a), c_int32(head_dim), ptr(kv_len), stream_ptr()), "fd_attn_bwd_generic")
     return dq, dk, dv
 
 

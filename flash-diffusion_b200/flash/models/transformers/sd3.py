@@ -25,7 +25,7 @@ from ...b200 import ops, raw
 from ...b200.ops import LinearPack, cache_of
 from ..lora import inject_lora
 from ..unets.unet import TimestepEmbedding, _Container
-from .transformers import FeedForward, sincos_2d
+from .transformers import FeedForward, patch_embed, sincos_2d
 
 
 class PatchEmbedSD3(_Container):
@@ -169,10 +169,7 @@ class DiffusersSD3Transformer2DWrapper(nn.Module):
                     "pos": raw.cast_scale(pe.cropped(hh, ww).to(dev).contiguous(), 1.0)}
         pk = cache_of(pe.proj).get(("patch", hh, ww), [pe.proj.weight, pe.proj.bias], build_patch)
         pos_b = self._pack(("pos_tiled", B, N), lambda: pk["pos"].repeat(B, 1).contiguous())
-        geom = (B, Cin, H, W, cpad)
-        if torch.is_grad_enabled() and sample.requires_grad:
-            return _PatchEmbedFn.apply(sample.float(), pk, pos_b, geom)
-        return _patch_embed_fwd(sample.float(), pk, pos_b, geom)
+        return patch_embed(sample.float(), pk, pos_b, (B, Cin, H, W, cpad))
 
     def forward(self, sample: torch.Tensor, timestep: Union[torch.Tensor, float, int],
                 conditioning: Dict[str, torch.Tensor], hidden_states_masks: Optional[torch.Tensor] = None,
@@ -269,33 +266,3 @@ class DiffusersSD3Transformer2DWrapper(nn.Module):
         nf = ops.modulate(h, mo[:, 0], mo[:, 1], N)
         out = ops.linear(nf, self._pack("proj_out", lambda: LinearPack(self.proj_out)), out_fp32=True)
         return ops.unpatchify(out, B, hh, ww, p, self.out_channels, c_keep)
-
-
-def _patch_embed_fwd(sample, pk, pos_b, geom):
-    """2x2/2 patch convolution + position table: space-to-depth, then a 4-tap implicit GEMM whose taps are the four
-    phase images; the table rides in the epilogue as the residual."""
-    B, Cin, H, W, cpad = geom
-    hh, ww = H // 2, W // 2
-    x = raw.space_to_depth(raw.nchw_to_nhwc(sample, cpad).view(B * H * W, cpad), B, H, W, cpad)
-    return raw.gemm(x, pk["w"], bias=pk["b"], residual=pos_b, M=B * hh * ww,
-                    conv=dict(NB_in=4 * B, H=hh, W=ww, C=cpad, taps=[(ph * B, 0, 0) for ph in range(4)]))
-
-
-class _PatchEmbedFn(torch.autograd.Function):
-    """Input gradient of the patch embedding (the GAN generator turn differentiates the frozen backbone with respect
-    to its input, reference flash_sd3/flash_diffusion_model.py:560-565): d(tokens) W gives the four phase images,
-    depth-to-space and NHWC->NCHW undo the forward re-layout."""
-
-    @staticmethod
-    def forward(ctx, sample, pk, pos_b, geom):
-        ctx.pk, ctx.geom = pk, geom
-        return _patch_embed_fwd(sample, pk, pos_b, geom)
-
-    @staticmethod
-    def backward(ctx, dh):
-        B, Cin, H, W, cpad = ctx.geom
-        hh, ww = H // 2, W // 2
-        d = raw.gemm(dh.contiguous(), ctx.pk["w_t"])                                  # [B*N, 4*64], column = tap*64 + c
-        phases = d.view(B * hh * ww, 4, 64)[:, :, :cpad].permute(1, 0, 2).contiguous().view(4 * B * hh * ww, cpad)
-        dx = raw.depth_to_space(phases, B, H, W, cpad)
-        return raw.nhwc_to_nchw(dx, B, Cin, H, W), None, None, None

@@ -2,9 +2,10 @@
 with the custom `AdaLayerNormSingle`, src/flash/models/transformers/utils.py:8-102; constructor kwargs as at
 examples/train_flash_pixart.py:65-86).
 
-Round-1 scope: FORWARD (teacher evaluation, LoRA student evaluation, `FlashDiffusion.sample`) on the hand-written
-kernels; the backward of this block type (AdaLN-modulate / gate kernels, attention backward for head dim 72 with a
-key-padding mask) is the next row, so a call that needs gradients raises.
+Forward and backward on the hand-written kernels: activation gradients (incl. the input gradient of the frozen GAN
+backbone) and LoRA gradients for every nn.Linear target of examples/train_flash_pixart.py:237-256 (attention with
+head-padded packs, feed-forward, caption projection, AdaLN-single and its embedders).  Not wrapped: the 2x2 patch
+convolution (peft would give it a LoRA too).
 
 Kernel mapping (UPSTREAM diffusers math, restated in oracle/dit.py):
   PatchEmbed conv 2x2/2    space-to-depth + 4-tap implicit-GEMM (fd_gemm conv mode) with the sin-cos position table added
@@ -12,8 +13,8 @@ Kernel mapping (UPSTREAM diffusers math, restated in oracle/dit.py):
   adaLN-single MLPs        small fd_gemm launches (M = batch)
   caption projection       fd_gemm with the gelu-tanh epilogue, then fd_gemm
   LN * (1+scale) + shift   fd_layernorm_modulate
-  attention (d = 72)       q/k/v packs zero-padded to 80 channels per head -> fd_attn_fwd_generic (T5 key-padding mask
-                           as per-sample valid lengths)
+  attention (d = 72)       q/k/v packs zero-padded to 80 channels per head -> fd_attn_fwd_generic / fd_attn_bwd_generic
+                           (T5 key-padding mask as per-sample valid lengths)
   gate * f(x) + x          fd_gemm epilogue: bias -> (gelu-tanh) -> per-sample gate vector -> residual
   un-patchify              fd_unpatchify (keeps the first `in_channels` channels, as the reference slices them)
 """
@@ -169,22 +170,18 @@ class DiffusersTransformer2DWrapper(nn.Module):
         return self
 
     @staticmethod
-    def _lin(x, pack: LinearPack, *, residual=None, act=0, rowscale=None, rows_per_group_scale=0, out_fp32=False):
-        """(LoRA-aware) GEMM with the DiT epilogue: bias -> act -> gate -> residual."""
-        p = pack.pack()
-        a2 = b2 = None
-        if pack.has_lora:
-            lp = pack.pack_lora()
-            a2, b2 = raw.gemm(x, lp["a"]), lp["b"]
-        return raw.gemm(x, p["w"], a2=a2, b2=b2, bias=p["b"], residual=residual, act=act, rowscale=rowscale,
-                        rows_per_group_scale=rows_per_group_scale, out_fp32=out_fp32)
+    def _silu_bf16(x):
+        """silu(fp32) -> bf16 on a [B, D] embedding; with a gradient it is three torch ops on B rows."""
+        if torch.is_grad_enabled() and x.requires_grad:
+            return torch.nn.functional.silu(x).to(torch.bfloat16)
+        return raw.silu_f32_to_bf16(x)
 
     def _mlp_rows(self, x_bf16, te: TimestepEmbedding, key):
         """TimestepEmbedding on [B, in] rows: linear_1 -> SiLU -> linear_2, fp32 out."""
         l1 = self._pack((key, 1), lambda: LinearPack(te.linear_1))
         l2 = self._pack((key, 2), lambda: LinearPack(te.linear_2))
-        h = raw.silu_f32_to_bf16(self._lin(x_bf16, l1, out_fp32=True))
-        return self._lin(h, l2, out_fp32=True)
+        h = self._silu_bf16(ops.linear(x_bf16, l1, out_fp32=True))
+        return ops.linear(h, l2, out_fp32=True)
 
     def _adaln(self, timestep, vector, B, dev):
         ad = self.adaln_single
@@ -202,24 +199,26 @@ class DiffusersTransformer2DWrapper(nn.Module):
                 emb = emb + torch.cat(parts, dim=1)
             else:
                 emb = emb + self._mlp_rows(v, ad.add_embedding, "ae")
-        t6 = self._lin(raw.silu_f32_to_bf16(emb), self._pack("adaln_linear", lambda: LinearPack(ad.linear)), out_fp32=True)
+        t6 = ops.linear(self._silu_bf16(emb), self._pack("adaln_linear", lambda: LinearPack(ad.linear)), out_fp32=True)
         return t6, emb
 
-    def _attention(self, a: Attention, x, ctx, B, kv_len, **epi):
+    def _attention(self, a: Attention, x, ctx, B, kv_len, residual, gate=None, rows=0):
         H, d = a.heads, a.dim_head
         dp = (d + 15) // 16 * 16
         hp = (H, d, dp) if dp != d else None
         inner = H * dp
         if not a.is_cross:
-            qkv = self._lin(x, self._pack(("qkv", id(a)), lambda: LinearPack([a.to_q, a.to_k, a.to_v], head_pad=hp)))
+            qkv = ops.linear(x, self._pack(("qkv", id(a)), lambda: LinearPack([a.to_q, a.to_k, a.to_v], head_pad=hp)))
             o = ops.attention_self(qkv.view(B, -1, 3 * inner), H, head_dim=dp, scale=d ** -0.5)
         else:
-            q = self._lin(x, self._pack(("q", id(a)), lambda: LinearPack(a.to_q, head_pad=hp)))
-            kv = self._lin(ctx, self._pack(("kv", id(a)), lambda: LinearPack([a.to_k, a.to_v], head_pad=hp)))
+            q = ops.linear(x, self._pack(("q", id(a)), lambda: LinearPack(a.to_q, head_pad=hp)))
+            kv = ops.linear(ctx, self._pack(("kv", id(a)), lambda: LinearPack([a.to_k, a.to_v], head_pad=hp)))
             o = ops.attention_cross(q.view(B, -1, inner), kv.view(B, -1, 2 * inner), H, head_dim=dp, scale=d ** -0.5,
                                     kv_len=kv_len)
-        return self._lin(o.view(-1, inner),
-                         self._pack(("o", id(a)), lambda: LinearPack(a.to_out[0], head_pad=hp, pad_cols=True)), **epi)
+        out_pack = self._pack(("o", id(a)), lambda: LinearPack(a.to_out[0], head_pad=hp, pad_cols=True))
+        if gate is not None:
+            return ops.gated_linear(o.view(-1, inner), out_pack, gate, residual, rows)
+        return ops.linear(o.view(-1, inner), out_pack, residual=residual)
 
     # ------------------------------------------------------------------------------------ forward
     def forward(self, sample: torch.Tensor, timestep: Union[torch.Tensor, float, int],
@@ -228,9 +227,6 @@ class DiffusersTransformer2DWrapper(nn.Module):
         assert isinstance(conditioning, dict), "conditionings must be a dictionary"
         if not sample.is_cuda:
             raise RuntimeError("DiffusersTransformer2DWrapper runs only on CUDA (B200) tensors: there is no CPU fallback")
-        if torch.is_grad_enabled() and (sample.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError("PixArt DiT backward (AdaLN / gate kernels, attention backward for d=72 + mask) is "
-                                      "the next row; call under torch.no_grad()")
         cond = conditioning["cond"]
         vector, crossattn, concat = cond.get("vector"), cond.get("crossattn"), cond.get("concat")
         mask = cond.get("attention_mask")
@@ -241,55 +237,88 @@ class DiffusersTransformer2DWrapper(nn.Module):
         dev, p, D = sample.device, self.patch_size, self.inner_dim
         hh, ww = H // p, W // p
         N = hh * ww
-        with torch.no_grad():
-            if not torch.is_tensor(timestep):
-                timestep = torch.tensor([float(timestep)], dtype=torch.float32, device=dev)
-            timestep = timestep.to(device=dev, dtype=torch.float32).reshape(-1)
-            if timestep.numel() == 1 and B > 1:
-                timestep = timestep.expand(B)
-            timestep = timestep.contiguous()
-            t6, emb = self._adaln(timestep, vector, B, dev)
-            # caption projection (gelu-tanh in the epilogue of linear_1)
-            cp = self.caption_projection
-            T = crossattn.shape[1]
-            c0 = raw.cast_scale(crossattn.detach().float().contiguous().view(B * T, -1), 1.0)
-            c1 = self._lin(c0, self._pack("cp1", lambda: LinearPack(cp.linear_1)), act=1)
-            ctx = self._lin(c1, self._pack("cp2", lambda: LinearPack(cp.linear_2)))
-            kv_len = None
-            if mask is not None:      # T5 padding mask (ones then zeros): per-sample number of valid keys
-                kv_len = mask.to(device=dev).reshape(B, T).sum(dim=1).to(torch.int32).contiguous()
-            # patch embedding: 2x2 stride-2 conv == 4-tap implicit GEMM over the space-to-depth image (+ position table)
-            cpad = (Cin + 7) // 8 * 8
-            x = raw.nchw_to_nhwc(sample.float(), cpad).view(B * H * W, cpad)
-            x = raw.space_to_depth(x, B, H, W, cpad)
-            pe = self.pos_embed
+        if not torch.is_tensor(timestep):
+            timestep = torch.tensor([float(timestep)], dtype=torch.float32, device=dev)
+        timestep = timestep.detach().to(device=dev, dtype=torch.float32).reshape(-1)
+        if timestep.numel() == 1 and B > 1:
+            timestep = timestep.expand(B)
+        timestep = timestep.contiguous()
+        t6, emb = self._adaln(timestep, vector, B, dev)
+        # caption projection (gelu-tanh in the epilogue of linear_1)
+        cp = self.caption_projection
+        T = crossattn.shape[1]
+        c0 = raw.cast_scale(crossattn.detach().float().contiguous().view(B * T, -1), 1.0)
+        c1 = ops.linear(c0, self._pack("cp1", lambda: LinearPack(cp.linear_1)), act=1)
+        ctx = ops.linear(c1, self._pack("cp2", lambda: LinearPack(cp.linear_2)))
+        kv_len = None
+        if mask is not None:      # T5 padding mask (ones then zeros): per-sample number of valid keys
+            kv_len = mask.to(device=dev).reshape(B, T).sum(dim=1).to(torch.int32).contiguous()
+        # patch embedding: 2x2 stride-2 conv == 4-tap implicit GEMM over the space-to-depth image (+ position table)
+        cpad = (Cin + 7) // 8 * 8
+        pe = self.pos_embed
 
-            def build_patch():
-                wt = pe.proj.weight.detach().float()                      # [D, Cin, 2, 2]
-                buf = torch.zeros((D, 4, 64), device=dev)
-                buf[:, :, :Cin] = wt.permute(0, 2, 3, 1).reshape(D, 4, Cin)
-                pos = pe.pos_embed[0, :N].to(dev)
-                return {"w": raw.cast_scale(buf.reshape(D, 256), 1.0), "b": pe.proj.bias.detach().float().contiguous(),
-                        "pos": raw.cast_scale(pos.contiguous(), 1.0)}
-            pk = cache_of(pe.proj).get(("patch", N), [pe.proj.weight, pe.proj.bias], build_patch)
-            pos_b = self._pack(("pos_tiled", B, N), lambda: pk["pos"].repeat(B, 1).contiguous())
-            taps = [(ph * B, 0, 0) for ph in range(4)]
-            h = raw.gemm(x, pk["w"], bias=pk["b"], residual=pos_b, M=B * N,
-                         conv=dict(NB_in=4 * B, H=hh, W=ww, C=cpad, taps=taps))
-            # AdaLN parameters of every block in one small op: [L, B, 6, D]
-            tables = self._pack("tables", lambda: torch.stack([b.scale_shift_table.detach().float()
-                                                               for b in self.transformer_blocks]))
-            mods = (tables[:, None] + t6.view(1, B, 6, D)).contiguous()
-            for li, blk in enumerate(self.transformer_blocks):
-                m = mods[li]                                              # [B, 6, D]: shift/scale/gate msa, mlp
-                n1 = raw.layernorm_modulate(h, m[:, 1], m[:, 0], N, self.norm_eps)
-                h = self._attention(blk.attn1, n1, None, B, None, residual=h, rowscale=m[:, 2], rows_per_group_scale=N)
-                h = self._attention(blk.attn2, h, ctx, B, kv_len, residual=h)
-                n2 = raw.layernorm_modulate(h, m[:, 4], m[:, 3], N, self.norm_eps)
-                f = self._lin(n2, self._pack(("ff1", id(blk)), lambda: LinearPack(blk.ff.net[0].proj)), act=1)
-                h = self._lin(f, self._pack(("ff2", id(blk)), lambda: LinearPack(blk.ff.net[2])), residual=h,
-                              rowscale=m[:, 5], rows_per_group_scale=N)
-            fin = (self.scale_shift_table.detach().float()[None] + emb[:, None]).contiguous()     # [B, 2, D]
-            nf = raw.layernorm_modulate(h, fin[:, 1], fin[:, 0], N, self.norm_eps)
-            out = self._lin(nf, self._pack("proj_out", lambda: LinearPack(self.proj_out)), out_fp32=True)
-            return raw.unpatchify(out, B, hh, ww, p, self.out_channels, c_keep)
+        def build_patch():
+            wt = pe.proj.weight.detach().float()                      # [D, Cin, 2, 2]
+            buf = torch.zeros((D, 4, 64), device=dev)
+            buf[:, :, :Cin] = wt.permute(0, 2, 3, 1).reshape(D, 4, Cin)
+            pos = pe.pos_embed[0, :N].to(dev)
+            return {"w": raw.cast_scale(buf.reshape(D, 256), 1.0),
+                    "w_t": raw.cast_scale(buf.reshape(D, 256).t().contiguous(), 1.0),
+                    "b": pe.proj.bias.detach().float().contiguous(), "pos": raw.cast_scale(pos.contiguous(), 1.0)}
+        pk = cache_of(pe.proj).get(("patch", N), [pe.proj.weight, pe.proj.bias], build_patch)
+        pos_b = self._pack(("pos_tiled", B, N), lambda: pk["pos"].repeat(B, 1).contiguous())
+        h = patch_embed(sample.float(), pk, pos_b, (B, Cin, H, W, cpad))
+        # AdaLN parameters of every block in one small op: [L, B, 6, D]
+        tables = self._pack("tables", lambda: torch.stack([b.scale_shift_table.detach().float()
+                                                           for b in self.transformer_blocks]))
+        mods = (tables[:, None] + t6.view(1, B, 6, D)).contiguous()
+        eps = self.norm_eps
+        for li, blk in enumerate(self.transformer_blocks):
+            m = mods[li]                                              # [B, 6, D]: shift/scale/gate msa, mlp
+            n1 = ops.modulate(h, m[:, 1], m[:, 0], N, eps)
+            h = self._attention(blk.attn1, n1, None, B, None, residual=h, gate=m[:, 2], rows=N)
+            h = self._attention(blk.attn2, h, ctx, B, kv_len, residual=h)
+            n2 = ops.modulate(h, m[:, 4], m[:, 3], N, eps)
+            f = ops.linear(n2, self._pack(("ff1", id(blk)), lambda: LinearPack(blk.ff.net[0].proj)), act=1)
+            h = ops.gated_linear(f, self._pack(("ff2", id(blk)), lambda: LinearPack(blk.ff.net[2])), m[:, 5], h, N)
+        fin = (self.scale_shift_table.detach().float()[None] + emb[:, None]).contiguous()     # [B, 2, D]
+        nf = ops.modulate(h, fin[:, 1], fin[:, 0], N, eps)
+        out = ops.linear(nf, self._pack("proj_out", lambda: LinearPack(self.proj_out)), out_fp32=True)
+        return ops.unpatchify(out, B, hh, ww, p, self.out_channels, c_keep)
+
+
+def _patch_embed_fwd(sample, pk, pos_b, geom):
+    """2x2/2 patch convolution + position table: space-to-depth, then a 4-tap implicit GEMM whose taps are the four
+    phase images; the table rides in the epilogue as the residual."""
+    B, Cin, H, W, cpad = geom
+    hh, ww = H // 2, W // 2
+    x = raw.space_to_depth(raw.nchw_to_nhwc(sample, cpad).view(B * H * W, cpad), B, H, W, cpad)
+    return raw.gemm(x, pk["w"], bias=pk["b"], residual=pos_b, M=B * hh * ww,
+                    conv=dict(NB_in=4 * B, H=hh, W=ww, C=cpad, taps=[(ph * B, 0, 0) for ph in range(4)]))
+
+
+class _PatchEmbedFn(torch.autograd.Function):
+    """Input gradient of the patch embedding (the GAN generator turn differentiates the frozen backbone with respect
+    to its input, reference flash_diffusion_model.py:563-592): d(tokens) W gives the four phase images; depth-to-space
+    and NHWC->NCHW undo the forward re-layout."""
+
+    @staticmethod
+    def forward(ctx, sample, pk, pos_b, geom):
+        ctx.pk, ctx.geom = pk, geom
+        return _patch_embed_fwd(sample, pk, pos_b, geom)
+
+    @staticmethod
+    def backward(ctx, dh):
+        B, Cin, H, W, cpad = ctx.geom
+        hh, ww = H // 2, W // 2
+        d = raw.gemm(dh.contiguous(), ctx.pk["w_t"])                                  # [B*N, 4*64], column = tap*64 + c
+        phases = d.view(B * hh * ww, 4, 64)[:, :, :cpad].permute(1, 0, 2).contiguous().view(4 * B * hh * ww, cpad)
+        dx = raw.depth_to_space(phases, B, H, W, cpad)
+        return raw.nhwc_to_nchw(dx, B, Cin, H, W), None, None, None
+
+
+def patch_embed(sample, pk, pos_b, geom):
+    """sample NCHW fp32 -> tokens [B*N, D] bf16; pk = {"w" [D,256], "w_t", "b", "pos"} (see the wrappers)."""
+    if torch.is_grad_enabled() and sample.requires_grad:
+        return _PatchEmbedFn.apply(sample, pk, pos_b, geom)
+    return _patch_embed_fwd(sample, pk, pos_b, geom)

@@ -158,7 +158,7 @@ typedef struct {
 int fd_attn_fwd(const FdAttnArgs* args, void* stream);
 /* Same contract for head dims other than 64 (multiple of 16, <= 192; q/k/v/o rows are H*head_dim wide) and an optional
  * key-padding mask kv_len[B] (keys >= kv_len[b] are ignored) — SD1.5 (d=40/80/160 zero-padded to 48/80/160 by the
- * weight packs) and PixArt-alpha (d=72 -> 80, masked T5 context).  Forward only. */
+ * weight packs) and PixArt-alpha (d=72 -> 80, masked T5 context).  Backward: fd_attn_bwd_generic. */
 int fd_attn_fwd_generic(const FdAttnArgs* args, int32_t head_dim, const int32_t* kv_len, void* stream);
 
 typedef struct {
@@ -171,6 +171,12 @@ typedef struct {
     float* dq_accum;              /* scratch [B, Nq, H*64] fp32, zero-initialised by the call */
 } FdAttnBwdArgs;
 int fd_attn_bwd(const FdAttnBwdArgs* args, void* stream);
+/* Backward for the shapes fd_attn_fwd_generic serves (same FdAttnBwdArgs; q/k/v/o/d_o/dq/dk/dv rows are H*head_dim wide,
+ * dq_accum [B, Nq, H*head_dim] fp32): head_dim a multiple of 16 up to 80 runs on tcgen05 for any sequence length;
+ * larger head dims (SD1.5's d = 160 at 16x16 / 8x8 tokens) run three CUDA-core passes for short sequences
+ * (Nq*Nkv <= 2^20), for which dq_accum is a scratch of 2*B*H*Nq*Nkv floats.  kv_len as in the forward.  Student LoRA backward of the SD1.5 UNet and the PixArt-alpha DiT (reference unets/unet.py:108-119,
+ * transformers/tranformers.py:58-92). */
+int fd_attn_bwd_generic(const FdAttnBwdArgs* args, int32_t head_dim, const int32_t* kv_len, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Layout / small elementwise helpers.

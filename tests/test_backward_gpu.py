@@ -34,6 +34,74 @@ def test_attention_bwd(B, H, Nq, Nkv):
     assert _rel(dv, vf.grad) < 2e-2, _rel(dv, vf.grad)
 
 
+def _sdpa_ref(q, k, v, do, H, d, scale, kv_len):
+    B, Nq, Nkv = q.shape[0], q.shape[1], k.shape[1]
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    mask = None
+    if kv_len is not None:
+        mask = (torch.arange(Nkv, device="cuda")[None, :] < kv_len[:, None].long())[:, None, None, :]
+    ref = F.scaled_dot_product_attention(qf.view(B, Nq, H, d).transpose(1, 2), kf.view(B, Nkv, H, d).transpose(1, 2),
+                                         vf.view(B, Nkv, H, d).transpose(1, 2), attn_mask=mask, scale=scale)
+    ref = ref.transpose(1, 2).reshape(B, Nq, H * d)
+    ref.backward(do.float())
+    return ref, qf.grad, kf.grad, vf.grad
+
+
+@pytest.mark.parametrize("B,H,d,Nq,Nkv,masked", [
+    (2, 2, 48, 256, 256, False),      # SD1.5 level 1 (40 -> 48), one sub-tile
+    (2, 3, 80, 200, 333, False),      # SD1.5 level 2 / PixArt (72 -> 80): 64 + 16 columns
+    (2, 2, 80, 1024, 1024, False),
+    (2, 4, 80, 256, 120, True),       # PixArt cross-attention with a T5 padding mask
+    (2, 2, 64, 256, 120, True),       # d = 64 with a mask
+    (2, 2, 16, 128, 77, False),
+    (2, 8, 160, 256, 256, False),     # SD1.5 level 3 self-attention (16x16 tokens): CUDA-core passes
+    (2, 8, 160, 64, 77, True),        # SD1.5 mid block cross-attention
+])
+def test_attention_bwd_generic(B, H, d, Nq, Nkv, masked):
+    from flash.b200 import raw
+    torch.manual_seed(B + H + d + Nq + Nkv)
+    q = torch.randn(B, Nq, H * d, device="cuda").bfloat16()
+    k = torch.randn(B, Nkv, H * d, device="cuda").bfloat16()
+    v = torch.randn(B, Nkv, H * d, device="cuda").bfloat16()
+    do = torch.randn(B, Nq, H * d, device="cuda").bfloat16()
+    kv_len = torch.tensor([Nkv - 43, Nkv][:B], device="cuda", dtype=torch.int32) if masked else None
+    scale = 0.9 * d ** -0.5
+    o, lse = raw.attention_fwd(q, k, v, H, scale=scale, need_lse=True, head_dim=d, kv_len=kv_len)
+    dq, dk, dv = raw.attention_bwd(q, k, v, o, lse, do, H, scale=scale, head_dim=d, kv_len=kv_len)
+    ref, gq, gk, gv = _sdpa_ref(q, k, v, do, H, d, scale, kv_len)
+    assert _rel(o, ref) < 2e-2
+    assert _rel(dq, gq) < 2e-2, _rel(dq, gq)
+    assert _rel(dk, gk) < 2e-2, _rel(dk, gk)
+    assert _rel(dv, gv) < 2e-2, _rel(dv, gv)
+    if masked:      # padded keys get exactly zero gradient
+        assert float(dk[0, Nkv - 43:].abs().max()) == 0 and float(dv[0, Nkv - 43:].abs().max()) == 0
+
+
+def test_attention_generic_fused_autograd_views():
+    """Strided q|k|v views of one fused projection buffer, as the UNet / DiT engines pass them."""
+    from flash.b200 import ops
+    torch.manual_seed(0)
+    B, N, H, d = 2, 200, 3, 80
+    qkv = torch.randn(B, N, 3 * H * d, device="cuda").bfloat16().requires_grad_(True)
+    o = ops.attention_self(qkv, H, head_dim=d, scale=72 ** -0.5)
+    g = torch.randn_like(o)
+    o.backward(g)
+    qf = qkv.detach().float().requires_grad_(True)
+    q, k, v = qf.view(B, N, 3, H, d).permute(2, 0, 3, 1, 4)
+    F.scaled_dot_product_attention(q, k, v, scale=72 ** -0.5).transpose(1, 2).reshape(B, N, H * d).backward(g.float())
+    assert _rel(qkv.grad, qf.grad) < 2e-2
+    q2 = torch.randn(B, N, H * d, device="cuda").bfloat16().requires_grad_(True)
+    kv = torch.randn(B, 120, 2 * H * d, device="cuda").bfloat16().requires_grad_(True)
+    kv_len = torch.tensor([77, 120], device="cuda", dtype=torch.int32)
+    ops.attention_cross(q2, kv, H, head_dim=d, kv_len=kv_len).backward(g)
+    qf2, kvf = q2.detach().float().requires_grad_(True), kv.detach().float().requires_grad_(True)
+    k2, v2 = kvf.view(B, 120, 2, H, d).permute(2, 0, 3, 1, 4)
+    mask = (torch.arange(120, device="cuda")[None, :] < kv_len[:, None].long())[:, None, None, :]
+    F.scaled_dot_product_attention(qf2.view(B, N, H, d).transpose(1, 2), k2, v2, attn_mask=mask) \
+        .transpose(1, 2).reshape(B, N, H * d).backward(g.float())
+    assert _rel(q2.grad, qf2.grad) < 2e-2 and _rel(kv.grad, kvf.grad) < 2e-2
+
+
 def test_attention_fused_autograd():
     from flash.b200 import ops
     torch.manual_seed(0)
@@ -137,3 +205,23 @@ def test_small_unet_backward_vs_oracle():
     xo2 = x.clone().requires_grad_(True)
     (ora(xo2, t, cond, return_intermediate=True) * gm).sum().backward()
     assert _cos(xp2.grad, xo2.grad) > 0.999
+
+
+def test_sd15_like_unet_backward_vs_oracle():
+    """Config-1 backbone shape (8 heads at every level -> head dims that are not 64, zero-padded packs) with the
+    reference's LoRA targets: LoRA gradients and input gradient against fp32 oracle autograd."""
+    from oracle.unet import SD15_KWARGS
+    from test_unet_gpu import _inputs, _pair
+    small15 = dict(SD15_KWARGS, block_out_channels=[320, 640, 1280, 1280], layers_per_block=1, cross_attention_dim=96)
+    prod, ora = _pair(small15, lora=True, seed=3)       # head dims 40 (-> 48), 80, 160
+    x, t, cond = _inputs(2, 32, 32, 96, 0)
+    g = torch.randn(2, 4, 32, 32, device="cuda")
+    xp, xo = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    out, ref = prod(xp, t, cond), ora(xo, t, cond)
+    assert _rel(out, ref) < 2e-2
+    (out * g).sum().backward()
+    (ref * g).sum().backward()
+    assert _cos(xp.grad, xo.grad) > 0.999, _cos(xp.grad, xo.grad)
+    po = dict(ora.named_parameters())
+    worst = min(_cos(p.grad, po[n].grad) for n, p in prod.named_parameters() if "lora_" in n)
+    assert worst > 0.995, worst

@@ -1,4 +1,5 @@
-"""GPU parity of the PixArt-alpha DiT path (DiffusersTransformer2DWrapper, forward) against the fp32 oracle DiT."""
+"""GPU parity of the DiT paths (PixArt-alpha `DiffusersTransformer2DWrapper`, SD3 `DiffusersSD3Transformer2DWrapper`, forward and
+backward, and `FlashDiffusionSD3` around them) against the fp32 oracle transformers."""
 import pytest
 import torch
 import torch.nn.functional as F
@@ -83,8 +84,6 @@ def test_small_pixart_forward(masked):
         out = prod(x, t, cond)
     assert out.shape == ref.shape == (2, 4, 32, 32)
     assert _rel(out, ref) < 2e-2, _rel(out, ref)
-    with pytest.raises(NotImplementedError):
-        prod(x.requires_grad_(True), t, cond)
 
 
 def test_small_pixart_lora_student_forward():
@@ -338,7 +337,7 @@ def test_sd3_objective_training_step_on_gpu():
     prod, ora = _sd3_objective_pair(8)
     torch.manual_seed(4)       # the recipe's discriminator is sized for 128x128 latents; 16x16 here
     disc = torch.nn.Sequential(torch.nn.Conv2d(16, 8, 4, 2, 1, bias=False), torch.nn.SiLU(True),
-                               torch.nn.Conv2d(8, 1, 4, 1, 0, bias=False), torch.nn.Flatten()).cuda()
+                               torch.nn.Conv2d(8, 1, 8, 1, 0, bias=False), torch.nn.Flatten()).cuda()
     prod.discriminator = disc
     ora._modules["discriminator"] = disc
     batch = sd3_batch(2, 3, "cuda", kwargs=SD3_SMALL, tokens=9, hw=16)
@@ -351,12 +350,63 @@ def test_sd3_objective_training_step_on_gpu():
         b = ora(batch, step=step, draws=draws)
         assert _rel(a["student_output"], b["student_output"]) < 3e-2
         assert _rel(a["teacher_output"], b["teacher_output"]) < 3e-2
-        assert abs(float(a["loss"][0]) - float(b["loss"][0])) < 5e-2 * abs(float(b["loss"][0]))
+        la, lb = float(a["loss"][0].detach()), float(b["loss"][0].detach())
+        assert abs(la - lb) < 5e-2 * abs(lb), (la, lb)
         if step == 1:
-            assert abs(float(a["loss"][1]) - float(b["loss"][1])) < 5e-2 * abs(float(b["loss"][1]))
+            da, db = float(a["loss"][1].detach()), float(b["loss"][1].detach())
+            assert abs(da - db) < 5e-2 * abs(db), (da, db)
     out = prod(batch, step=0, draws=draws)
     out["loss"][0].backward()
     grads = [p.grad for n, p in prod.student_denoiser.named_parameters() if p.requires_grad]
     assert all(g_ is not None and torch.isfinite(g_).all() for g_ in grads)
     assert sum(float(g_.norm()) for g_ in grads) > 0
     assert all(p.grad is None for p in prod.teacher_denoiser.parameters())
+
+
+def test_small_pixart_lora_backward_matches_oracle():
+    """Student LoRA backward through the PixArt DiT (head dim 24 -> 32 padded packs here, 72 -> 80 at full size; masked
+    T5 context; LoRA targets of examples/train_flash_pixart.py:237-256) against fp32 autograd."""
+    from flash.models.lora import LoraConfig
+    from oracle.unet import LoraConfig as OLoraConfig
+    from oracle.unet import UNet2DConditionOracle
+    prod, ora = _pair(SMALL, seed=5)
+    targets = ["to_k", "to_q", "to_v", "to_out.0", "net.2", "linear", "linear_1", "linear_2"]
+    cfg = dict(r=8, lora_alpha=8, target_modules=targets)
+    ora = ora.cpu()
+    UNet2DConditionOracle.add_adapter(ora, OLoraConfig(**cfg))
+    prod.add_adapter(LoraConfig(**cfg))
+    with torch.no_grad():
+        for n, p in ora.named_parameters():
+            if "lora_B" in n:
+                p.normal_(0, 0.05)
+    ora = ora.cuda()
+    prod.load_state_dict(ora.state_dict())
+    prod.train(); ora.train()
+    x, t, cond = _inputs(2, 32, 20, 64, 24, masked=True)
+    w = torch.randn(2, 4, 32, 32, device="cuda")
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya, yb = prod(xa, t, cond), ora(xb, t, cond)
+    assert _rel(ya, yb) < 2e-2, _rel(ya, yb)
+    (ya * w).sum().backward()
+    (yb * w).sum().backward()
+    assert _rel(xa.grad, xb.grad) < 3e-2, _rel(xa.grad, xb.grad)
+    ga = {n: p.grad for n, p in prod.named_parameters() if p.requires_grad}
+    gb = {n: p.grad for n, p in ora.named_parameters() if p.requires_grad}
+    assert set(ga) == set(gb) and len(ga) > 20 and all(g is not None for g in ga.values())
+    big = max(v.norm() for v in gb.values())
+    worst = max((_rel(ga[n], gb[n]), n) for n in ga if gb[n].norm() > 1e-6 * big)
+    assert worst[0] < 6e-2, worst
+    tot_a = torch.cat([ga[n].flatten() for n in sorted(ga)])
+    tot_b = torch.cat([gb[n].flatten() for n in sorted(ga)])
+    assert _rel(tot_a, tot_b) < 3e-2, _rel(tot_a, tot_b)
+
+
+def test_small_pixart_frozen_backbone_input_gradient():
+    prod, ora = _pair(SMALL, seed=6)
+    prod.freeze(); ora.freeze()
+    x, t, cond = _inputs(2, 32, 20, 64, 24, masked=True)
+    w = torch.randn(2, 4, 32, 32, device="cuda")
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    (prod(xa, t, cond) * w).sum().backward()
+    (ora(xb, t, cond) * w).sum().backward()
+    assert _rel(xa.grad, xb.grad) < 3e-2, _rel(xa.grad, xb.grad)

@@ -100,8 +100,6 @@ def test_sd15_unet_forward_head_dims_40_80_160():
         out = prod(x, t, cond)
         ref = ora(x, t, cond)
     assert _rel(out, ref) < 2e-2, _rel(out, ref)
-    with pytest.raises(NotImplementedError):
-        prod(x.requires_grad_(True), t, cond)
 
 
 def test_cuda_graph_replay_matches_eager():
