@@ -163,15 +163,15 @@ def build_sdxl_distillation(device, **kw):
 
 
 def sd15_discriminator(color_dim=1280, d=64):
-    """examples/train_flash_sd.py:225-240"""
-    return nn.Sequential(nn.Conv2d(color_dim, d, 4, 2, 1, bias=False), nn.SiLU(True),
-                         nn.Conv2d(d, d * 2, 4, 2, 1, bias=False), nn.GroupNorm(4, d * 2), nn.SiLU(True),
+    """examples/train_flash_sd.py:221-240 (mid-block features 1280 x 8 x 8 -> 1 logit)."""
+    return nn.Sequential(nn.Conv2d(color_dim, d, 3, 1, 1), nn.SiLU(True),
+                         nn.Conv2d(d, d * 2, 4, 2, 1, bias=False), nn.SiLU(True), nn.GroupNorm(4, d * 2),
                          nn.Conv2d(d * 2, 1, 4, 1, 0, bias=False), nn.Flatten())
 
 
 def build_sd15_distillation(device, **kw):
-    """Config 1 objects (SD1.5, LoRA r=128).  Forward / sampling only on GPU this round: the attention backward is
-    built for head dim 64 (SD1.5 has 40/80/160)."""
+    """Config 1 objects (examples/train_flash_sd.py + configs/flash_sd.yaml: SD1.5 UNet, LoRA r=128 on q/k/v/out,
+    K=32).  Head dims 40 / 80 / 160 run through zero-padded packs and the generic attention kernels."""
     kw.setdefault("lora_rank", 128)
     return build_distillation(SD15_UNET_KWARGS, sd15_discriminator(), device, conditioner=text_only_conditioner(),
                               ucg_keys=("text_emb",), **kw)
@@ -185,40 +185,84 @@ PIXART_KWARGS = dict(   # examples/train_flash_pixart.py:65-86
     timesteps_embedding_num_channels=256, use_concat_vector_conditioning=True, num_vector_conditionings=3)
 
 
-def build_pixart_sampler(device, lora_rank=64, seed=1234):
-    """PixArt-alpha student (LoRA on the Linear targets of examples/train_flash_pixart.py:237-256) inside a
-    FlashDiffusion for the few-step sampler (config 5).  Training for this backbone is the next row."""
+# examples/train_flash_pixart.py:239-252 and examples/train_flash_sd3.py:104-117 (the same list)
+DIT_LORA_TARGETS = ["to_q", "to_k", "to_v", "to_out.0", "proj_in", "proj_out", "ff.net.0.proj", "ff.net.2", "proj",
+                    "linear", "linear_1", "linear_2"]
+
+
+def pixart_discriminator(color_dim=4, d=64):
+    """examples/train_flash_pixart.py:277-325 (on the 4-channel backbone output: the DiT wrapper has no mid-block
+    features to return)."""
+    return nn.Sequential(nn.Conv2d(color_dim, d, 4, 2, 1, bias=False), nn.SiLU(True),
+                         nn.Conv2d(d, d * 2, 4, 2, 1, bias=False), nn.GroupNorm(4, d * 2), nn.SiLU(True),
+                         nn.Conv2d(d * 2, d * 4, 4, 2, 1, bias=False), nn.GroupNorm(4, d * 4), nn.SiLU(True),
+                         nn.Conv2d(d * 4, d * 8, 4, 2, 1, bias=False), nn.GroupNorm(4, d * 8), nn.SiLU(True),
+                         nn.Conv2d(d * 8, d * 16, 4, 2, 1, bias=False), nn.GroupNorm(4, d * 16), nn.SiLU(True),
+                         nn.Conv2d(d * 16, 1, 4, 1, 0, bias=False), nn.Flatten())
+
+
+def build_pixart_distillation(device, lora_rank=64, seed=1234, K=16, lr=1e-5, kwargs=None, discriminator=None,
+                              lora_b_std=0.0):
+    """Config 3 objects (examples/train_flash_pixart.py + configs/flash_pixart.yaml): PixArt-alpha XL/2 teacher, LoRA
+    r=64 student (peft default lora_alpha 8) on the script's Linear targets, DPM-Solver++ trailing K=16 teacher, LCM
+    sampler, DMD + lsgan through the frozen backbone.  Returns (model, pipe)."""
     from .models.embedders import PrecomputedTextEmbedder, PrecomputedTextEmbedderConfig
     from .models.transformers import DiffusersTransformer2DWrapper
+    from .models.transformers.transformers import sincos_2d
+    kwargs = kwargs or PIXART_KWARGS
     with torch.device("meta"):
-        teacher = DiffusersTransformer2DWrapper(**PIXART_KWARGS)
+        teacher = DiffusersTransformer2DWrapper(**kwargs)
     teacher = teacher.to_empty(device=device)
     init_random_(teacher, seed)
-    from .models.transformers.transformers import sincos_2d
-    teacher.pos_embed.pos_embed = torch.from_numpy(sincos_2d(1152, 64, 64, 2)).float()[None].to(device)
+    grid = kwargs["sample_size"] // kwargs["patch_size"]
+    D = kwargs["num_attention_heads"] * kwargs["attention_head_dim"]
+    teacher.pos_embed.pos_embed = torch.from_numpy(
+        sincos_2d(D, grid, grid, max(kwargs["sample_size"] // 64, 1))).float()[None].to(device)
     student = copy.deepcopy(teacher)
-    student.add_adapter(LoraConfig(r=lora_rank, lora_alpha=8, target_modules=[
-        "to_k", "to_q", "to_v", "to_out.0", "net.2", "linear", "linear_1", "linear_2"]))
+    student.add_adapter(LoraConfig(r=lora_rank, lora_alpha=8, target_modules=DIT_LORA_TARGETS))
+    _perturb_lora_b(student, lora_b_std, seed + 1)
     teacher.freeze()
+    fc = kwargs["projection_class_embeddings_input_dim"]
     conditioner = ConditionerWrapper([
         PrecomputedTextEmbedder(PrecomputedTextEmbedderConfig(input_key="text_emb", mask_key="text_mask")),
-        TimestepsEmbedder(TimestepsEmbedderConfig(input_key="resolution", num_channels=256)),
-        TimestepsEmbedder(TimestepsEmbedderConfig(input_key="aspect_ratio", num_channels=256))])
-    cfg = FlashDiffusionConfig(K=[32], num_iterations_per_K=[10 ** 9], distill_loss_type="l2", ucg_keys=["text_emb"],
-                               use_dmd_loss=False, gan_loss_type="lsgan", input_key="image")
-    sched = DPMSolverMultistepScheduler.from_pretrained("PixArt-alpha/PixArt-XL-2-1024-MS", subfolder="scheduler",
-                                                        timestep_spacing="trailing")
-    lcm = LCMScheduler.from_pretrained("PixArt-alpha/PixArt-XL-2-1024-MS", subfolder="scheduler",
-                                       timestep_spacing="trailing")
-    disc = nn.Sequential(nn.Conv2d(4, 8, 4, 2, 1, bias=False), nn.Flatten())
+        TimestepsEmbedder(TimestepsEmbedderConfig(input_key="resolution", num_channels=fc)),
+        TimestepsEmbedder(TimestepsEmbedderConfig(input_key="aspect_ratio", num_channels=fc))])
+    cfg = FlashDiffusionConfig(K=[K], num_iterations_per_K=[10 ** 9], guidance_scale_min=2.0, guidance_scale_max=9.0,
+                               distill_loss_type="l2", ucg_keys=["text_emb"], use_dmd_loss=True, gan_loss_type="lsgan",
+                               timestep_distribution="mixture", mixture_num_components=4, mixture_var=0.5,
+                               input_key="image")
+    name = "PixArt-alpha/PixArt-XL-2-1024-MS"
+    sched = DPMSolverMultistepScheduler.from_pretrained(name, subfolder="scheduler", timestep_spacing="trailing")
+    lcm = LCMScheduler.from_pretrained(name, subfolder="scheduler", timestep_spacing="trailing")
+    disc = discriminator if discriminator is not None else pixart_discriminator(kwargs["in_channels"])
     model = FlashDiffusion(cfg, student_denoiser=student, teacher_denoiser=teacher, teacher_noise_scheduler=sched,
                            sampling_noise_scheduler=lcm, vae=None, conditioner=conditioner, discriminator=disc).to(device)
-    return model
+    pipe = TrainingPipeline(model, TrainingConfig(
+        optimizers_name=["AdamW", "AdamW"], learning_rates=[lr, lr],
+        trainable_params=[["student_denoiser"], ["discriminator."]]))
+    pipe.configure_optimizers()
+    return model, pipe
 
 
-def pixart_batch(B, seed, device, tokens=120, valid=77):
+def build_pixart_sampler(device, lora_rank=64, seed=1234):
+    """PixArt-alpha LoRA student inside a FlashDiffusion for the few-step sampler (config 5)."""
+    return build_pixart_distillation(device, lora_rank=lora_rank, seed=seed)[0]
+
+
+def _perturb_lora_b(module, std, seed):
+    """peft initialises lora_B to zero (student == teacher); a small non-zero B makes parity / timing runs exercise the
+    adapter products."""
+    if std > 0:
+        g = torch.Generator(device=next(module.parameters()).device).manual_seed(seed)
+        with torch.no_grad():
+            for n, p in module.named_parameters():
+                if "lora_B" in n:
+                    p.normal_(0.0, std, generator=g)
+
+
+def pixart_batch(B, seed, device, tokens=120, valid=77, hw=128, ctx_dim=4096):
     g = torch.Generator().manual_seed(seed)
-    batch = {"image": torch.randn(B, 4, 128, 128, generator=g), "text_emb": torch.randn(B, tokens, 4096, generator=g),
+    batch = {"image": torch.randn(B, 4, hw, hw, generator=g), "text_emb": torch.randn(B, tokens, ctx_dim, generator=g),
              "text_mask": (torch.arange(tokens)[None] < valid).long().repeat(B, 1),
              "resolution": torch.tensor([[1024., 1024.]] * B), "aspect_ratio": torch.tensor([[1.0]] * B)}
     return {k: v.to(device) for k, v in batch.items()}
@@ -236,9 +280,7 @@ SD3_KWARGS = dict(   # examples/train_flash_sd3.py:65-77
     joint_attention_dim=4096, caption_projection_dim=1536, pooled_projection_dim=2048, out_channels=16,
     pos_embed_max_size=192)
 
-# examples/train_flash_sd3.py:104-117
-SD3_LORA_TARGETS = ["to_q", "to_k", "to_v", "to_out.0", "proj_in", "proj_out", "ff.net.0.proj", "ff.net.2", "proj",
-                    "linear", "linear_1", "linear_2"]
+SD3_LORA_TARGETS = DIT_LORA_TARGETS          # examples/train_flash_sd3.py:104-117
 
 
 def sd3_discriminator(color_dim=16, d=64):
@@ -250,10 +292,10 @@ def sd3_discriminator(color_dim=16, d=64):
                          nn.Conv2d(d * 8, 1, 4, 1, 0, bias=False), nn.Flatten())
 
 
-def build_sd3(device, kwargs=None, lora_rank=64, seed=1234, K=32):
-    """Config 4 objects (SD3-medium MMDiT, LoRA r=64 on the reference's targets, flow-matching schedulers) inside a
-    `FlashDiffusionSD3`.  On CUDA the MMDiT is forward-only: teacher rollout, DMD/GAN teacher evaluations and the
-    few-step sampler run; the student backward is the next row."""
+def build_sd3(device, kwargs=None, lora_rank=64, seed=1234, K=32, discriminator=None, lora_b_std=0.0):
+    """Config 4 objects (examples/train_flash_sd3.py + configs/flash_sd3.yaml): SD3-medium MMDiT teacher, LoRA student
+    (lora_alpha = peft default 8) on the script's Linear targets, flow-matching schedulers, DMD + lsgan, inside a
+    `FlashDiffusionSD3`."""
     from .models.flash_sd3 import FlashDiffusionSD3, FlashDiffusionSD3Config
     from .models.transformers import DiffusersSD3Transformer2DWrapper
     from .schedulers import FlashFlowMatchEulerDiscreteScheduler, FlowMatchEulerDiscreteScheduler
@@ -268,7 +310,8 @@ def build_sd3(device, kwargs=None, lora_rank=64, seed=1234, K=32):
     pe.pos_embed = fresh.pos_embed.to(device)
     student = copy.deepcopy(teacher)
     if lora_rank:
-        student.add_adapter(LoraConfig(r=lora_rank, lora_alpha=lora_rank, target_modules=SD3_LORA_TARGETS))
+        student.add_adapter(LoraConfig(r=lora_rank, lora_alpha=8, target_modules=SD3_LORA_TARGETS))
+        _perturb_lora_b(student, lora_b_std, seed + 1)
     teacher.freeze()
     cfg = FlashDiffusionSD3Config(K=[K], num_iterations_per_K=[10 ** 9], guidance_scale_min=7.0,
                                   guidance_scale_max=13.0, distill_loss_type="l2", use_dmd_loss=True,
@@ -278,7 +321,18 @@ def build_sd3(device, kwargs=None, lora_rank=64, seed=1234, K=32):
                              teacher_noise_scheduler=mk(FlowMatchEulerDiscreteScheduler, timestep_spacing="trailing"),
                              sampling_noise_scheduler=mk(FlashFlowMatchEulerDiscreteScheduler, timestep_spacing="trailing"),
                              teacher_sampling_noise_scheduler=mk(FlowMatchEulerDiscreteScheduler),
-                             discriminator=sd3_discriminator(kwargs["out_channels"])).to(device)
+                             discriminator=discriminator if discriminator is not None
+                             else sd3_discriminator(kwargs["out_channels"])).to(device)
+
+
+def build_sd3_distillation(device, lr=1e-5, **kw):
+    """(model, pipe) for the SD3 distillation step; two AdamW optimizers as in examples/train_flash_sd3.py:300-330."""
+    model = build_sd3(device, **kw)
+    pipe = TrainingPipeline(model, TrainingConfig(
+        optimizers_name=["AdamW", "AdamW"], learning_rates=[lr, lr],
+        trainable_params=[["student_denoiser"], ["discriminator."]]))
+    pipe.configure_optimizers()
+    return model, pipe
 
 
 def sd3_batch(B, seed, device, kwargs=None, tokens=154, hw=None):

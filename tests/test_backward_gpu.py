@@ -225,3 +225,22 @@ def test_sd15_like_unet_backward_vs_oracle():
     po = dict(ora.named_parameters())
     worst = min(_cos(p.grad, po[n].grad) for n, p in prod.named_parameters() if "lora_" in n)
     assert worst > 0.995, worst
+
+
+def test_sd15_like_distillation_training_step():
+    """BASELINE config 1 pipeline at reduced width: FlashDiffusion + TrainingPipeline around an SD1.5-shaped UNet (8 heads
+    per level -> padded head dims), the reference's SD1.5 discriminator on the 8x8 mid-block features."""
+    from flash import recipes
+    from oracle.unet import SD15_KWARGS
+    small15 = dict(SD15_KWARGS, block_out_channels=[64, 128, 256, 256], cross_attention_dim=96)
+    model, pipe = recipes.build_distillation(small15, recipes.sd15_discriminator(256), "cuda", lora_rank=16, K=4,
+                                             conditioner=recipes.text_only_conditioner(), ucg_keys=("text_emb",), lr=1e-3)
+    snap = {n: p.detach().clone() for n, p in model.named_parameters()}
+    for i in range(2):
+        batch = recipes.synthetic_batch(2, 64, 77, 96, 0, seed=20 + i, device="cuda", image_px=512.0)
+        out = pipe.training_step(batch, i, draws={"start_idx": [1, 3][i]})
+        assert float(out["loss_optimizer_0"]) > 0 and float(out["loss_optimizer_1"]) > 0
+    changed = {n for n, p in model.named_parameters() if not torch.equal(p, snap[n])}
+    assert any("lora_" in n for n in changed) and any(n.startswith("discriminator") for n in changed)
+    assert all(("lora_" in n and n.startswith("student_denoiser")) or n.startswith("discriminator") for n in changed)
+    assert all(torch.isfinite(p).all() for p in model.parameters())

@@ -410,3 +410,38 @@ def test_small_pixart_frozen_backbone_input_gradient():
     (prod(xa, t, cond) * w).sum().backward()
     (ora(xb, t, cond) * w).sum().backward()
     assert _rel(xa.grad, xb.grad) < 3e-2, _rel(xa.grad, xb.grad)
+
+
+def _small_disc(cin, hw):
+    return torch.nn.Sequential(torch.nn.Conv2d(cin, 8, 4, 2, 1, bias=False), torch.nn.SiLU(True),
+                               torch.nn.Conv2d(8, 1, hw // 2, 1, 0, bias=False), torch.nn.Flatten())
+
+
+def _check_training_step(model, pipe, make_batch, K):
+    snap = {n: p.detach().clone() for n, p in model.named_parameters()}
+    for i in range(2):
+        out = pipe.training_step(make_batch(i), i, draws={"start_idx": [1, K - 1][i]})
+        assert torch.isfinite(out["loss_optimizer_0"]).all() and torch.isfinite(out["loss_optimizer_1"]).all()
+        assert float(out["loss_optimizer_0"]) > 0 and float(out["loss_optimizer_1"]) > 0
+    changed = {n for n, p in model.named_parameters() if not torch.equal(p, snap[n])}
+    assert any(n.startswith("student_denoiser") and "lora_" in n for n in changed)
+    assert any(n.startswith("discriminator") for n in changed)
+    assert all(("lora_" in n and n.startswith("student_denoiser")) or n.startswith("discriminator") for n in changed)
+    assert all(torch.isfinite(p).all() for p in model.parameters())
+
+
+def test_pixart_distillation_training_step():
+    """BASELINE config 3 pipeline at a small size: FlashDiffusion + TrainingPipeline around the PixArt DiT (two
+    optimizers, DMD, lsgan through the frozen DiT, masked T5 context)."""
+    from flash.recipes import build_pixart_distillation, pixart_batch
+    model, pipe = build_pixart_distillation("cuda", lora_rank=8, K=4, kwargs=SMALL, discriminator=_small_disc(4, 32),
+                                            lora_b_std=0.02, lr=1e-3)
+    _check_training_step(model, pipe, lambda i: pixart_batch(2, 10 + i, "cuda", tokens=20, valid=13, hw=32, ctx_dim=64), 4)
+
+
+def test_sd3_distillation_training_step():
+    """BASELINE config 4 pipeline at a small size: FlashDiffusionSD3 + TrainingPipeline around the MMDiT."""
+    from flash.recipes import build_sd3_distillation, sd3_batch
+    model, pipe = build_sd3_distillation("cuda", kwargs=SD3_SMALL, lora_rank=8, K=4, discriminator=_small_disc(16, 16),
+                                         lora_b_std=0.02, lr=1e-3)
+    _check_training_step(model, pipe, lambda i: sd3_batch(2, 10 + i, "cuda", kwargs=SD3_SMALL, tokens=9, hw=16), 4)
