@@ -22,9 +22,9 @@ Prompt embeddings: the reference calls `pipeline.encode_prompt` (three text enco
 and `to`), and when it is None the four embedding tensors are read from the batch under the names the pipeline
 returns (`prompt_embeds`, `negative_prompt_embeds`, `pooled_prompt_embeds`, `negative_pooled_prompt_embeds`).
 
-GPU status: the MMDiT wrapper is forward-only (its LoRA targets include every AdaLN linear, so the backward needs the
-modulate / gate gradients that are not written yet): on CUDA this class samples and evaluates the teacher side; the
-training `forward` runs wherever the student denoiser supports autograd (the CPU oracle denoisers in tests/).
+On CUDA the denoisers are the B200 MMDiT wrappers (flash.models.transformers.sd3): teacher rollout, DMD / GAN
+evaluations, the student forward and its LoRA backward all run on the hand-written kernels; on CPU (tests/) the class is
+exercised around the fp32 oracle MMDiT.
 """
 import logging
 from copy import deepcopy
