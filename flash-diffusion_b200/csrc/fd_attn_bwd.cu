@@ -9,7 +9,8 @@
 // P and dS are written once to shared memory as 128B-swizzled [query][key] tiles and are consumed
 // both K-major (dQ = dS K) and MN-major (dV = P^T dO, dK = dS^T Q) — no transposes are materialised;
 // Q, dO, K are likewise consumed MN-major where the contraction runs over their row index.
-// Warps: 0 TMA producer, 1 MMA issuer, 2-5 softmax/dS (one query row per thread), 6-9 dQ drain.
+// Warps: 0 TMA producer, 1 MMA issuer, 2-9 softmax/dS (two warps per TMEM lane quarter, 64 keys of one query row per
+// thread: the exp / dS arithmetic is the critical path of a tile, ncu r01), 10-13 dQ drain.
 //
 // UPSTREAM math: autograd of F.scaled_dot_product_attention (student-LoRA backward and the GAN
 // generator path through the frozen teacher, reference flash_diffusion_model.py:260-265,563-592).
@@ -38,7 +39,7 @@ __global__ void attn_dq_convert_kernel(const float* __restrict__ acc, bf16* __re
 constexpr int AB_T = 128;                   // tile edge (queries and keys)
 constexpr int AB_D = 64;
 constexpr int AB_TILE = AB_T * AB_D * 2;    // 16 KB
-constexpr int AB_THREADS = 320;
+constexpr int AB_THREADS = 448;
 // K, V (resident) + 2 x (Q, dO) + P + dS
 constexpr int AB_SMEM = 2 * AB_TILE + 4 * AB_TILE + 2 * (2 * AB_TILE) + 256 + 1024;
 
@@ -51,6 +52,12 @@ struct AttnBwdKParams {
     bf16* dk; long long lddk, dk_bs;
     bf16* dv; long long lddv, dv_bs;
 };
+
+__device__ __forceinline__ float ab_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __global__ void attn_delta_kernel(const bf16* __restrict__ o, long long ldo, long long o_bs,
                                   const bf16* __restrict__ d_o, long long lddo, long long do_bs,
@@ -118,7 +125,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             mbar_init(&qdo_empty[s], 1);
         }
         mbar_init(s_full, 1);
-        mbar_init(pds_ready, 128);
+        mbar_init(pds_ready, 256);
         mbar_init(mma2_done, 1);
         mbar_init(dq_full, 1);
         mbar_init(dq_empty, 128);
@@ -198,48 +205,71 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 tc_commit(dq_full);
             }
         }
-    } else if (warp < 6) {
-        // softmax / dS warps: one query row per thread
+    } else if (warp < 10) {
+        // softmax / dS warps: thread (row, half) owns 64 keys of one query row
         const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         const int kv_valid = min(AB_T, p.Nkv - kv_tile * AB_T);
         const float* lse_bh = p.lse + ((long long)batch * p.H + head) * p.Nq;
         const float* delta_bh = p.delta + ((long long)batch * p.H + head) * p.Nq;
+        int q_row = row;
+        float lse_next = q_row < p.Nq ? lse_bh[q_row] : 0.f;
+        float dlt_next = q_row < p.Nq ? delta_bh[q_row] : 0.f;
         for (int i = 0; i < n_q_tiles; ++i) {
-            const int q_row = i * AB_T + row;
+            q_row = i * AB_T + row;
             const bool q_ok = q_row < p.Nq;
-            const float lse2 = q_ok ? lse_bh[q_row] * 1.4426950408889634f : 0.f;
-            const float dlt = q_ok ? delta_bh[q_row] : 0.f;
+            const float lse2 = lse_next * 1.4426950408889634f;
+            const float dlt = dlt_next;
+            if (i + 1 < n_q_tiles) {           // next tile's row scalars: off the critical path
+                const int nr = q_row + AB_T;
+                lse_next = nr < p.Nq ? lse_bh[nr] : 0.f;
+                dlt_next = nr < p.Nq ? delta_bh[nr] : 0.f;
+            }
+            const bool full = (i + 1) * AB_T <= p.Nq && kv_valid == AB_T;      // block-uniform: no masking needed
             mbar_wait(s_full, i & 1);
             tc_fence_after();
-            if (i > 0) mbar_wait(mma2_done, (i - 1) & 1);   // P / dS buffers free again
 #pragma unroll 1
-            for (int c = 0; c < AB_T / 32; ++c) {
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c = half * 2 + cc;
                 uint32_t rs[32], rp[32];
                 tmem_ld_32x32(tmem_S + lane_base + c * 32, rs);
                 tmem_ld_32x32(tmem_dP + lane_base + c * 32, rp);
                 tmem_ld_wait();
                 uint32_t pk[16], dk_[16];
+                if (full) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
-                    if (q_ok && c * 32 + j < kv_valid) {
-                        p0 = exp2f(__uint_as_float(rs[j]) * p.scale_log2 - lse2);
-                        d0 = p0 * (__uint_as_float(rp[j]) - dlt) * p.scale;
+                    for (int j = 0; j < 32; j += 2) {
+                        const float p0 = ab_ex2(fmaf(__uint_as_float(rs[j]), p.scale_log2, -lse2));
+                        const float p1 = ab_ex2(fmaf(__uint_as_float(rs[j + 1]), p.scale_log2, -lse2));
+                        const float d0 = p0 * (__uint_as_float(rp[j]) - dlt) * p.scale;
+                        const float d1 = p1 * (__uint_as_float(rp[j + 1]) - dlt) * p.scale;
+                        pk[j >> 1] = pack_bf16x2(p0, p1);
+                        dk_[j >> 1] = pack_bf16x2(d0, d1);
                     }
-                    if (q_ok && c * 32 + j + 1 < kv_valid) {
-                        p1 = exp2f(__uint_as_float(rs[j + 1]) * p.scale_log2 - lse2);
-                        d1 = p1 * (__uint_as_float(rp[j + 1]) - dlt) * p.scale;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
+                        if (q_ok && c * 32 + j < kv_valid) {
+                            p0 = ab_ex2(fmaf(__uint_as_float(rs[j]), p.scale_log2, -lse2));
+                            d0 = p0 * (__uint_as_float(rp[j]) - dlt) * p.scale;
+                        }
+                        if (q_ok && c * 32 + j + 1 < kv_valid) {
+                            p1 = ab_ex2(fmaf(__uint_as_float(rs[j + 1]), p.scale_log2, -lse2));
+                            d1 = p1 * (__uint_as_float(rp[j + 1]) - dlt) * p.scale;
+                        }
+                        pk[j >> 1] = pack_bf16x2(p0, p1);
+                        dk_[j >> 1] = pack_bf16x2(d0, d1);
                     }
-                    pk[j >> 1] = pack_bf16x2(p0, p1);
-                    dk_[j >> 1] = pack_bf16x2(d0, d1);
                 }
-                uint8_t* subp = sP + (c >> 1) * AB_TILE + row * 128;
-                uint8_t* subd = sDS + (c >> 1) * AB_TILE + row * 128;
+                if (cc == 0 && i > 0) mbar_wait(mma2_done, (i - 1) & 1);   // P / dS buffers free again
+                uint8_t* subp = sP + half * AB_TILE + row * 128;
+                uint8_t* subd = sDS + half * AB_TILE + row * 128;
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
-                    const int chunk = ((c & 1) * 4 + q4) ^ (row & 7);
+                    const int chunk = (cc * 4 + q4) ^ (row & 7);
                     *reinterpret_cast<uint4*>(subp + chunk * 16) =
                         make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
                     *reinterpret_cast<uint4*>(subd + chunk * 16) =
@@ -256,8 +286,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const int kv_row = kv_tile * AB_T + row;
         bf16* dk_row = p.dk + (long long)batch * p.dk_bs + (long long)kv_row * p.lddk + head * AB_D;
         bf16* dv_row = p.dv + (long long)batch * p.dv_bs + (long long)kv_row * p.lddv + head * AB_D;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
+        {
+            const int c = half;
             uint32_t rk[32], rv[32];
             tmem_ld_32x32(tmem_dK + lane_base + c * 32, rk);
             tmem_ld_32x32(tmem_dV + lane_base + c * 32, rv);
@@ -280,7 +310,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             }
         }
     } else {
-        // dQ drain warps 6..9: TMEM -> fp32 atomics
+        // dQ drain warps 10..13: TMEM -> fp32 atomics
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;

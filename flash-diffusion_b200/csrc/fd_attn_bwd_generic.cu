@@ -19,7 +19,7 @@ namespace fd {
 
 constexpr int GB_T = 128;
 constexpr int GB_TILE = GB_T * 64 * 2;   // one [128][64] bf16 sub-tile, 16 KB
-constexpr int GB_THREADS = 320;
+constexpr int GB_THREADS = 448;   // warps: 0 TMA, 1 MMA, 2-9 softmax / dS (two per TMEM lane quarter), 10-13 dQ drain
 
 struct AttnBwdGParams {
     int Nq, Nkv, H, d;
@@ -31,6 +31,12 @@ struct AttnBwdGParams {
     bf16* dk; long long lddk, dk_bs;
     bf16* dv; long long lddv, dv_bs;
 };
+
+__device__ __forceinline__ float gb_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __global__ void attn_delta_g_kernel(const bf16* __restrict__ o, long long ldo, long long o_bs,
                                     const bf16* __restrict__ d_o, long long lddo, long long do_bs,
@@ -116,7 +122,7 @@ attn_bwd_g_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             mbar_init(&qdo_empty[s], 1);
         }
         mbar_init(s_full, 1);
-        mbar_init(pds_ready, 128);
+        mbar_init(pds_ready, 256);
         mbar_init(mma2_done, 1);
         mbar_init(dq_full, 1);
         mbar_init(dq_empty, 128);
@@ -203,9 +209,10 @@ attn_bwd_g_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 }
             }
         }
-    } else if (warp < 6) {
-        // softmax / dS warps: one query row per thread
+    } else if (warp < 10) {
+        // softmax / dS warps: thread (row, half) owns 64 keys of one query row
         const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
         const int row = quarter * 32 + lane;
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
         const int nkv = p.kv_len != nullptr ? min(p.Nkv, max(1, p.kv_len[batch])) : p.Nkv;
@@ -217,35 +224,49 @@ attn_bwd_g_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             const bool q_ok = q_row < p.Nq;
             const float lse2 = q_ok ? lse_bh[q_row] * 1.4426950408889634f : 0.f;
             const float dlt = q_ok ? delta_bh[q_row] : 0.f;
+            const bool full = (i + 1) * GB_T <= p.Nq && kv_valid == GB_T;      // block-uniform: no masking needed
             mbar_wait(s_full, i & 1);
             tc_fence_after();
-            if (i > 0) mbar_wait(mma2_done, (i - 1) & 1);   // P / dS buffers free again
 #pragma unroll 1
-            for (int c = 0; c < GB_T / 32; ++c) {
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c = half * 2 + cc;
                 uint32_t rs[32], rp[32];
                 tmem_ld_32x32(tmem_S + lane_base + c * 32, rs);
                 tmem_ld_32x32(tmem_dP + lane_base + c * 32, rp);
                 tmem_ld_wait();
                 uint32_t pk[16], dk_[16];
+                if (full) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 2) {
-                    float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
-                    if (q_ok && c * 32 + j < kv_valid) {
-                        p0 = exp2f(__uint_as_float(rs[j]) * p.scale_log2 - lse2);
-                        d0 = p0 * (__uint_as_float(rp[j]) - dlt) * p.scale;
+                    for (int j = 0; j < 32; j += 2) {
+                        const float p0 = gb_ex2(fmaf(__uint_as_float(rs[j]), p.scale_log2, -lse2));
+                        const float p1 = gb_ex2(fmaf(__uint_as_float(rs[j + 1]), p.scale_log2, -lse2));
+                        const float d0 = p0 * (__uint_as_float(rp[j]) - dlt) * p.scale;
+                        const float d1 = p1 * (__uint_as_float(rp[j + 1]) - dlt) * p.scale;
+                        pk[j >> 1] = pack_bf16x2(p0, p1);
+                        dk_[j >> 1] = pack_bf16x2(d0, d1);
                     }
-                    if (q_ok && c * 32 + j + 1 < kv_valid) {
-                        p1 = exp2f(__uint_as_float(rs[j + 1]) * p.scale_log2 - lse2);
-                        d1 = p1 * (__uint_as_float(rp[j + 1]) - dlt) * p.scale;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 2) {
+                        float p0 = 0.f, p1 = 0.f, d0 = 0.f, d1 = 0.f;
+                        if (q_ok && c * 32 + j < kv_valid) {
+                            p0 = gb_ex2(fmaf(__uint_as_float(rs[j]), p.scale_log2, -lse2));
+                            d0 = p0 * (__uint_as_float(rp[j]) - dlt) * p.scale;
+                        }
+                        if (q_ok && c * 32 + j + 1 < kv_valid) {
+                            p1 = gb_ex2(fmaf(__uint_as_float(rs[j + 1]), p.scale_log2, -lse2));
+                            d1 = p1 * (__uint_as_float(rp[j + 1]) - dlt) * p.scale;
+                        }
+                        pk[j >> 1] = pack_bf16x2(p0, p1);
+                        dk_[j >> 1] = pack_bf16x2(d0, d1);
                     }
-                    pk[j >> 1] = pack_bf16x2(p0, p1);
-                    dk_[j >> 1] = pack_bf16x2(d0, d1);
                 }
-                uint8_t* subp = sP + (c >> 1) * GB_TILE + row * 128;
-                uint8_t* subd = sDS + (c >> 1) * GB_TILE + row * 128;
+                if (cc == 0 && i > 0) mbar_wait(mma2_done, (i - 1) & 1);   // P / dS buffers free again
+                uint8_t* subp = sP + half * GB_TILE + row * 128;
+                uint8_t* subd = sDS + half * GB_TILE + row * 128;
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
-                    const int chunk = ((c & 1) * 4 + q4) ^ (row & 7);
+                    const int chunk = (cc * 4 + q4) ^ (row & 7);
                     *reinterpret_cast<uint4*>(subp + chunk * 16) =
                         make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
                     *reinterpret_cast<uint4*>(subd + chunk * 16) =
@@ -262,8 +283,9 @@ attn_bwd_g_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const int kv_row = kv_tile * GB_T + row;
         bf16* dk_row = p.dk + (long long)batch * p.dk_bs + (long long)kv_row * p.lddk + head * d;
         bf16* dv_row = p.dv + (long long)batch * p.dv_bs + (long long)kv_row * p.lddv + head * d;
+        const int nch = d / 16, split = (nch + 1) / 2;
 #pragma unroll 1
-        for (int c = 0; c < d / 16; ++c) {
+        for (int c = half ? split : 0; c < (half ? nch : split); ++c) {
             uint32_t rk[16], rv[16];
             tmem_ld_32x16(tmem_dK + lane_base + c * 16, rk);
             tmem_ld_32x16(tmem_dV + lane_base + c * 16, rv);
@@ -286,7 +308,7 @@ attn_bwd_g_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             }
         }
     } else {
-        // dQ drain warps 6..9: TMEM -> fp32 atomics
+        // dQ drain warps 10..13: TMEM -> fp32 atomics
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
         const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
