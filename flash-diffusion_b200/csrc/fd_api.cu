@@ -96,6 +96,7 @@ struct ProfRec {
     int M, N, K;
 };
 static bool g_prof = false;
+bool profiling_on() { return g_prof; }
 static std::vector<ProfRec> g_recs;
 static std::mutex g_prof_mu;
 

@@ -50,6 +50,7 @@ int num_sms();
 
 // launch accounting (fd_launch_count) and optional per-launch CUDA-event profiling (fd_profile_*)
 void count_launch();
+bool profiling_on();
 enum ProfCat { PROF_GEMM = 0, PROF_CONV = 1, PROF_ATTN_FWD = 2, PROF_ATTN_BWD = 3, PROF_NCAT = 4 };
 struct ProfScope {
     cudaStream_t stream;
