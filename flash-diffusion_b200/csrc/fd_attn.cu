@@ -2,9 +2,7 @@
 //
 //   O = softmax(Q K^T * scale) V       per (batch, head), Q/K/V read in place from [B, N, H*64]
 //
-// Persistent CTAs (one per SM when the key-tile count is even) over work items (256 queries = two 128-row tiles, head,
-// batch): the roles keep global tile counters, so the producer prefetches the next item's K/V and Q and the issuer
-// starts its first S while the softmax warps still normalise and store the previous item's O.  18 warps:
+// One CTA per (256 queries = two 128-row tiles, head, batch); 18 warps:
 //   warp 0    TMA producer  : Q0,Q1 once, K/V tiles (128 keys) through a 3-stage ring
 //   warp 1    MMA issuer    : S_w = Q_w K^T (tcgen05 128x128x64) and O_w += P_w V (128x64x128) for w = 0,1,
 //                             interleaved so that the softmax of one tile overlaps the MMAs of the other
@@ -20,8 +18,6 @@
 //
 // UPSTREAM math: diffusers Attention + AttnProcessor2_0 -> F.scaled_dot_product_attention
 // (SURVEY.md §2.2); reference call path src/flash/models/unets/unet.py:108-119.
-#include <stdlib.h>
-
 #include "fd_common.cuh"
 #include "fd_host.h"
 
@@ -38,7 +34,7 @@ constexpr int ATT_STAGES = 3;
 constexpr int ATT_THREADS = 64 + 512;         // TMA warp, MMA warp, 2 tiles x 2 column halves x 4 softmax warps
 constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB
 // Q0,Q1 | K,V x stages | P0,P1 (2 sub-tiles each) | barriers
-constexpr int ATT_SMEM = 2 * ATT_TILE_BYTES + 2 * ATT_STAGES * ATT_TILE_BYTES + 4 * ATT_TILE_BYTES + 256 + 4096 + 128 + 1024;
+constexpr int ATT_SMEM = 2 * ATT_TILE_BYTES + 2 * ATT_STAGES * ATT_TILE_BYTES + 4 * ATT_TILE_BYTES + 256 + 4096 + 1024;
 
 struct AttnKParams {
     int Nq, Nkv;
@@ -47,7 +43,6 @@ struct AttnKParams {
     long long ldo, o_batch_stride;
     float* lse;  // [B,H,Nq] or null
     int H;
-    int q_blocks, n_items;   // work items = (q block of 256 rows, head, batch), q block fastest
 };
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -99,7 +94,7 @@ __device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
 // 16 ex2 per clock per SM and is the softmax bottleneck (ncu: mio_throttle is the top stall), so every
 // FD_ATTN_POLY_MOD-th pair of scores takes this path instead.  Relative error < 7e-4 (bf16 P has 2^-9 = 2e-3).
 #ifndef FD_ATTN_POLY_MOD
-#define FD_ATTN_POLY_MOD 8   // every 8th pair: with 4 the packed constants push the loop over the 96-register cap (270 B of spills)
+#define FD_ATTN_POLY_MOD 4
 #endif
 __device__ __forceinline__ float2 exp2_poly2(float2 x) {
     const float kMagic = 12582912.0f;   // 1.5 * 2^23
@@ -122,29 +117,161 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 // final O / l is invariant to the reference maximum).
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;
 
-struct AttnSmemParams {      // the kernel parameters the softmax warps need, staged in shared memory
-    int Nq, Nkv, H, q_blocks, n_kv_tiles;
-    float scale_log2;
-    long long ldo, o_bs;
-    bf16* o;
-    float* lse;
-};
-constexpr int ATT_BAR_BYTES = 256;                 // mbarriers + TMEM holder
-constexpr int ATT_MX_BYTES = 4096;                 // row-max exchange [tile][parity][half][128] floats
-constexpr int ATT_PAR_OFF = ATT_BAR_BYTES + ATT_MX_BYTES;
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmV, const AttnKParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    uint8_t* sQ = smem;                                   // 2 tiles
+    uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;                // ATT_STAGES tiles
+    uint8_t* sV = sK + ATT_STAGES * ATT_TILE_BYTES;       // ATT_STAGES tiles
+    uint8_t* sP = sV + ATT_STAGES * ATT_TILE_BYTES;       // 2 x (2 sub-tiles of [128][64])
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * ATT_TILE_BYTES);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;                  // [ATT_STAGES]
+    uint64_t* kv_empty = kv_full + ATT_STAGES;     // [ATT_STAGES]
+    uint64_t* s_full = kv_empty + ATT_STAGES;      // [2]  S_w(j) written by the tensor core
+    uint64_t* s_free = s_full + 2;                 // [2]  S_w(j) copied to registers: S_w(j+1) may be issued
+    uint64_t* p_ready = s_free + 2;                // [2]  P_w(j) in smem
+    uint64_t* pv_done = p_ready + 2;               // [2]  O_w += P_w(j) V(j) complete
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pv_done + 2);
+    float* mx_buf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [tile][parity][half][128]
 
-// Softmax / O-normalisation of ONE work item for the calling softmax warp (see attn_fwd_kernel).
-__device__ __noinline__ void attn_softmax_item(uint64_t* bars, uint32_t tmem_base, int it) {
-    const AttnSmemParams* sp = reinterpret_cast<const AttnSmemParams*>(reinterpret_cast<uint8_t*>(bars) + ATT_PAR_OFF);
-    uint64_t* s_full = bars + 1 + 2 * ATT_STAGES;
-    uint64_t* s_free = s_full + 2;
-    uint64_t* p_ready = s_free + 2;
-    uint64_t* pv_done = p_ready + 2;
-    float* mx_buf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + ATT_BAR_BYTES);
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int nkt = sp->n_kv_tiles;
-    {
+    const int q_blk = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
+    const int n_kv_tiles = (p.Nkv + ATT_BN - 1) / ATT_BN;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int s = 0; s < ATT_STAGES; ++s) {
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&kv_empty[s], 1);
+        }
+        for (int w = 0; w < 2; ++w) {
+            mbar_init(&s_full[w], 1);
+            mbar_init(&s_free[w], 256);
+            mbar_init(&p_ready[w], 256);
+            mbar_init(&pv_done[w], 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(tmem_holder, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+    // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+            tma_load_3d(&tmQ, q_full, sQ, head * ATT_D, q_blk * ATT_BM, batch);
+            tma_load_3d(&tmQ, q_full, sQ + ATT_TILE_BYTES, head * ATT_D, q_blk * ATT_BM + 128, batch);
+            int st = 0;
+            uint32_t ph = 0;
+            for (int j = 0; j < n_kv_tiles; ++j) {
+                mbar_wait(&kv_empty[st], ph ^ 1u);
+                mbar_arrive_expect_tx(&kv_full[st], 2 * ATT_TILE_BYTES);
+                tma_load_3d(&tmK, &kv_full[st], sK + st * ATT_TILE_BYTES, head * ATT_D, j * ATT_BN, batch);
+                tma_load_3d(&tmV, &kv_full[st], sV + st * ATT_TILE_BYTES, head * ATT_D, j * ATT_BN, batch);
+                if (++st == ATT_STAGES) {
+                    st = 0;
+                    ph ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_qk = make_idesc_bf16(128, ATT_BN, 0, 0);
+            constexpr uint32_t idesc_pv = make_idesc_bf16(128, ATT_D, 0, 1);  // B (=V) MN-major
+            const uint32_t q_addr = smem_u32(sQ);
+            const uint32_t p_addr = smem_u32(sP);
+            auto issue_s = [&](int w, int st) {
+                const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES);
+                const uint32_t qa = q_addr + w * ATT_TILE_BYTES;
+#pragma unroll
+                for (int k = 0; k < ATT_D / 16; ++k)
+                    tc_mma_bf16(tmem_base + w * 128, make_desc_k_sw128(qa + k * 32),
+                                make_desc_k_sw128(k_addr + k * 32), idesc_qk, k != 0 ? 1u : 0u);
+                tc_commit(&s_full[w]);
+            };
+            auto issue_pv = [&](int w, int st, int j) {
+                const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES);
+#if FD_ATTN_P_TMEM
+                // A operand (P, bf16) straight from TMEM: 8 columns (= 16 keys) per MMA
+#pragma unroll
+                for (int k = 0; k < ATT_BN / 16; ++k)
+                    tc_mma_bf16_ts(tmem_base + 256 + w * 64, tmem_base + 384 + w * 64 + k * 8,
+                                   make_desc_mn_sw128(v_addr + k * 2048, 0, 1024), idesc_pv, (j | k) != 0 ? 1u : 0u);
+#else
+                const uint32_t pa = p_addr + w * 2 * ATT_TILE_BYTES;
+#pragma unroll
+                for (int k = 0; k < ATT_BN / 16; ++k)
+                    tc_mma_bf16(tmem_base + 256 + w * 64,
+                                make_desc_k_sw128(pa + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32),
+                                make_desc_mn_sw128(v_addr + k * 2048, 0, 1024), idesc_pv, (j | k) != 0 ? 1u : 0u);
+#endif
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(&kv_full[0], 0);
+            tc_fence_after();
+            issue_s(0, 0);
+            issue_s(1, 0);
+            // Event-driven issue: per query tile w, S_w(j+1) may go as soon as S_w(j) was copied to registers
+            // (s_free) and K(j+1) has landed; P_w(j) V(j) as soon as P_w(j) is in smem (p_ready).  Whichever
+            // event fires first is served first, so a late warpgroup never delays the other one.
+            int next_s[2] = {1, 1};      // next S tile to issue
+            int next_pv[2] = {0, 0};     // next P V tile to issue
+            int kv_seen = 1;             // number of K/V tiles known to have landed
+            while (next_pv[0] < n_kv_tiles || next_pv[1] < n_kv_tiles) {
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                    const int js = next_s[w];
+                    if (js < n_kv_tiles) {
+                        // needs: s_free[w](js-1) and kv_full(js)
+                        if (mbar_test_wait(&s_free[w], (js - 1) & 1)) {
+                            bool kv_ok = js < kv_seen;
+                            if (!kv_ok && js == kv_seen) {
+                                const int stg = js % ATT_STAGES;
+                                if (mbar_test_wait(&kv_full[stg], (js / ATT_STAGES) & 1)) {
+                                    kv_seen = js + 1;
+                                    kv_ok = true;
+                                }
+                            }
+                            if (kv_ok) {
+                                tc_fence_after();
+                                issue_s(w, js % ATT_STAGES);
+                                next_s[w] = js + 1;
+                            }
+                        }
+                    }
+                    const int jp = next_pv[w];
+                    if (jp < n_kv_tiles && mbar_test_wait(&p_ready[w], jp & 1)) {
+                        tc_fence_after();
+                        issue_pv(w, jp % ATT_STAGES, jp);
+                        tc_commit(&pv_done[w]);
+                        next_pv[w] = jp + 1;
+                        // the K/V stage of tile jp is free once BOTH query tiles have issued their P V on it
+                        if (next_pv[w ^ 1] > jp) tc_commit(&kv_empty[jp % ATT_STAGES]);
+                    }
+                }
+            }
+        }
+    } else {
+        // 16 softmax warps: query tile w (0/1) x column half h (0/1) x TMEM lane quarter (= warp % 4).
+        // Thread (w, h, row) owns 64 of the 128 score columns of its row: half the serial work per thread and
+        // twice the warps per scheduler to hide the TMEM / MUFU / barrier latencies.  The two halves of a row
+        // exchange their partial row maximum through shared memory once per key tile.
         const int g = (warp - 2) >> 2;
         const int w = g >> 1, h = g & 1;
         const int quarter = warp & 3;
@@ -158,10 +285,10 @@ __device__ __noinline__ void attn_softmax_item(uint64_t* bars, uint32_t tmem_bas
         float* mxw = mx_buf + w * 512;
         const int bar_id = 1 + w;
         float m_used = -INFINITY, l_run = 0.f;
-        for (int j = 0; j < nkt; ++j) {
+        for (int j = 0; j < n_kv_tiles; ++j) {
             mbar_wait(&s_full[w], j & 1);
             tc_fence_after();
-            const int kv_valid = min(ATT_BN, sp->Nkv - j * ATT_BN) - h * 64;   // valid columns within this half
+            const int kv_valid = min(ATT_BN, p.Nkv - j * ATT_BN) - h * 64;   // valid columns within this half
             uint32_t sr[2][32];
             tmem_ld_32x32(tmem_S + lane_base, sr[0]);
             tmem_ld_32x32(tmem_S + lane_base + 32, sr[1]);
@@ -186,12 +313,12 @@ __device__ __noinline__ void attn_softmax_item(uint64_t* bars, uint32_t tmem_bas
             slot[h * 128 + row] = mx;
             asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
             mx = fmaxf(mx, slot[(h ^ 1) * 128 + row]);
-            const float m_new = mx * sp->scale_log2;
+            const float m_new = mx * p.scale_log2;
             const bool grow = m_new > m_used + ATT_RESCALE_THRESHOLD;      // first tile: m_used = -inf -> true
             const float alpha = (grow && j > 0) ? fast_exp2(m_used - m_new) : 1.0f;
             if (grow) m_used = m_new;
             l_run *= alpha;
-            const float2 sc2 = make_float2(sp->scale_log2, sp->scale_log2);
+            const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
             const float2 nm2 = make_float2(-m_used, -m_used);
             float2 ps2 = make_float2(0.f, 0.f);
             uint32_t pk[2][16];
@@ -253,26 +380,20 @@ __device__ __noinline__ void attn_softmax_item(uint64_t* bars, uint32_t tmem_bas
             mbar_arrive(&p_ready[w]);
         }
         // epilogue: combine the two halves' row sums, then O / l -> bf16 (each half stores 32 of the 64 channels)
-        float* slot = mxw + (nkt & 1) * 256;
+        float* slot = mxw + (n_kv_tiles & 1) * 256;
         slot[h * 128 + row] = l_run;
         asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
         l_run += slot[(h ^ 1) * 128 + row];
-        // the next item's first tile may re-use this slot for its row maximum: everyone must have read it first
-        asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
-        mbar_wait(&pv_done[w], (nkt - 1) & 1);
+        mbar_wait(&pv_done[w], (n_kv_tiles - 1) & 1);
         tc_fence_after();
-        const int item = (int)blockIdx.x + it * (int)gridDim.x;
-        const int q_blk = item % sp->q_blocks;
-        const int bh = item / sp->q_blocks;
-        const int head = bh % sp->H, batch = bh / sp->H;
         const int q_row = q_blk * ATT_BM + w * 128 + row;
         const float inv_l = 1.f / l_run;
-        bf16* orow = sp->o + (long long)batch * sp->o_bs + (long long)q_row * sp->ldo + head * ATT_D + h * 32;
+        bf16* orow = p.o + (long long)batch * p.o_batch_stride + (long long)q_row * p.ldo + head * ATT_D + h * 32;
         {
             uint32_t r[32];
             tmem_ld_32x32(tmem_O + lane_base, r);
             tmem_ld_wait();
-            if (q_row < sp->Nq) {
+            if (q_row < p.Nq) {
 #pragma unroll
                 for (int q4 = 0; q4 < 4; ++q4) {
                     uint4 u;
@@ -284,202 +405,8 @@ __device__ __noinline__ void attn_softmax_item(uint64_t* bars, uint32_t tmem_bas
                 }
             }
         }
-        if (h == 0 && sp->lse != nullptr && q_row < sp->Nq)
-            sp->lse[((long long)batch * sp->H + head) * sp->Nq + q_row] = (m_used + log2f(l_run)) * 0.69314718055994531f;
-    }
-}
-
-__global__ void __launch_bounds__(ATT_THREADS, 1)
-attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const AttnKParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t raw_addr = smem_u32(smem_raw);
-    uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-    uint8_t* sQ = smem;                                   // 2 tiles
-    uint8_t* sK = sQ + 2 * ATT_TILE_BYTES;                // ATT_STAGES tiles
-    uint8_t* sV = sK + ATT_STAGES * ATT_TILE_BYTES;       // ATT_STAGES tiles
-    uint8_t* sP = sV + ATT_STAGES * ATT_TILE_BYTES;       // 2 x (2 sub-tiles of [128][64])
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 4 * ATT_TILE_BYTES);
-    uint64_t* q_full = bars;
-    uint64_t* kv_full = bars + 1;                  // [ATT_STAGES]
-    uint64_t* kv_empty = kv_full + ATT_STAGES;     // [ATT_STAGES]
-    uint64_t* s_full = kv_empty + ATT_STAGES;      // [2]  S_w(j) written by the tensor core
-    uint64_t* s_free = s_full + 2;                 // [2]  S_w(j) copied to registers: S_w(j+1) may be issued
-    uint64_t* p_ready = s_free + 2;                // [2]  P_w(j) in smem
-    uint64_t* pv_done = p_ready + 2;               // [2]  O_w += P_w(j) V(j) complete
-    uint64_t* q_empty = pv_done + 2;               // every S of the current item has been issued and completed: sQ is free
-    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(q_empty + 1);
-    // bars + 256: row-max exchange buffer [tile][parity][half][128] floats, then the staged parameters (attn_softmax_item)
-
-    const int warp = threadIdx.x >> 5;
-    const int lane = threadIdx.x & 31;
-    const int n_kv_tiles = (p.Nkv + ATT_BN - 1) / ATT_BN;
-    // persistent CTA: items blockIdx.x, blockIdx.x + gridDim.x, ...; the barrier phases of a tile are j & 1 in every
-    // item, which needs an EVEN tile count whenever a CTA owns more than one item (the host launches one CTA per item
-    // otherwise)
-    const int n_local = p.n_items > (int)blockIdx.x ? (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmQ);
-        tma_prefetch_desc(&tmK);
-        tma_prefetch_desc(&tmV);
-    }
-    if (warp == 1 && lane == 0) {
-        AttnSmemParams* sp = reinterpret_cast<AttnSmemParams*>(reinterpret_cast<uint8_t*>(bars) + ATT_PAR_OFF);
-        sp->Nq = p.Nq; sp->Nkv = p.Nkv; sp->H = p.H; sp->q_blocks = p.q_blocks; sp->n_kv_tiles = n_kv_tiles;
-        sp->scale_log2 = p.scale_log2; sp->ldo = p.ldo; sp->o_bs = p.o_batch_stride; sp->o = p.o; sp->lse = p.lse;
-        mbar_init(q_full, 1);
-        mbar_init(q_empty, 1);
-        for (int s = 0; s < ATT_STAGES; ++s) {
-            mbar_init(&kv_full[s], 1);
-            mbar_init(&kv_empty[s], 1);
-        }
-        for (int w = 0; w < 2; ++w) {
-            mbar_init(&s_full[w], 1);
-            mbar_init(&s_free[w], 256);
-            mbar_init(&p_ready[w], 256);
-            mbar_init(&pv_done[w], 1);
-        }
-        fence_barrier_init();
-    }
-    if (warp == 0) {
-        tmem_alloc(tmem_holder, 512);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_holder;
-    // TMEM columns: S0 [0,128) S1 [128,256) O0 [256,320) O1 [320,384)
-
-    if (warp == 0) {
-        if (lane == 0) {
-            int st = 0;
-            uint32_t ph = 0;
-            for (int it = 0; it < n_local; ++it) {
-                const int item = (int)blockIdx.x + it * (int)gridDim.x;
-                const int q_blk = item % p.q_blocks;
-                const int bh = item / p.q_blocks;
-                const int head = bh % p.H, batch = bh / p.H;
-                if (it > 0) mbar_wait(q_empty, (it - 1) & 1);
-                mbar_arrive_expect_tx(q_full, 2 * ATT_TILE_BYTES);
-                tma_load_3d(&tmQ, q_full, sQ, head * ATT_D, q_blk * ATT_BM, batch);
-                tma_load_3d(&tmQ, q_full, sQ + ATT_TILE_BYTES, head * ATT_D, q_blk * ATT_BM + 128, batch);
-                for (int j = 0; j < n_kv_tiles; ++j) {
-                    mbar_wait(&kv_empty[st], ph ^ 1u);
-                    mbar_arrive_expect_tx(&kv_full[st], 2 * ATT_TILE_BYTES);
-                    tma_load_3d(&tmK, &kv_full[st], sK + st * ATT_TILE_BYTES, head * ATT_D, j * ATT_BN, batch);
-                    tma_load_3d(&tmV, &kv_full[st], sV + st * ATT_TILE_BYTES, head * ATT_D, j * ATT_BN, batch);
-                    if (++st == ATT_STAGES) {
-                        st = 0;
-                        ph ^= 1u;
-                    }
-                }
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc_qk = make_idesc_bf16(128, ATT_BN, 0, 0);
-            constexpr uint32_t idesc_pv = make_idesc_bf16(128, ATT_D, 0, 1);  // B (=V) MN-major
-            const uint32_t q_addr = smem_u32(sQ);
-            const uint32_t p_addr = smem_u32(sP);
-            auto issue_s = [&](int w, int st) {
-                const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES);
-                const uint32_t qa = q_addr + w * ATT_TILE_BYTES;
-#pragma unroll
-                for (int k = 0; k < ATT_D / 16; ++k)
-                    tc_mma_bf16(tmem_base + w * 128, make_desc_k_sw128(qa + k * 32),
-                                make_desc_k_sw128(k_addr + k * 32), idesc_qk, k != 0 ? 1u : 0u);
-                tc_commit(&s_full[w]);
-            };
-            auto issue_pv = [&](int w, int st, int j) {
-                const uint32_t v_addr = smem_u32(sV + st * ATT_TILE_BYTES);
-#if FD_ATTN_P_TMEM
-                // A operand (P, bf16) straight from TMEM: 8 columns (= 16 keys) per MMA
-#pragma unroll
-                for (int k = 0; k < ATT_BN / 16; ++k)
-                    tc_mma_bf16_ts(tmem_base + 256 + w * 64, tmem_base + 384 + w * 64 + k * 8,
-                                   make_desc_mn_sw128(v_addr + k * 2048, 0, 1024), idesc_pv, (j | k) != 0 ? 1u : 0u);
-#else
-                const uint32_t pa = p_addr + w * 2 * ATT_TILE_BYTES;
-#pragma unroll
-                for (int k = 0; k < ATT_BN / 16; ++k)
-                    tc_mma_bf16(tmem_base + 256 + w * 64,
-                                make_desc_k_sw128(pa + (k >> 2) * ATT_TILE_BYTES + (k & 3) * 32),
-                                make_desc_mn_sw128(v_addr + k * 2048, 0, 1024), idesc_pv, (j | k) != 0 ? 1u : 0u);
-#endif
-            };
-            // Event-driven issue on global tile counters: per query tile w, S_w(g) may go as soon as S_w(g-1) was
-            // copied to registers (s_free), K(g) has landed and -- for the first tile of an item -- its Q has landed;
-            // P_w(g) V(g) as soon as P_w(g) is ready (p_ready).  Whichever event fires first is served first, so a late
-            // warpgroup never delays the other one, and the first S of the NEXT item is issued while the softmax
-            // warps are still normalising and storing the previous item's O.
-            const int total = n_local * n_kv_tiles;
-            int next_s[2] = {0, 0};      // next global S tile to issue
-            int next_pv[2] = {0, 0};     // next global P V tile to issue
-            int js[2] = {0, 0}, its[2] = {0, 0};   // (item, tile) of next_s
-            int jp[2] = {0, 0};                    // tile-within-item of next_pv
-            int kv_seen = 0;             // number of K/V tiles known to have landed
-            int q_seen = 0;              // number of items whose Q is known to have landed
-            uint32_t idle = 0;
-            while (next_pv[0] < total || next_pv[1] < total) {
-                bool progressed = false;
-#pragma unroll
-                for (int w = 0; w < 2; ++w) {
-                    const int gs = next_s[w];
-                    if (gs < total && (gs == 0 || mbar_test_wait(&s_free[w], (gs - 1) & 1))) {
-                        bool ok = gs < kv_seen;
-                        if (!ok && gs == kv_seen && mbar_test_wait(&kv_full[gs % ATT_STAGES], (gs / ATT_STAGES) & 1)) {
-                            kv_seen = gs + 1;
-                            ok = true;
-                        }
-                        if (ok && js[w] == 0 && its[w] >= q_seen) {
-                            if (mbar_test_wait(q_full, its[w] & 1))
-                                q_seen = its[w] + 1;
-                            else
-                                ok = false;
-                        }
-                        if (ok) {
-                            tc_fence_after();
-                            issue_s(w, gs % ATT_STAGES);
-                            next_s[w] = gs + 1;
-                            if (++js[w] == n_kv_tiles) {
-                                js[w] = 0;
-                                ++its[w];
-                                // last S of this item for tile w; when the other tile is past it too, sQ is free
-                                if (next_s[w ^ 1] >= its[w] * n_kv_tiles) tc_commit(q_empty);
-                            }
-                            progressed = true;
-                        }
-                    }
-                    const int gp = next_pv[w];
-                    if (gp < total && mbar_test_wait(&p_ready[w], gp & 1)) {
-                        tc_fence_after();
-                        issue_pv(w, gp % ATT_STAGES, jp[w]);
-                        tc_commit(&pv_done[w]);
-                        next_pv[w] = gp + 1;
-                        if (++jp[w] == n_kv_tiles) jp[w] = 0;
-                        // the K/V stage of tile gp is free once BOTH query tiles have issued their P V on it
-                        if (next_pv[w ^ 1] > gp) tc_commit(&kv_empty[gp % ATT_STAGES]);
-                        progressed = true;
-                    }
-                }
-                if (progressed) {
-                    idle = 0;
-                } else if (++idle > (FD_SPIN_LIMIT << 2)) {
-                    printf("fd: attention issue loop stalled, block %d\n", (int)blockIdx.x);
-                    __trap();
-                }
-            }
-        }
-    } else {
-        // 16 softmax warps: query tile w (0/1) x column half h (0/1) x TMEM lane quarter (= warp % 4).
-        // Thread (w, h, row) owns 64 of the 128 score columns of its row: half the serial work per thread and
-        // twice the warps per scheduler to hide the TMEM / MUFU / barrier latencies.  The two halves of a row
-        // exchange their partial row maximum through shared memory once per key tile.
-        // one call per work item: the softmax loop is register-bound (64 scores + 32 packed probabilities per thread at
-        // the 96-register cap of a 576-thread CTA), and as a separate function it keeps the allocation of a one-item kernel
-        for (int it = 0; it < n_local; ++it) attn_softmax_item(bars, tmem_base, it);
+        if (h == 0 && p.lse != nullptr && q_row < p.Nq)
+            p.lse[((long long)batch * p.H + head) * p.Nq + q_row] = (m_used + log2f(l_run)) * 0.69314718055994531f;
     }
 
     tc_fence_before();
@@ -526,14 +453,7 @@ extern "C" int fd_attn_fwd(const FdAttnArgs* a, void* stream_) {
         FD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         attr_set = true;
     }
-    p.q_blocks = (a->Nq + ATT_BM - 1) / ATT_BM;
-    const long long items = (long long)p.q_blocks * a->H * a->B;
-    FD_CHECK_ARG(items < (1LL << 30), "fd_attn_fwd: too many work items");
-    p.n_items = (int)items;
-    // persistent CTAs need an even number of key tiles per item (barrier parities); otherwise one CTA per item
-    static const bool no_persist = getenv("FD_ATTN_NO_PERSIST") != nullptr;
-    const bool persistent = (((a->Nkv + ATT_BN - 1) / ATT_BN) % 2 == 0) && !no_persist;
-    const int grid = (persistent && p.n_items > num_sms()) ? num_sms() : p.n_items;
+    dim3 grid((a->Nq + ATT_BM - 1) / ATT_BM, a->H, a->B);
     ProfScope prof(stream, PROF_ATTN_FWD, 4.0 * (double)a->B * a->H * (double)a->Nq * (double)a->Nkv * ATT_D);
     attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tq, tk, tv, p);
     FD_CHECK_LAUNCH();
