@@ -49,8 +49,44 @@ class LoRALinear(nn.Module):
         raise RuntimeError("parameter container: executed by the B200 engine")
 
 
-def inject_lora(model: nn.Module, config: LoraConfig):
-    """Wrap every nn.Linear whose qualified name ends with a target suffix; freeze all non-LoRA parameters
+class LoRAConv2d(nn.Module):
+    """Parameter container for a LoRA-wrapped Conv2d with peft-0.9 keys (`lora_A.default.weight` [r, Cin, kh, kw],
+    `lora_B.default.weight` [Cout, r, 1, 1]).  The only convolution the example scripts' target lists reach is the DiT
+    patch embedding (`pos_embed.proj` matches "proj"); its forward / backward live in
+    flash.models.transformers.transformers.patch_embed."""
+
+    def __init__(self, base: nn.Conv2d, r: int, lora_alpha: float, init=True):
+        super().__init__()
+        self.base_layer = base
+        self.r = r
+        self.scaling = lora_alpha / r
+        self.lora_A = nn.ModuleDict({"default": nn.Conv2d(base.in_channels, r, base.kernel_size, base.stride,
+                                                         base.padding, bias=False)})
+        self.lora_B = nn.ModuleDict({"default": nn.Conv2d(r, base.out_channels, 1, 1, bias=False)})
+        self.lora_A.to(base.weight.device)
+        self.lora_B.to(base.weight.device)
+        if init == "gaussian":
+            nn.init.normal_(self.lora_A["default"].weight, std=1.0 / r)
+        else:
+            nn.init.kaiming_uniform_(self.lora_A["default"].weight, a=math.sqrt(5))
+        nn.init.zeros_(self.lora_B["default"].weight)
+
+    @property
+    def weight(self):
+        return self.base_layer.weight
+
+    @property
+    def bias(self):
+        return self.base_layer.bias
+
+    def forward(self, *a, **k):
+        raise RuntimeError("parameter container: executed by the B200 engine")
+
+
+def inject_lora(model: nn.Module, config: LoraConfig, conv_names=("pos_embed.proj",)):
+    """Wrap every nn.Linear whose qualified name ends with a target suffix, and the convolutions named in `conv_names`
+    when a target suffix matches them (peft wraps any matching Conv2d; the engines execute LoRA only on the DiT patch
+    convolution, and no target list of the example scripts reaches another one); freeze all non-LoRA parameters
     (peft `inject_adapter_in_model` + `mark_only_lora_as_trainable`)."""
     for p in model.parameters():
         p.requires_grad = False
@@ -58,8 +94,12 @@ def inject_lora(model: nn.Module, config: LoraConfig):
     for name, module in list(model.named_modules()):
         for child_name, child in list(module.named_children()):
             full = f"{name}.{child_name}" if name else child_name
-            if isinstance(child, nn.Linear) and any(full == t or full.endswith("." + t) for t in config.target_modules):
-                wrapped = LoRALinear(child, config.r, config.lora_alpha, config.init_lora_weights)
+            hit = any(full == t or full.endswith("." + t) for t in config.target_modules)
+            if hit and isinstance(child, nn.Conv2d) and full not in conv_names:
+                raise NotImplementedError(f"LoRA on the convolution {full!r} is not executed by the B200 engines")
+            if hit and isinstance(child, (nn.Linear, nn.Conv2d)):
+                cls = LoRALinear if isinstance(child, nn.Linear) else LoRAConv2d
+                wrapped = cls(child, config.r, config.lora_alpha, config.init_lora_weights)
                 if isinstance(module, nn.ModuleList):
                     module[int(child_name)] = wrapped
                 else:

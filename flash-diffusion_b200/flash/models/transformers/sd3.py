@@ -1,8 +1,8 @@
 """B200-native `DiffusersSD3Transformer2DWrapper` — SD3 MMDiT (reference src/flash/models/transformers/tranformers.py:103-163;
 constructor kwargs as at examples/train_flash_sd3.py:65-77).  Forward and backward: activation gradients (incl. the
 input gradient the GAN generator turn needs through the frozen backbone) and LoRA gradients for every Linear the
-reference's target list names (attention, feed-forward, AdaLN and embedding linears).  Not wrapped: the 2x2 patch
-convolution, which peft would also give a LoRA (its name ends in "proj").
+reference's target list names (attention, feed-forward, AdaLN and embedding linears) and for the 2x2 patch convolution,
+which the "proj" target also names (peft `lora.Conv2d`).
 
 Kernel mapping (UPSTREAM diffusers `SD3Transformer2DModel` math, restated in oracle/sd3.py):
   PatchEmbed conv 2x2/2 + cropped sin-cos table   space-to-depth + 4-tap implicit GEMM, table added as the epilogue residual
@@ -25,7 +25,7 @@ from ...b200 import ops, raw
 from ...b200.ops import LinearPack, cache_of
 from ..lora import inject_lora
 from ..unets.unet import TimestepEmbedding, _Container
-from .transformers import FeedForward, patch_embed, sincos_2d
+from .transformers import FeedForward, patch_embed, patch_lora_pack, sincos_2d
 
 
 class PatchEmbedSD3(_Container):
@@ -169,7 +169,7 @@ class DiffusersSD3Transformer2DWrapper(nn.Module):
                     "pos": raw.cast_scale(pe.cropped(hh, ww).to(dev).contiguous(), 1.0)}
         pk = cache_of(pe.proj).get(("patch", hh, ww), [pe.proj.weight, pe.proj.bias], build_patch)
         pos_b = self._pack(("pos_tiled", B, N), lambda: pk["pos"].repeat(B, 1).contiguous())
-        return patch_embed(sample.float(), pk, pos_b, (B, Cin, H, W, cpad))
+        return patch_embed(sample.float(), pk, pos_b, (B, Cin, H, W, cpad), patch_lora_pack(pe.proj, Cin, dev))
 
     def forward(self, sample: torch.Tensor, timestep: Union[torch.Tensor, float, int],
                 conditioning: Dict[str, torch.Tensor], hidden_states_masks: Optional[torch.Tensor] = None,

@@ -4,8 +4,8 @@ examples/train_flash_pixart.py:65-86).
 
 Forward and backward on the hand-written kernels: activation gradients (incl. the input gradient of the frozen GAN
 backbone) and LoRA gradients for every nn.Linear target of examples/train_flash_pixart.py:237-256 (attention with
-head-padded packs, feed-forward, caption projection, AdaLN-single and its embedders).  Not wrapped: the 2x2 patch
-convolution (peft would give it a LoRA too).
+head-padded packs, feed-forward, caption projection, AdaLN-single and its embedders) and for the 2x2 patch convolution,
+which the "proj" target also names (peft `lora.Conv2d`).
 
 Kernel mapping (UPSTREAM diffusers math, restated in oracle/dit.py):
   PatchEmbed conv 2x2/2    space-to-depth + 4-tap implicit-GEMM (fd_gemm conv mode) with the sin-cos position table added
@@ -164,7 +164,7 @@ class DiffusersTransformer2DWrapper(nn.Module):
             p.requires_grad = False
 
     def add_adapter(self, lora_config):
-        """LoRA on the nn.Linear targets (peft would also wrap the Conv2d `pos_embed.proj`, which this round does not)."""
+        """LoRA on the targets' nn.Linear modules and, as peft does for the "proj" target, on the patch convolution."""
         inject_lora(self, lora_config)
         self.__dict__["_packs"] = {}
         return self
@@ -267,7 +267,7 @@ class DiffusersTransformer2DWrapper(nn.Module):
                     "b": pe.proj.bias.detach().float().contiguous(), "pos": raw.cast_scale(pos.contiguous(), 1.0)}
         pk = cache_of(pe.proj).get(("patch", N), [pe.proj.weight, pe.proj.bias], build_patch)
         pos_b = self._pack(("pos_tiled", B, N), lambda: pk["pos"].repeat(B, 1).contiguous())
-        h = patch_embed(sample.float(), pk, pos_b, (B, Cin, H, W, cpad))
+        h = patch_embed(sample.float(), pk, pos_b, (B, Cin, H, W, cpad), patch_lora_pack(pe.proj, Cin, dev))
         # AdaLN parameters of every block in one small op: [L, B, 6, D]
         tables = self._pack("tables", lambda: torch.stack([b.scale_shift_table.detach().float()
                                                            for b in self.transformer_blocks]))
@@ -287,38 +287,84 @@ class DiffusersTransformer2DWrapper(nn.Module):
         return ops.unpatchify(out, B, hh, ww, p, self.out_channels, c_keep)
 
 
-def _patch_embed_fwd(sample, pk, pos_b, geom):
+def patch_lora_pack(proj, Cin, dev):
+    """Kernel-side view of a LoRA-wrapped patch convolution (peft `lora.Conv2d`: lora_A is a 2x2/2 conv to r channels,
+    lora_B a 1x1 conv): A as a [r, 4*64] matrix in the tap-major column order of the patch GEMM, s*B as [D, r]."""
+    if not hasattr(proj, "lora_A"):
+        return None
+
+    def build():
+        A = proj.lora_A["default"].weight.detach().float()                              # [r, Cin, 2, 2]
+        Bm = proj.lora_B["default"].weight.detach().float()[:, :, 0, 0] * proj.scaling   # [D, r]
+        r = A.shape[0]
+        buf = torch.zeros((r, 4, 64), device=dev)
+        buf[:, :, :Cin] = A.permute(0, 2, 3, 1).reshape(r, 4, Cin)
+        a = buf.reshape(r, 256)
+        return {"a": raw.cast_scale(a.contiguous(), 1.0), "a_t": raw.cast_scale(a.t().contiguous(), 1.0),
+                "b": raw.cast_scale(Bm.contiguous(), 1.0), "b_t": raw.cast_scale(Bm.t().contiguous(), 1.0),
+                "r": r, "scaling": proj.scaling, "Cin": Cin}
+    pack = cache_of(proj).get(("patch_lora", Cin), [proj.lora_A["default"].weight, proj.lora_B["default"].weight], build)
+    return dict(pack, params=(proj.lora_A["default"].weight, proj.lora_B["default"].weight))
+
+
+def _patch_embed_fwd(sample, pk, pos_b, geom, lora=None):
     """2x2/2 patch convolution + position table: space-to-depth, then a 4-tap implicit GEMM whose taps are the four
-    phase images; the table rides in the epilogue as the residual."""
+    phase images; the table rides in the epilogue as the residual, a LoRA on the convolution as a second K segment.
+    Returns (tokens, space-to-depth image, x A^T or None)."""
     B, Cin, H, W, cpad = geom
     hh, ww = H // 2, W // 2
     x = raw.space_to_depth(raw.nchw_to_nhwc(sample, cpad).view(B * H * W, cpad), B, H, W, cpad)
-    return raw.gemm(x, pk["w"], bias=pk["b"], residual=pos_b, M=B * hh * ww,
-                    conv=dict(NB_in=4 * B, H=hh, W=ww, C=cpad, taps=[(ph * B, 0, 0) for ph in range(4)]))
+    conv = dict(NB_in=4 * B, H=hh, W=ww, C=cpad, taps=[(ph * B, 0, 0) for ph in range(4)])
+    t = a2 = b2 = None
+    if lora is not None:
+        t = raw.gemm(x, lora["a"], M=B * hh * ww, conv=conv)
+        a2, b2 = t, lora["b"]
+    return raw.gemm(x, pk["w"], a2=a2, b2=b2, bias=pk["b"], residual=pos_b, M=B * hh * ww, conv=conv), x, t
 
 
 class _PatchEmbedFn(torch.autograd.Function):
-    """Input gradient of the patch embedding (the GAN generator turn differentiates the frozen backbone with respect
-    to its input, reference flash_diffusion_model.py:563-592): d(tokens) W gives the four phase images; depth-to-space
-    and NHWC->NCHW undo the forward re-layout."""
+    """Gradients of the patch embedding: with respect to its input (the GAN generator turn differentiates the frozen
+    backbone with respect to its input, reference flash_diffusion_model.py:563-592) — d(tokens) W gives the four phase
+    images, depth-to-space and NHWC->NCHW undo the forward re-layout — and with respect to a LoRA on the convolution."""
 
     @staticmethod
-    def forward(ctx, sample, pk, pos_b, geom):
-        ctx.pk, ctx.geom = pk, geom
-        return _patch_embed_fwd(sample, pk, pos_b, geom)
+    def forward(ctx, sample, pk, pos_b, geom, lora, *lora_params):
+        h, x, t = _patch_embed_fwd(sample, pk, pos_b, geom, lora)
+        ctx.pk, ctx.geom, ctx.lora = pk, geom, lora
+        ctx.save_for_backward(x if lora is not None else None, t)
+        return h
 
     @staticmethod
     def backward(ctx, dh):
         B, Cin, H, W, cpad = ctx.geom
         hh, ww = H // 2, W // 2
-        d = raw.gemm(dh.contiguous(), ctx.pk["w_t"])                                  # [B*N, 4*64], column = tap*64 + c
-        phases = d.view(B * hh * ww, 4, 64)[:, :, :cpad].permute(1, 0, 2).contiguous().view(4 * B * hh * ww, cpad)
-        dx = raw.depth_to_space(phases, B, H, W, cpad)
-        return raw.nhwc_to_nchw(dx, B, Cin, H, W), None, None, None
+        BN = B * hh * ww
+        lora = ctx.lora
+        x, t = ctx.saved_tensors
+        dh = dh.contiguous()
+        grads = ()
+        dt = None
+        if lora is not None:
+            r = lora["r"]
+            dt = raw.gemm(dh, lora["b_t"])                                               # [BN, r] = dh (sB)
+            X = torch.zeros((BN, 4, 64), device=dh.device, dtype=dh.dtype)                # the patch GEMM's A matrix
+            X[:, :, :cpad] = x.view(4, BN, cpad).permute(1, 0, 2)
+            d_a = raw.gemm(raw.transpose(dt), raw.transpose(X.view(BN, 256)), out_fp32=True)      # [r, 256]
+            d_b = raw.gemm(raw.transpose(dh), raw.transpose(t), out_fp32=True)                    # [D, r]
+            g_a = d_a.view(r, 4, 64)[:, :, :Cin].permute(0, 2, 1).reshape(r, Cin, 2, 2)
+            grads = (g_a, (d_b * lora["scaling"]).view(d_b.shape[0], r, 1, 1))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            d = raw.gemm(dh, ctx.pk["w_t"], a2=dt, b2=lora["a_t"] if lora is not None else None)   # [BN, 4*64]
+            phases = d.view(BN, 4, 64)[:, :, :cpad].permute(1, 0, 2).contiguous().view(4 * BN, cpad)
+            dx = raw.nhwc_to_nchw(raw.depth_to_space(phases, B, H, W, cpad), B, Cin, H, W)
+        return (dx, None, None, None, None, *grads)
 
 
-def patch_embed(sample, pk, pos_b, geom):
-    """sample NCHW fp32 -> tokens [B*N, D] bf16; pk = {"w" [D,256], "w_t", "b", "pos"} (see the wrappers)."""
-    if torch.is_grad_enabled() and sample.requires_grad:
-        return _PatchEmbedFn.apply(sample, pk, pos_b, geom)
-    return _patch_embed_fwd(sample, pk, pos_b, geom)
+def patch_embed(sample, pk, pos_b, geom, lora=None):
+    """sample NCHW fp32 -> tokens [B*N, D] bf16; pk = {"w" [D,256], "w_t", "b", "pos"} (see the wrappers), lora from
+    patch_lora_pack."""
+    params = lora["params"] if lora is not None else ()
+    if torch.is_grad_enabled() and (sample.requires_grad or any(q.requires_grad for q in params)):
+        return _PatchEmbedFn.apply(sample, pk, pos_b, geom, lora, *params)
+    return _patch_embed_fwd(sample, pk, pos_b, geom, lora)[0]

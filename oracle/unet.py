@@ -66,6 +66,29 @@ class LoRALinear(nn.Module):
         return self.base_layer(x) + self.lora_B["default"](self.lora_A["default"](x)) * self.scaling
 
 
+class LoRAConv2d(nn.Module):
+    """peft 0.9 `lora.Conv2d`: y = base(x) + lora_B(lora_A(x)) * (alpha / r); lora_A has the base kernel / stride /
+    padding, lora_B is 1x1.  Reached by the DiT recipes, whose target "proj" also names the patch convolution
+    (examples/train_flash_pixart.py:239-252, examples/train_flash_sd3.py:104-117)."""
+
+    def __init__(self, base: nn.Conv2d, r: int, lora_alpha: int, init: Union[bool, str] = True):
+        super().__init__()
+        self.base_layer = base
+        self.r = r
+        self.scaling = lora_alpha / r
+        self.lora_A = nn.ModuleDict({"default": nn.Conv2d(base.in_channels, r, base.kernel_size, base.stride,
+                                                         base.padding, bias=False)})
+        self.lora_B = nn.ModuleDict({"default": nn.Conv2d(r, base.out_channels, 1, 1, bias=False)})
+        if init == "gaussian":
+            nn.init.normal_(self.lora_A["default"].weight, std=1.0 / r)
+        else:
+            nn.init.kaiming_uniform_(self.lora_A["default"].weight, a=math.sqrt(5))
+        nn.init.zeros_(self.lora_B["default"].weight)
+
+    def forward(self, x):
+        return self.base_layer(x) + self.lora_B["default"](self.lora_A["default"](x)) * self.scaling
+
+
 class ResnetBlock2D(nn.Module):
     def __init__(self, in_channels, out_channels, temb_channels, groups=32, eps=1e-5):
         super().__init__()
@@ -377,7 +400,7 @@ class UNet2DConditionOracle(nn.Module):
             p.requires_grad = False
 
     def add_adapter(self, lora_config):
-        """diffusers PeftAdapterMixin.add_adapter -> peft inject_adapter_in_model: wrap every Linear whose
+        """diffusers PeftAdapterMixin.add_adapter -> peft inject_adapter_in_model: wrap every Linear / Conv2d whose
         name ends with one of target_modules; freeze everything that is not a LoRA weight."""
         targets = list(lora_config.target_modules)
         for p in self.parameters():
@@ -385,8 +408,9 @@ class UNet2DConditionOracle(nn.Module):
         for name, module in list(self.named_modules()):
             for child_name, child in list(module.named_children()):
                 full = f"{name}.{child_name}" if name else child_name
-                if isinstance(child, nn.Linear) and any(full == t or full.endswith("." + t) for t in targets):
-                    lora = LoRALinear(child, lora_config.r, lora_config.lora_alpha, lora_config.init_lora_weights)
+                if isinstance(child, (nn.Linear, nn.Conv2d)) and any(full == t or full.endswith("." + t) for t in targets):
+                    cls = LoRALinear if isinstance(child, nn.Linear) else LoRAConv2d
+                    lora = cls(child, lora_config.r, lora_config.lora_alpha, lora_config.init_lora_weights)
                     if isinstance(module, nn.ModuleList):
                         module[int(child_name)] = lora
                     else:

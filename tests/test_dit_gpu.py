@@ -195,10 +195,14 @@ def _sd3_objective_pair(lora_rank, seed=0):
     t_ora = SD3TransformerOracle(**SD3_SMALL).cuda()
     t_ora.load_state_dict(prod.teacher_denoiser.state_dict())
     s_ora = copy.deepcopy(t_ora)
+    from flash.models.lora import LoRAConv2d
     with torch.no_grad():
         for name, m in prod.student_denoiser.named_modules():
             if isinstance(m, LoRALinear):
                 s_ora.get_submodule(name).weight += m.scaling * (m.lora_B["default"].weight @ m.lora_A["default"].weight)
+            elif isinstance(m, LoRAConv2d):
+                a, b = m.lora_A["default"].weight, m.lora_B["default"].weight[:, :, 0, 0]
+                s_ora.get_submodule(name).weight += m.scaling * (b @ a.flatten(1)).view_as(m.weight)
     t_ora.freeze(); s_ora.freeze()
     ora = copy.copy(prod)
     ora.__dict__ = dict(prod.__dict__)
@@ -369,9 +373,9 @@ def test_small_pixart_lora_backward_matches_oracle():
     from flash.models.lora import LoraConfig
     from oracle.unet import LoraConfig as OLoraConfig
     from oracle.unet import UNet2DConditionOracle
+    from flash.recipes import DIT_LORA_TARGETS
     prod, ora = _pair(SMALL, seed=5)
-    targets = ["to_k", "to_q", "to_v", "to_out.0", "net.2", "linear", "linear_1", "linear_2"]
-    cfg = dict(r=8, lora_alpha=8, target_modules=targets)
+    cfg = dict(r=8, lora_alpha=8, target_modules=DIT_LORA_TARGETS)      # includes "proj": the patch convolution too
     ora = ora.cpu()
     UNet2DConditionOracle.add_adapter(ora, OLoraConfig(**cfg))
     prod.add_adapter(LoraConfig(**cfg))
