@@ -254,3 +254,23 @@ def test_sample_four_steps_and_teacher_reference():
                             generator=torch.Generator().manual_seed(0))
     assert out.shape == z.shape and ref.shape == z.shape and torch.isfinite(out).all() and torch.isfinite(ref).all()
     assert len(model.sampling_noise_scheduler.timesteps) == 4
+
+
+def test_inject_lora_wraps_the_patch_convolution_like_peft():
+    """The "proj" target of the DiT scripts also names `pos_embed.proj` (a Conv2d): peft gives it a `lora.Conv2d`
+    (lora_A with the base kernel / stride, lora_B 1x1).  Any other convolution a target list reaches is refused."""
+    from flash.models.lora import LoRAConv2d
+    from flash.recipes import DIT_LORA_TARGETS
+    student = SD3TransformerOracle(**TINY)
+    inject_lora(student, LoraConfig(r=4, lora_alpha=8, target_modules=DIT_LORA_TARGETS))
+    proj = student.pos_embed.proj
+    assert isinstance(proj, LoRAConv2d) and proj.scaling == 2.0
+    sd = student.state_dict()
+    assert sd["pos_embed.proj.lora_A.default.weight"].shape == (4, 4, 2, 2)
+    assert sd["pos_embed.proj.lora_B.default.weight"].shape == (16, 4, 1, 1)
+    assert sd["pos_embed.proj.base_layer.weight"].shape == (16, 4, 2, 2)
+    assert proj.lora_A["default"].stride == (2, 2) and float(proj.lora_B["default"].weight.abs().max()) == 0.0
+    net = nn.Sequential()
+    net.add_module("body", nn.Conv2d(3, 3, 3))
+    with pytest.raises(NotImplementedError, match="convolution"):
+        inject_lora(net, LoraConfig(r=4, target_modules=["body"]))
