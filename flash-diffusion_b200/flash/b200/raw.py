@@ -262,9 +262,9 @@ def attention_bwd(q, k, v, o, lse, do, H, scale=None, dq=None, dk=None, dv=None,
     dk = torch.empty((B, Nkv, HD), device=q.device, dtype=BF16) if dk is None else dk
     dv = torch.empty((B, Nkv, HD), device=q.device, dtype=BF16) if dv is None else dv
     delta = torch.empty((B, H, Nq), device=q.device, dtype=torch.float32)
-    if head_dim <= 80 or (head_dim == 64 and kv_len is None):
+    if head_dim <= 80:
         dq_accum = torch.empty((B, Nq, HD), device=q.device, dtype=torch.float32)
-    else:       # short-sequence kernel: scratch for P and dS
+    else:       # short-sequence kernels: scratch for P and dS
         dq_accum = torch.empty((2 * B * H * Nq * Nkv,), device=q.device, dtype=torch.float32)
     a = _l.FdAttnBwdArgs()
     f = a.f
