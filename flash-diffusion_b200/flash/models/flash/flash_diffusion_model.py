@@ -421,3 +421,47 @@ class FlashDiffusion(BaseModel):
                 ref = ts_sched.step(eps, t, ref, return_dict=False)[0]
             decoded_ref = self.vae.decode(ref) if self.vae is not None else ref
         return decoded, decoded_ref
+
+    # ------------------------------------------------------------------ sample logging (reference :917-1019)
+    def log_samples(self, batch: Dict[str, Any], input_shape=None, guidance_scale: float = 1.0,
+                    teacher_guidance_scale: float = 5.0, max_samples: int = 8, num_steps=20, device="cpu",
+                    log_teacher_samples=False, conditioner_inputs: Dict = None, conditioner_uncond_inputs: Dict = None,
+                    **sample_kwargs):
+        """{"samples_{n}_steps/{SamplerClass}_{cfg}_cfg/student": tensor, ".../teacher": tensor} for every n in
+        `num_steps`; the number of samples is capped by `max_samples` and by the shortest conditioning entry."""
+        steps = [num_steps] if isinstance(num_steps, int) else list(num_steps)
+        logs = {}
+        N = max_samples
+        if batch is not None:
+            N = min(N, min(len(batch[key]) for key in batch))
+
+        def merge(extra):
+            nonlocal N
+            N = min(N, min(len(extra[key]) for key in extra))
+            extra.update({k: v.to(device) for k, v in extra.items() if isinstance(v, torch.Tensor)})
+            return extra
+
+        if conditioner_inputs is not None:
+            batch.update(merge(conditioner_inputs))
+        batch_uncond = None
+        if conditioner_uncond_inputs is not None:
+            batch_uncond = deepcopy(batch)
+            batch_uncond.update(merge(conditioner_uncond_inputs))
+        if input_shape is None:
+            if self.vae is None:
+                raise ValueError("input_shape must be passed when no VAE is used in the model")
+            px = batch[self.vae.config.input_key].shape[2:]
+            f = self.vae.downsampling_factor
+            input_shape = (self.vae.latent_channels, px[0] // f, px[1] // f)
+        for n in steps:
+            z = torch.randn(N, *input_shape).to(device)
+            logging.debug(f"Sampling {N} samples: steps={n}, guidance_scale={guidance_scale}")
+            samples, samples_ref = self.sample(z, num_steps=n, conditioner_inputs=batch,
+                                               uncond_conditioner_inputs=batch_uncond, guidance_scale=guidance_scale,
+                                               teacher_guidance_scale=teacher_guidance_scale, max_samples=N,
+                                               log_teacher_samples=log_teacher_samples, **sample_kwargs)
+            logs[f"samples_{n}_steps/{self.sampling_noise_scheduler.__class__.__name__}_{guidance_scale}_cfg/student"] = samples
+            if samples_ref is not None:
+                logs[f"samples_{n}_steps/{self.teacher_sampling_noise_scheduler.__class__.__name__}"
+                     f"_{teacher_guidance_scale}_cfg/teacher"] = samples_ref
+        return logs

@@ -274,3 +274,13 @@ def test_inject_lora_wraps_the_patch_convolution_like_peft():
     net.add_module("body", nn.Conv2d(3, 3, 3))
     with pytest.raises(NotImplementedError, match="convolution"):
         inject_lora(net, LoraConfig(r=4, target_modules=["body"]))
+
+
+def test_sd3_log_samples():
+    model = _model()
+    logs = model.log_samples(_batch(), input_shape=(4, 8, 8), num_steps=[1, 4], max_samples=8, log_teacher_samples=True)
+    assert set(logs) == {"samples_1_steps/FlashFlowMatchEulerDiscreteScheduler_1.0_cfg/student",
+                         "samples_4_steps/FlashFlowMatchEulerDiscreteScheduler_1.0_cfg/student",
+                         "samples_1_steps/FlowMatchEulerDiscreteScheduler_5.0_cfg/teacher",
+                         "samples_4_steps/FlowMatchEulerDiscreteScheduler_5.0_cfg/teacher"}
+    assert all(v.shape == (2, 4, 8, 8) and torch.isfinite(v).all() for v in logs.values())

@@ -212,3 +212,21 @@ def test_lean_discriminator_turn_is_output_preserving():
     assert all(p.grad is None for p in lean.student_denoiser.parameters())
     # generator turn untouched
     assert lean(b, step=0, draws=d)["loss"][0] is not None
+
+
+def test_log_samples_keys_and_sample_cap():
+    """reference flash_diffusion_model.py:917-1019: one entry per num_steps (plus the teacher's when asked), N capped by
+    max_samples and by the shortest conditioning entry; input_shape is mandatory without a VAE."""
+    model = _model()
+    model.teacher_sampling_noise_scheduler = DPMSolverMultistepScheduler.from_pretrained("x", timestep_spacing="trailing")
+    b = _batch(B=2)
+    logs = model.log_samples(dict(b), input_shape=(4, 16, 16), num_steps=[1, 2], max_samples=8, guidance_scale=1.0,
+                             teacher_guidance_scale=3.0, log_teacher_samples=True)
+    assert set(logs) == {"samples_1_steps/LCMScheduler_1.0_cfg/student", "samples_2_steps/LCMScheduler_1.0_cfg/student",
+                         "samples_1_steps/DPMSolverMultistepScheduler_3.0_cfg/teacher",
+                         "samples_2_steps/DPMSolverMultistepScheduler_3.0_cfg/teacher"}
+    assert all(v.shape == (2, 4, 16, 16) and torch.isfinite(v).all() for v in logs.values())
+    one = model.log_samples(dict(b), input_shape=(4, 16, 16), num_steps=1, max_samples=1)
+    assert list(one.values())[0].shape[0] == 1
+    with pytest.raises(ValueError, match="input_shape"):
+        model.log_samples(dict(b), num_steps=1)
