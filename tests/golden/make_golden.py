@@ -16,7 +16,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 
+from oracle import flash_step_sd3 as O3  # noqa: E402
 from oracle import schedulers as OS  # noqa: E402
+from oracle.dit import PixArtTransformerOracle  # noqa: E402
+from oracle.sd3 import SD3TransformerOracle  # noqa: E402
 from oracle.unet import LoraConfig, UNet2DConditionOracle  # noqa: E402
 
 GOLD_UNET = dict(in_channels=4, out_channels=4, down_block_types=["DownBlock2D", "CrossAttnDownBlock2D"],
@@ -61,7 +64,54 @@ def gold_inputs():
     return x, t, cond
 
 
+GOLD_PIXART = dict(sample_size=32, num_layers=2, attention_head_dim=24, in_channels=4, out_channels=8, patch_size=2,
+                   attention_bias=True, num_attention_heads=4, cross_attention_dim=96, activation_fn="gelu-approximate",
+                   norm_type="ada_norm_single", norm_elementwise_affine=False, norm_eps=1e-6, caption_channels=64,
+                   projection_class_embeddings_input_dim=8, time_embed_dim=96, timesteps_embedding_num_channels=32,
+                   use_concat_vector_conditioning=True, num_vector_conditionings=3)
+GOLD_SD3 = dict(sample_size=16, patch_size=2, in_channels=16, num_layers=3, attention_head_dim=64, num_attention_heads=2,
+                joint_attention_dim=48, caption_projection_dim=128, pooled_projection_dim=40, out_channels=16,
+                pos_embed_max_size=12)
+
+
+def _seeded(net, seed):
+    sd = seeded_state_dict(net, seed)
+    for name, buf in net.named_buffers():          # deterministic position tables stay as constructed
+        if name in sd:
+            sd[name] = buf.clone()
+    net.load_state_dict(sd)
+    return net
+
+
+def gold_pixart():
+    return _seeded(PixArtTransformerOracle(**GOLD_PIXART), 2025)
+
+
+def gold_sd3():
+    return _seeded(SD3TransformerOracle(**GOLD_SD3), 2026)
+
+
+def gold_dit_inputs(channels, hw, tokens, ctx_dim, vec_dim, masked):
+    g = torch.Generator().manual_seed(77)
+    x = torch.randn(2, channels, hw, hw, generator=g)
+    t = torch.tensor([999.0, 250.0])
+    cond = {"cond": {"crossattn": torch.randn(2, tokens, ctx_dim, generator=g), "vector": torch.randn(2, vec_dim, generator=g)}}
+    if masked:
+        cond["cond"]["attention_mask"] = (torch.arange(tokens)[None, :] < torch.tensor([[tokens - 6], [tokens - 3]])).long()
+    return x, t, cond
+
+
 def main():
+    with torch.no_grad():
+        px = gold_pixart()(*gold_dit_inputs(4, 32, 20, 64, 24, True))
+        s3 = gold_sd3()(*gold_dit_inputs(16, 16, 9, 48, 40, False))
+    grids = {}
+    for K in (4, 32):
+        ts, sig = O3.inference_grid(K)
+        grids[f"trailing_K{K}"] = {"timesteps": ts, "sigmas": sig}
+    tt, ss = O3.training_grid()
+    grids["train_0_499_999"] = {"timesteps": tt[[0, 499, 999]], "sigmas": ss[[0, 499, 999]]}
+    torch.save({"pixart_out": px, "sd3_out": s3, "flow_grids": grids}, os.path.join(HERE, "tiny_dit.pt"))
     net = gold_unet()
     x, t, cond = gold_inputs()
     with torch.no_grad():

@@ -13,6 +13,7 @@ import make_golden as G  # noqa: E402
 
 UNET_GOLD = torch.load(os.path.join(HERE, "golden", "tiny_unet_lora.pt"))
 SCHED_GOLD = torch.load(os.path.join(HERE, "golden", "schedulers.pt"))
+DIT_GOLD = torch.load(os.path.join(HERE, "golden", "tiny_dit.pt"))
 
 
 def _rel(a, b):
@@ -69,3 +70,40 @@ def test_b200_unet_matches_golden():
         mid = net(x.cuda(), t.cuda(), cond, return_intermediate=True)
     assert _rel(out.cpu(), UNET_GOLD["out"]) < 2e-2, _rel(out.cpu(), UNET_GOLD["out"])
     assert _rel(mid.mean(dim=(2, 3)).cpu(), UNET_GOLD["mid_mean"]) < 2e-2
+
+
+def test_oracle_dits_and_flow_grids_match_golden():
+    with torch.no_grad():
+        assert _rel(G.gold_pixart()(*G.gold_dit_inputs(4, 32, 20, 64, 24, True)), DIT_GOLD["pixart_out"]) < 1e-4
+        assert _rel(G.gold_sd3()(*G.gold_dit_inputs(16, 16, 9, 48, 40, False)), DIT_GOLD["sd3_out"]) < 1e-4
+    from flash.schedulers import FlowMatchEulerDiscreteScheduler
+    s = FlowMatchEulerDiscreteScheduler.from_pretrained("x", timestep_spacing="trailing")
+    g = DIT_GOLD["flow_grids"]["train_0_499_999"]
+    idx = torch.tensor([0, 499, 999])
+    assert torch.equal(s.timesteps[idx], g["timesteps"]) and torch.equal(s.sigmas[idx], g["sigmas"])
+    for K in (4, 32):
+        s.set_timesteps(K)
+        g = DIT_GOLD["flow_grids"][f"trailing_K{K}"]
+        assert torch.equal(s.timesteps, g["timesteps"]) and torch.equal(s.sigmas, g["sigmas"])
+
+
+@pytest.mark.gpu
+def test_b200_dits_match_golden():
+    from flash.models.transformers import DiffusersSD3Transformer2DWrapper, DiffusersTransformer2DWrapper
+
+    def run(cls, kwargs, ora, inputs):
+        with torch.device("meta"):
+            net = cls(**kwargs)
+        net = net.to_empty(device="cuda")
+        net.load_state_dict(ora.state_dict(), strict=False)
+        if hasattr(ora.pos_embed, "pos_embed"):
+            net.pos_embed.pos_embed = ora.pos_embed.pos_embed.clone().cuda()
+        net.freeze()
+        x, t, cond = inputs
+        cond = {"cond": {k: v.cuda() for k, v in cond["cond"].items()}}
+        with torch.no_grad():
+            return net(x.cuda(), t.cuda(), cond).cpu()
+    px = run(DiffusersTransformer2DWrapper, G.GOLD_PIXART, G.gold_pixart(), G.gold_dit_inputs(4, 32, 20, 64, 24, True))
+    assert _rel(px, DIT_GOLD["pixart_out"]) < 2e-2, _rel(px, DIT_GOLD["pixart_out"])
+    s3 = run(DiffusersSD3Transformer2DWrapper, G.GOLD_SD3, G.gold_sd3(), G.gold_dit_inputs(16, 16, 9, 48, 40, False))
+    assert _rel(s3, DIT_GOLD["sd3_out"]) < 2e-2, _rel(s3, DIT_GOLD["sd3_out"])
