@@ -38,8 +38,10 @@ def _sincos_1d(embed_dim, pos):
 
 def sincos_2d(embed_dim, grid_size, base_size, interpolation_scale):
     """UPSTREAM diffusers `get_2d_sincos_pos_embed` (PixArt position table; not a parameter, not in the state dict)."""
-    g = np.arange(grid_size, dtype=np.float32) / (grid_size / base_size) / interpolation_scale
-    grid = np.stack(np.meshgrid(g, g), axis=0).reshape(2, 1, grid_size, grid_size)
+    gh, gw = (grid_size, grid_size) if isinstance(grid_size, int) else grid_size
+    g_h = np.arange(gh, dtype=np.float32) / (gh / base_size) / interpolation_scale
+    g_w = np.arange(gw, dtype=np.float32) / (gw / base_size) / interpolation_scale
+    grid = np.stack(np.meshgrid(g_w, g_h), axis=0).reshape(2, 1, gh, gw)          # w goes first (upstream)
     return np.concatenate([_sincos_1d(embed_dim // 2, grid[0]), _sincos_1d(embed_dim // 2, grid[1])], axis=1)
 
 
@@ -48,8 +50,19 @@ class PatchEmbed(_Container):
         super().__init__()
         self.proj = nn.Conv2d(in_channels, embed_dim, patch_size, stride=patch_size)
         grid = sample_size // patch_size
-        pe = sincos_2d(embed_dim, grid, base_size=grid, interpolation_scale=max(sample_size // 64, 1))
+        self.grid, self.base_size, self.interpolation_scale = grid, grid, max(sample_size // 64, 1)
+        pe = sincos_2d(embed_dim, grid, base_size=grid, interpolation_scale=self.interpolation_scale)
         self.register_buffer("pos_embed", torch.from_numpy(pe).float()[None], persistent=False)
+
+    def table(self, hh, ww):
+        """Position table of an hh x ww patch grid.  diffusers' PatchEmbed.forward RECOMPUTES the 2-D sincos table
+        for (height, width) whenever the input grid differs from the configured square one (same base_size and
+        interpolation_scale) — slicing the first rows of the square table would give wrong 2-D positions."""
+        if (hh, ww) == (self.grid, self.grid):
+            return self.pos_embed[0]
+        pe = sincos_2d(self.pos_embed.shape[-1], (hh, ww), base_size=self.base_size,
+                       interpolation_scale=self.interpolation_scale)
+        return torch.from_numpy(pe).float()
 
 
 class AdaLayerNormSingle(_Container):
@@ -261,12 +274,12 @@ class DiffusersTransformer2DWrapper(nn.Module):
             wt = pe.proj.weight.detach().float()                      # [D, Cin, 2, 2]
             buf = torch.zeros((D, 4, 64), device=dev)
             buf[:, :, :Cin] = wt.permute(0, 2, 3, 1).reshape(D, 4, Cin)
-            pos = pe.pos_embed[0, :N].to(dev)
+            pos = pe.table(H // 2, W // 2).to(dev)
             return {"w": raw.cast_scale(buf.reshape(D, 256), 1.0),
                     "w_t": raw.cast_scale(buf.reshape(D, 256).t().contiguous(), 1.0),
                     "b": pe.proj.bias.detach().float().contiguous(), "pos": raw.cast_scale(pos.contiguous(), 1.0)}
-        pk = cache_of(pe.proj).get(("patch", N), [pe.proj.weight, pe.proj.bias], build_patch)
-        pos_b = self._pack(("pos_tiled", B, N), lambda: pk["pos"].repeat(B, 1).contiguous())
+        pk = cache_of(pe.proj).get(("patch", H // 2, W // 2), [pe.proj.weight, pe.proj.bias], build_patch)
+        pos_b = self._pack(("pos_tiled", B, H // 2, W // 2), lambda: pk["pos"].repeat(B, 1).contiguous())
         h = patch_embed(sample.float(), pk, pos_b, (B, Cin, H, W, cpad), patch_lora_pack(pe.proj, Cin, dev))
         # AdaLN parameters of every block in one small op: [L, B, 6, D]
         tables = self._pack("tables", lambda: torch.stack([b.scale_shift_table.detach().float()

@@ -240,6 +240,16 @@ class DiffusersUNet2DCondWrapper(nn.Module):
     def add_adapter(self, lora_config):
         """diffusers `add_adapter` (peft inject_adapter_in_model) — reference call examples/train_flash_sdxl.py:217."""
         inject_lora(self, lora_config)
+        # The UNet engine executes LoRA on the attention projections, proj_in/proj_out and ff.net.2 (ops.linear).  The
+        # GEGLU projection and the time / class embedding MLPs run fused, LoRA-free GEMMs: a target list reaching them
+        # would create adapters that are never applied and never receive gradients — refuse instead (ADVICE r1).
+        bad = [n for n, m in self.named_modules() if isinstance(m, LoRALinear) and
+               (n.endswith("ff.net.0.proj") or n.endswith("time_emb_proj") or n.startswith("time_embedding.")
+                or n.startswith("class_embedding."))]
+        if bad:
+            raise NotImplementedError(f"LoRA on {bad[:3]}... is not executed by the B200 UNet engine (GEGLU / "
+                                      "time-embedding GEMMs are fused without an adapter segment); the reference's "
+                                      "SD / SDXL target lists (to_q, to_k, to_v, to_out.0) do not reach them")
         self.__dict__["_packs"] = {}
         return self
 

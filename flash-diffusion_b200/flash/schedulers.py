@@ -39,9 +39,17 @@ def _spaced_timesteps(num_train: int, num_inference: int, spacing: str, steps_of
 
 # repo -> scheduler config used by `from_pretrained` (there is no network; these are the published
 # scheduler_config.json values of the checkpoints the reference examples name)
+_SD_CFG = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+               steps_offset=1)
 _KNOWN_CONFIGS = {
-    "default_sd": dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
-                       steps_offset=1),
+    # examples/train_flash_sdxl.py:221-236 and examples/train_flash_sd.py:204-219 (SD1.5 also reads the SDXL repo)
+    "stabilityai/stable-diffusion-xl-base-1.0": _SD_CFG,
+    "runwayml/stable-diffusion-v1-5": _SD_CFG,
+    # examples/train_flash_pixart.py:259-274: the published PixArt-alpha scheduler_config.json is a
+    # DPMSolverMultistepScheduler over LINEAR betas 1e-4 .. 0.02, steps_offset 0 (restated from memory: the file is
+    # not available offline — flagged "parity unpinned" like every upstream constant)
+    "PixArt-alpha/PixArt-XL-2-1024-MS": dict(num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02,
+                                             beta_schedule="linear", steps_offset=0),
 }
 
 
@@ -63,7 +71,11 @@ class _SchedulerBase:
 
     @classmethod
     def from_pretrained(cls, repo: str = None, subfolder: str = None, revision: str = None, **overrides):
-        cfg = dict(_KNOWN_CONFIGS["default_sd"])
+        """There is no network: `repo` selects one of the scheduler configs of the checkpoints the reference example
+        scripts name; an unknown repo raises instead of silently training on the wrong alphas_cumprod."""
+        if repo not in _KNOWN_CONFIGS:
+            raise ValueError(f"unknown scheduler repo {repo!r}: offline build, known configs: {sorted(_KNOWN_CONFIGS)}")
+        cfg = dict(_KNOWN_CONFIGS[repo])
         cfg.update(overrides)
         return cls(**cfg)
 
@@ -138,8 +150,19 @@ class DPMSolverMultistepScheduler(_SchedulerBase):
 
     order = 1
 
-    def __init__(self, solver_order=2, timestep_spacing="leading", **kw):
+    def __init__(self, solver_order=2, timestep_spacing="leading", add_noise_mode="closed_form", **kw):
+        """add_noise_mode (SURVEY.md §8c decision 1; the reference's diffusers fork is a moving branch, so BOTH readings
+        of `add_noise` for the off-schedule DMD / GAN timesteps (flash_diffusion_model.py:416-428, :524-539) exist):
+          "closed_form"     sqrt(abar_t) x + sqrt(1 - abar_t) eps for any integer t (diffusers < 0.26; default, and what
+                            the model's own `sqrt_alpha_cumprod` / `sigmas` buffers at :110-119 assume);
+          "schedule_index"  diffusers >= 0.27: sigma looked up BY POSITION in the current K-step table
+                            (`index_for_timestep`), a timestep that is not on the table maps to the LAST index."""
         kw.pop("algorithm_type", None)
+        if add_noise_mode not in ("closed_form", "schedule_index"):
+            raise ValueError(f"add_noise_mode={add_noise_mode!r}")
+        if solver_order > 2:
+            raise NotImplementedError("third-order DPM-Solver++ update (no example script configures solver_order=3)")
+        self.add_noise_mode = add_noise_mode
         super().__init__(timestep_spacing=timestep_spacing, solver_order=solver_order, **kw)
         self.model_outputs = [None] * solver_order
         self.lower_order_nums = 0
@@ -162,6 +185,22 @@ class DPMSolverMultistepScheduler(_SchedulerBase):
         self.model_outputs = [None] * self.config.solver_order
         self.lower_order_nums = 0
         self._step_index = None
+
+    def add_noise(self, original_samples, noise, timesteps):
+        if self.add_noise_mode == "closed_form":
+            return super().add_noise(original_samples, noise, timesteps)
+        sched = self.timesteps.tolist()
+        last = len(sched) - 1
+        pos = {}
+        for i, t in enumerate(sched):          # second occurrence wins when a timestep is duplicated (upstream)
+            pos.setdefault(t, []).append(i)
+        idx = [(pos[t][1] if len(pos[t]) > 1 else pos[t][0]) if t in pos else last
+               for t in timesteps.reshape(-1).tolist()]
+        sig = self.sigmas[idx].to(device=original_samples.device, dtype=original_samples.dtype)
+        alpha_t = 1.0 / (sig * sig + 1.0).sqrt()
+        sigma_t = sig * alpha_t
+        shape = (-1,) + (1,) * (original_samples.dim() - 1)
+        return alpha_t.view(shape) * original_samples + sigma_t.view(shape) * noise
 
     @staticmethod
     def _alpha_sigma(sigma: float):
@@ -187,8 +226,9 @@ class DPMSolverMultistepScheduler(_SchedulerBase):
         a_s0, s_s0 = self._alpha_sigma(sig_s0)
         a_t, s_t = self._alpha_sigma(sig_t)
         lam_s0 = math.log(a_s0) - math.log(s_s0)
+        # upstream order selection: `order==1 or lower_order_nums<1 or lower_order_final` -> 1st; `order==2 or ...`
+        # -> 2nd.  `lower_order_second` only demotes a THIRD-order solver, so it plays no role at solver_order 2.
         lower_final = (i == n - 1)
-        lower_second = (i == n - 2) and n < 15
         first_order = self.config.solver_order == 1 or self.lower_order_nums < 1 or lower_final
         if s_t == 0.0:
             expm1_negh, ratio = -1.0, 0.0          # h = +inf
@@ -200,7 +240,7 @@ class DPMSolverMultistepScheduler(_SchedulerBase):
         c_x = ratio
         c_d0 = a_t * expm1_negh
         c_d1r = 0.0
-        if not first_order and not lower_second:
+        if not first_order:
             sig_s1 = float(self.sigmas[i - 1])
             a_s1, s_s1 = self._alpha_sigma(sig_s1)
             lam_s1 = math.log(a_s1) - math.log(s_s1)

@@ -98,7 +98,35 @@ class TrainingPipeline(torch.nn.Module):
         logging.info(f"Number of trainable parameters: {sum(p.numel() for p in self.model.parameters() if p.requires_grad)}")
         self.optims, self._buckets = optimizers, buckets
         self.lr_schedulers = self.configure_lr_schedulers()
+        self.sync_replicas()
         return optimizers
+
+    def sync_replicas(self):
+        """What Lightning's DDP wrap does at construction: every rank starts from rank 0's parameters and buffers
+        (LoRA A and the discriminator are randomly initialised per process, so without this the replicas would apply
+        averaged gradients to different weights forever).  One flat broadcast per dtype/device group."""
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return
+        groups = {}
+        with torch.no_grad():
+            for t in list(self.model.parameters()) + list(self.model.buffers()):
+                groups.setdefault((t.dtype, t.device), []).append(t)
+            # frozen tensors are built from the same seed on every rank; broadcasting them too costs one pass over the
+            # replica at start-up and removes the assumption.  Chunks of <= 256 Mi elements bound the staging buffer.
+            for (dtype, dev), ts in groups.items():
+                chunk, n = [], 0
+                for t in ts + [None]:
+                    if t is not None and (n == 0 or n + t.numel() <= (1 << 28)):
+                        chunk.append(t)
+                        n += t.numel()
+                        continue
+                    flat = torch.cat([c.detach().reshape(-1) for c in chunk])
+                    dist.broadcast(flat, src=0)
+                    off = 0
+                    for c in chunk:
+                        c.copy_(flat[off:off + c.numel()].view_as(c))
+                        off += c.numel()
+                    chunk, n = ([t], t.numel()) if t is not None else ([], 0)
 
     def configure_lr_schedulers(self):
         cfg = self.pipeline_config

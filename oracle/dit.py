@@ -31,8 +31,10 @@ def sincos_1d(embed_dim, pos):
 
 def sincos_2d(embed_dim, grid_size, base_size, interpolation_scale):
     """diffusers get_2d_sincos_pos_embed (w first in the meshgrid, [emb_h | emb_w] concatenation)."""
-    g = np.arange(grid_size, dtype=np.float32) / (grid_size / base_size) / interpolation_scale
-    grid = np.stack(np.meshgrid(g, g), axis=0).reshape(2, 1, grid_size, grid_size)
+    rows, cols = (grid_size, grid_size) if np.isscalar(grid_size) else grid_size
+    ys = np.arange(rows, dtype=np.float32) / (rows / base_size) / interpolation_scale
+    xs = np.arange(cols, dtype=np.float32) / (cols / base_size) / interpolation_scale
+    grid = np.stack(np.meshgrid(xs, ys), axis=0).reshape(2, 1, rows, cols)
     emb_h = sincos_1d(embed_dim // 2, grid[0])
     emb_w = sincos_1d(embed_dim // 2, grid[1])
     return np.concatenate([emb_h, emb_w], axis=1)
@@ -43,11 +45,16 @@ class PatchEmbed(nn.Module):
         super().__init__()
         self.proj = nn.Conv2d(in_channels, embed_dim, patch_size, stride=patch_size)
         grid = sample_size // patch_size
-        pe = sincos_2d(embed_dim, grid, base_size=grid, interpolation_scale=max(sample_size // 64, 1))
+        self.patch, self.grid, self.interp = patch_size, grid, max(sample_size // 64, 1)
+        pe = sincos_2d(embed_dim, grid, base_size=grid, interpolation_scale=self.interp)
         self.register_buffer("pos_embed", torch.from_numpy(pe).float()[None], persistent=False)
 
     def forward(self, x):
+        rows, cols = x.shape[-2] // self.patch, x.shape[-1] // self.patch
         x = self.proj(x).flatten(2).transpose(1, 2)
+        if (rows, cols) != (self.grid, self.grid):      # diffusers PatchEmbed.forward: table recomputed for (h, w)
+            pe = sincos_2d(self.pos_embed.shape[-1], (rows, cols), base_size=self.grid, interpolation_scale=self.interp)
+            return x + torch.from_numpy(pe).float()[None].to(x)
         return x + self.pos_embed.to(x.dtype)
 
 

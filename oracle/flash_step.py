@@ -22,11 +22,17 @@ def predicted_x0(eps, t, x_t, ac):
 
 
 def flash_forward(student, teacher, discriminator, z, cond, uncond, draws, *, K=32, step=0, use_dmd=True,
-                  gan_loss_type="lsgan", distill_type="l2", scales=(1.0, 1.0, 1.0), use_teacher_as_real=False):
+                  gan_loss_type="lsgan", distill_type="l2", scales=(1.0, 1.0, 1.0), use_teacher_as_real=False,
+                  add_noise_mode="closed_form", distill_fn=None):
     """Returns dict(loss_G, loss_D, student_output, teacher_output, distill, dmd, gan_G).
     draws: noise, start_idx, guidance, dmd_noise, dmd_timestep, dmd_guidance, gan_noise, gan_timesteps."""
     ac = S.alphas_cumprod()
     ts = S.trailing_timesteps(K)
+
+    def add_noise(x, eps, t):        # off-schedule DMD / GAN timesteps: both upstream readings (decision (1), §8c)
+        if add_noise_mode == "schedule_index":
+            return S.add_noise_schedule_index(ac, x, eps, t, K)
+        return S.add_noise(ac, x, eps, t)
     B = z.shape[0]
     start_idx = int(draws["start_idx"])
     t0 = torch.full((B,), int(ts[start_idx]), device=z.device, dtype=torch.long)
@@ -46,12 +52,15 @@ def flash_forward(student, teacher, discriminator, z, cond, uncond, draws, *, K=
         teacher_output = S.dpm_rollout(eps_fn, x_t.detach().clone(), ac, K, start_idx)
     student_output = c_skip * x_t + c_out * x0_s
     diff = student_output - teacher_output
-    distill = (diff ** 2 if distill_type == "l2" else diff.abs()).reshape(B, -1).mean(1).mean()
+    if distill_fn is not None:          # e.g. the lpips branch (oracle/lpips.py), reference :383-397
+        distill = distill_fn(student_output, teacher_output)
+    else:
+        distill = (diff ** 2 if distill_type == "l2" else diff.abs()).reshape(B, -1).mean(1).mean()
     loss = distill * scales[0]
     dmd = torch.zeros((), device=z.device)
     if use_dmd:
         td = draws["dmd_timestep"].long()
-        noisy_s = S.add_noise(ac, student_output, draws["dmd_noise"], td)
+        noisy_s = add_noise(student_output, draws["dmd_noise"], td)
         with torch.no_grad():
             wd = float(draws["dmd_guidance"])
             real = wd * teacher(noisy_s, td.float(), cond) + (1 - wd) * teacher(noisy_s, td.float(), uncond)
@@ -65,7 +74,7 @@ def flash_forward(student, teacher, discriminator, z, cond, uncond, draws, *, K=
     tg = draws["gan_timesteps"].long()
     real_x = teacher_output if use_teacher_as_real else z
     fake_x = student_output if step % 2 == 0 else student_output.detach()
-    noisy = torch.cat([S.add_noise(ac, fake_x, draws["gan_noise"], tg), S.add_noise(ac, real_x, draws["gan_noise"], tg)])
+    noisy = torch.cat([add_noise(fake_x, draws["gan_noise"], tg), add_noise(real_x, draws["gan_noise"], tg)])
     cond2 = {"cond": {k: torch.cat([v, v]) for k, v in cond["cond"].items()}}
     feats = teacher(noisy, torch.cat([tg, tg]).float(), cond2, return_intermediate=True)
     f_fake, f_real = feats.chunk(2)

@@ -31,6 +31,19 @@ def add_noise(ac, x, eps, t):
     return a.sqrt().view(shape) * x + (1 - a).sqrt().view(shape) * eps
 
 
+def add_noise_schedule_index(ac, x, eps, t, K):
+    """diffusers >= 0.27 `DPMSolverMultistepScheduler.add_noise` (the other reading of decision (1)):
+    sigma taken BY POSITION in the current K-step trailing table; a timestep that is not on the table maps to the last
+    position.  On-table timesteps give exactly the closed form."""
+    ts = trailing_timesteps(K).tolist()
+    sig_hat = np.sqrt((1 - ac[ts]) / ac[ts])
+    idx = [ts.index(int(v)) if int(v) in ts else len(ts) - 1 for v in t.reshape(-1).tolist()]
+    s = torch.as_tensor(sig_hat[idx], dtype=x.dtype, device=x.device)
+    alpha_t = 1.0 / (s * s + 1.0).sqrt()
+    shape = (-1,) + (1,) * (x.dim() - 1)
+    return alpha_t.view(shape) * x + (s * alpha_t).view(shape) * eps
+
+
 def dpm_rollout(eps_fn, x, ac, K, start_idx):
     """x_{K} from x at timesteps[start_idx] with DPM-Solver++(2M); eps_fn(x, t_int) -> eps.
     First step of the rollout and the final step are first order (Appendix B.2)."""
@@ -52,7 +65,9 @@ def dpm_rollout(eps_fn, x, ac, K, start_idx):
             h = lam[i + 1] - lam[i]
             em = math.expm1(-h)
             x_next = (sigma[i + 1] / sigma[i]) * x - alpha[i + 1] * em * x0
-            second = x0_prev is not None and not (i == K - 2 and K < 15)
+            # order 2 (2M): second order whenever a previous x0 exists; upstream's `lower_order_second` (K < 15)
+            # only demotes a third-order solver
+            second = x0_prev is not None
             if second:
                 r = (lam[i] - lam[i - 1]) / h
                 x_next = x_next - 0.5 * alpha[i + 1] * em * (x0 - x0_prev) / r

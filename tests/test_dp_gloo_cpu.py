@@ -34,12 +34,14 @@ def _slice(d, lo, hi):
     return {k: (v[lo:hi] if torch.is_tensor(v) and v.dim() > 0 and v.shape[0] >= hi else v) for k, v in d.items()}
 
 
-def _worker(rank, world, port, out_dir):
+def _worker(rank, world, port, out_dir, seed_per_rank=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     torch.set_num_threads(2)
-    model, pipe = _build()
+    # seed_per_rank: every process initialises LoRA A / the discriminator differently, as real launches do; the
+    # start-up broadcast in TrainingPipeline.sync_replicas (Lightning DDP's wrap-time sync) must make them rank 0's
+    model, pipe = _build(seed=100 * rank if seed_per_rank else 0)
     batch, draws = _data(4, 5)
     b = _slice(batch, 2 * rank, 2 * rank + 2)
     d = _slice(draws, 2 * rank, 2 * rank + 2)
@@ -50,10 +52,14 @@ def _worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_two_ranks_equal_one_rank_double_batch(tmp_path):
+import pytest
+
+
+@pytest.mark.parametrize("seed_per_rank", [False, True])
+def test_two_ranks_equal_one_rank_double_batch(tmp_path, seed_per_rank):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    port = 29500 + os.getpid() % 500
-    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    port = 29500 + (os.getpid() + 7 * int(seed_per_rank)) % 500
+    mp.spawn(_worker, args=(2, port, str(tmp_path), seed_per_rank), nprocs=2, join=True)
     dp = torch.load(os.path.join(tmp_path, "dp.pt"))
     torch.set_num_threads(4)
     model, pipe = _build()

@@ -56,12 +56,12 @@ def _model(gan="lsgan", K=4, dmd=True, seed=0, disc=True):
     cfg = FlashDiffusionSD3Config(K=[K], num_iterations_per_K=[100], guidance_scale_min=7.0, guidance_scale_max=13.0,
                                   distill_loss_type="l2", use_dmd_loss=dmd, gan_loss_type=gan,
                                   timestep_distribution="mixture", mixture_num_components=2, mixture_var=0.5)
-    mk = lambda cls: cls.from_pretrained("x", subfolder="scheduler", timestep_spacing="trailing")
+    mk = lambda cls: cls.from_pretrained("stabilityai/stable-diffusion-3-medium", subfolder="scheduler", timestep_spacing="trailing")
     torch.manual_seed(seed + 1)
     return FlashDiffusionSD3(cfg, student_denoiser=student, teacher_denoiser=teacher,
                              teacher_noise_scheduler=mk(FlowMatchEulerDiscreteScheduler),
                              sampling_noise_scheduler=mk(FlashFlowMatchEulerDiscreteScheduler),
-                             teacher_sampling_noise_scheduler=FlowMatchEulerDiscreteScheduler.from_pretrained("x"),
+                             teacher_sampling_noise_scheduler=FlowMatchEulerDiscreteScheduler.from_pretrained("stabilityai/stable-diffusion-3-medium"),
                              discriminator=_disc() if disc else None)
 
 
@@ -74,7 +74,7 @@ def _draws(B=2, hw=8, seed=3, start_idx=1):
 
 
 def test_flow_match_grids_match_oracle():
-    s = FlowMatchEulerDiscreteScheduler.from_pretrained("x", timestep_spacing="trailing")
+    s = FlowMatchEulerDiscreteScheduler.from_pretrained("stabilityai/stable-diffusion-3-medium", timestep_spacing="trailing")
     ts, sig = O3.training_grid()
     assert torch.equal(s.timesteps, ts) and torch.equal(s.sigmas, sig)
     assert s.timesteps[0] == 1000.0 and abs(float(s.sigmas[-1]) - 3 / 1002) < 1e-6       # shift 3 at s = 1/1000
@@ -83,7 +83,7 @@ def test_flow_match_grids_match_oracle():
         ts, sig = O3.inference_grid(K)
         assert torch.equal(s.timesteps, ts) and torch.equal(s.sigmas, sig)
         assert len(s.timesteps) == K and s.sigmas[-1] == 0 and s.timesteps[0] == 1000.0
-    up = FlowMatchEulerDiscreteScheduler.from_pretrained("x")                               # upstream spacing
+    up = FlowMatchEulerDiscreteScheduler.from_pretrained("stabilityai/stable-diffusion-3-medium")                               # upstream spacing
     up.set_timesteps(4)
     ts, sig = O3.inference_grid(4, spacing="linspace")
     assert torch.equal(up.timesteps, ts) and torch.equal(up.sigmas, sig)
@@ -91,7 +91,7 @@ def test_flow_match_grids_match_oracle():
 
 def test_euler_rollout_integrates_a_straight_flow_exactly():
     """For the straight flow x_t = (1-s) x0 + s e the velocity is e - x0 everywhere: Euler from any level lands on x0."""
-    s = FlowMatchEulerDiscreteScheduler.from_pretrained("x", timestep_spacing="trailing")
+    s = FlowMatchEulerDiscreteScheduler.from_pretrained("stabilityai/stable-diffusion-3-medium", timestep_spacing="trailing")
     s.set_timesteps(8)
     x0, e = torch.randn(2, 4, 8, 8), torch.randn(2, 4, 8, 8)
     x = float(s.sigmas[3]) * e + (1 - float(s.sigmas[3])) * x0
@@ -104,7 +104,7 @@ def test_euler_rollout_integrates_a_straight_flow_exactly():
 
 
 def test_flash_sampler_renoises_to_the_next_level():
-    s = FlashFlowMatchEulerDiscreteScheduler.from_pretrained("x", timestep_spacing="trailing")
+    s = FlashFlowMatchEulerDiscreteScheduler.from_pretrained("stabilityai/stable-diffusion-3-medium", timestep_spacing="trailing")
     s.set_timesteps(4)
     x0, e = torch.randn(1, 4, 8, 8), torch.randn(1, 4, 8, 8)
     t = s.timesteps[1]

@@ -61,9 +61,9 @@ def _model(gan="lsgan", K=4, dmd=True, seed=0):
                                distill_loss_type="l2", ucg_keys=["text_emb", "pooled_emb"], use_dmd_loss=dmd,
                                gan_loss_type=gan, timestep_distribution="mixture", mixture_num_components=2,
                                mixture_var=0.5, switch_teacher=False, allow_full_noise=False)
-    sched = DPMSolverMultistepScheduler.from_pretrained("x", subfolder="scheduler", timestep_spacing="trailing")
+    sched = DPMSolverMultistepScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", subfolder="scheduler", timestep_spacing="trailing")
     model = FlashDiffusion(cfg, student_denoiser=student, teacher_denoiser=teacher, teacher_noise_scheduler=sched,
-                           sampling_noise_scheduler=LCMScheduler.from_pretrained("x", timestep_spacing="trailing"),
+                           sampling_noise_scheduler=LCMScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", timestep_spacing="trailing"),
                            vae=None, conditioner=_conditioner(), discriminator=disc)
     return model
 
@@ -85,7 +85,7 @@ def test_conditioner_wrapper_ucg_semantics():
 
 
 def test_dpm_scheduler_matches_oracle_rollout():
-    sched = DPMSolverMultistepScheduler.from_pretrained("x", timestep_spacing="trailing")
+    sched = DPMSolverMultistepScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", timestep_spacing="trailing")
     sched.set_timesteps(32)
     assert sched.timesteps.tolist() == OS.trailing_timesteps(32).tolist()
     assert sched.timesteps[0] == 999 and sched.timesteps[-1] == 30
@@ -108,7 +108,7 @@ def test_dpm_scheduler_matches_oracle_rollout():
 
 
 def test_lcm_scheduler_timesteps_and_scalings():
-    lcm = LCMScheduler.from_pretrained("x")
+    lcm = LCMScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0")
     lcm.set_timesteps(4)
     assert lcm.timesteps.tolist() == [999, 759, 499, 259] == OS.lcm_timesteps(4).tolist()
     cs, co = lcm.scalings(500)
@@ -218,7 +218,7 @@ def test_log_samples_keys_and_sample_cap():
     """reference flash_diffusion_model.py:917-1019: one entry per num_steps (plus the teacher's when asked), N capped by
     max_samples and by the shortest conditioning entry; input_shape is mandatory without a VAE."""
     model = _model()
-    model.teacher_sampling_noise_scheduler = DPMSolverMultistepScheduler.from_pretrained("x", timestep_spacing="trailing")
+    model.teacher_sampling_noise_scheduler = DPMSolverMultistepScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", timestep_spacing="trailing")
     b = _batch(B=2)
     logs = model.log_samples(dict(b), input_shape=(4, 16, 16), num_steps=[1, 2], max_samples=8, guidance_scale=1.0,
                              teacher_guidance_scale=3.0, log_teacher_samples=True)
@@ -230,3 +230,87 @@ def test_log_samples_keys_and_sample_cap():
     assert list(one.values())[0].shape[0] == 1
     with pytest.raises(ValueError, match="input_shape"):
         model.log_samples(dict(b), num_steps=1)
+
+
+# ------------------------------------------------------------------------------------------ round-2 additions
+def test_scheduler_configs_are_keyed_by_repo():
+    """`from_pretrained` must not hand the SD config to every repo."""
+    sd = DPMSolverMultistepScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", timestep_spacing="trailing")
+    px = DPMSolverMultistepScheduler.from_pretrained("PixArt-alpha/PixArt-XL-2-1024-MS", timestep_spacing="trailing")
+    assert sd.config.beta_schedule == "scaled_linear" and abs(float(sd.betas[0]) - 0.00085) < 1e-7
+    assert px.config.beta_schedule == "linear" and abs(float(px.betas[0]) - 1e-4) < 1e-8 and abs(float(px.betas[-1]) - 0.02) < 1e-7
+    assert px.config.steps_offset == 0 and sd.config.steps_offset == 1
+    assert not torch.allclose(sd.alphas_cumprod, px.alphas_cumprod)
+    with pytest.raises(ValueError, match="unknown scheduler repo"):
+        DPMSolverMultistepScheduler.from_pretrained("somebody/some-model")
+
+
+def test_dpm_second_order_at_penultimate_step_for_short_schedules():
+    """with solver_order 2 upstream takes the 2M step at index n-2 also when n < 15 (`lower_order_second`
+    only demotes a third-order solver)."""
+    s = DPMSolverMultistepScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", timestep_spacing="trailing")
+    s.set_timesteps(4)
+    coefs = [s.step_coefficients(t) for t in s.timesteps]
+    assert coefs[0][4] == 0.0            # first step: no history
+    assert coefs[1][4] != 0.0
+    assert coefs[2][4] != 0.0            # index n-2 with n = 4 < 15: still second order
+    assert coefs[3][4] == 0.0            # final step: first order (final_sigmas_type="zero")
+
+
+@pytest.mark.parametrize("mode", ["closed_form", "schedule_index"])
+def test_add_noise_modes_match_oracle(mode):
+    """SURVEY §8c decision (1), both readings: off-schedule DMD/GAN timesteps either use the closed form or (diffusers
+    >= 0.27) the sigma at the LAST position of the current K-step table."""
+    K = 32
+    s = DPMSolverMultistepScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", timestep_spacing="trailing",
+                                                    add_noise_mode=mode)
+    s.set_timesteps(K)
+    ac = OS.alphas_cumprod()
+    g = torch.Generator().manual_seed(1)
+    x, e = torch.randn(5, 4, 8, 8, generator=g), torch.randn(5, 4, 8, 8, generator=g)
+    t = torch.tensor([999, 30, 500, 10, 968])         # 999 / 30 / 968 are on the trailing table, 500 / 10 are not
+    got = s.add_noise(x, e, t)
+    ref = OS.add_noise(ac, x, e, t) if mode == "closed_form" else OS.add_noise_schedule_index(ac, x, e, t, K)
+    assert torch.allclose(got, ref, rtol=1e-5, atol=1e-6)
+    closed = OS.add_noise(ac, x, e, t)
+    on_table = [0, 1, 4]
+    assert torch.allclose(got[on_table], closed[on_table], rtol=1e-5, atol=1e-6)     # identical on the table
+    if mode == "schedule_index":
+        last = OS.add_noise(ac, x, e, torch.full((5,), 30))
+        assert torch.allclose(got[[2, 3]], last[[2, 3]], rtol=1e-5, atol=1e-6)      # misses -> last index (t = 30)
+        assert not torch.allclose(got[[2, 3]], closed[[2, 3]], atol=1e-3)
+
+
+@pytest.mark.parametrize("step", [0, 1])
+def test_forward_matches_oracle_step_schedule_index_mode(step):
+    model = _model()
+    model.teacher_noise_scheduler = DPMSolverMultistepScheduler.from_pretrained(
+        "stabilityai/stable-diffusion-xl-base-1.0", timestep_spacing="trailing", add_noise_mode="schedule_index")
+    b, d = _batch(), _draws()
+    out = model(b, step=step, draws=d)
+    cw = model.conditioner
+    cond, uncond = cw(b, set_ucg_rate_zero=True), cw(b, ucg_keys=["text_emb", "pooled_emb"])
+    ref = OF.flash_forward(model.student_denoiser, model.teacher_denoiser, model.discriminator, b["image"], cond,
+                           uncond, d, K=4, step=step, add_noise_mode="schedule_index")
+    ref_closed = OF.flash_forward(model.student_denoiser, model.teacher_denoiser, model.discriminator, b["image"], cond,
+                                  uncond, d, K=4, step=step)
+    assert torch.allclose(out["loss"][0], ref["loss_G"], rtol=1e-4, atol=1e-6)
+    assert not torch.allclose(ref["loss_G"], ref_closed["loss_G"], rtol=1e-4)       # the two readings do differ
+    if step == 1:
+        assert torch.allclose(out["loss"][1], ref["loss_D"], rtol=1e-4, atol=1e-6)
+
+
+def test_pixart_position_table_is_recomputed_for_other_grids():
+    """diffusers' PatchEmbed recomputes the 2-D sincos table for (h, w) != configured grid."""
+    from flash.models.transformers.transformers import PatchEmbed
+    from oracle.dit import PatchEmbed as OraclePatchEmbed
+    pe = PatchEmbed(sample_size=32, patch_size=2, in_channels=4, embed_dim=16)
+    ope = OraclePatchEmbed(sample_size=32, patch_size=2, in_channels=4, embed_dim=16)
+    assert torch.equal(pe.table(16, 16), pe.pos_embed[0])
+    t = pe.table(8, 12)
+    assert t.shape == (96, 16) and not torch.allclose(t, pe.pos_embed[0, :96])
+    with torch.no_grad():
+        for p in ope.parameters():
+            p.zero_()
+        got = ope(torch.zeros(1, 4, 16, 24))[0]        # zero conv -> the table itself
+    assert torch.allclose(got, t, atol=1e-6)

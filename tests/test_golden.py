@@ -32,7 +32,7 @@ def test_oracle_unet_matches_golden():
 
 def test_host_schedulers_match_golden():
     from flash.schedulers import DPMSolverMultistepScheduler, LCMScheduler
-    s = DPMSolverMultistepScheduler.from_pretrained("x", timestep_spacing="trailing")
+    s = DPMSolverMultistepScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", timestep_spacing="trailing")
     s.set_timesteps(32)
     assert torch.equal(s.timesteps, SCHED_GOLD["timesteps_K32"])
     ac = s.alphas_cumprod.double()
@@ -48,7 +48,7 @@ def test_host_schedulers_match_golden():
             eps = torch.tanh(torch.einsum("ij,bjhw->bihw", W, x)) * (1 + int(t) / 1000.0)
             x = s.step(eps, t, x)[0]
         assert torch.allclose(x, ref, rtol=1e-4, atol=1e-5), key
-    lcm = LCMScheduler.from_pretrained("x")
+    lcm = LCMScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0")
     lcm.set_timesteps(4)
     assert torch.equal(lcm.timesteps, SCHED_GOLD["lcm_timesteps_4"])
 
@@ -77,7 +77,7 @@ def test_oracle_dits_and_flow_grids_match_golden():
         assert _rel(G.gold_pixart()(*G.gold_dit_inputs(4, 32, 20, 64, 24, True)), DIT_GOLD["pixart_out"]) < 1e-4
         assert _rel(G.gold_sd3()(*G.gold_dit_inputs(16, 16, 9, 48, 40, False)), DIT_GOLD["sd3_out"]) < 1e-4
     from flash.schedulers import FlowMatchEulerDiscreteScheduler
-    s = FlowMatchEulerDiscreteScheduler.from_pretrained("x", timestep_spacing="trailing")
+    s = FlowMatchEulerDiscreteScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", timestep_spacing="trailing")
     g = DIT_GOLD["flow_grids"]["train_0_499_999"]
     idx = torch.tensor([0, 499, 999])
     assert torch.equal(s.timesteps[idx], g["timesteps"]) and torch.equal(s.sigmas[idx], g["sigmas"])
