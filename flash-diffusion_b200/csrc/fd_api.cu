@@ -39,6 +39,11 @@ static EncodeTiledFn get_encode_fn() {
 
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box) {
+    return encode_tmap_bf16_sw(map, base, rank, dims, strides_bytes, box, 128);
+}
+
+int encode_tmap_bf16_sw(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
     // cuTensorMapEncodeTiled is a DRIVER call: it needs the primary context current on this thread.
     // A thread that has not yet issued a runtime call that binds it (e.g. a PyTorch autograd worker
     // entering our backward first) would get CUDA_ERROR_INVALID_CONTEXT, so bind it once per thread.
@@ -75,7 +80,10 @@ int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_
     }
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
                     gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                    : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                    : swizzle_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)",

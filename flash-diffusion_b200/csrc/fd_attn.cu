@@ -18,6 +18,8 @@
 //
 // UPSTREAM math: diffusers Attention + AttnProcessor2_0 -> F.scaled_dot_product_attention
 // (SURVEY.md §2.2); reference call path src/flash/models/unets/unet.py:108-119.
+#include <stdlib.h>
+
 #include "fd_common.cuh"
 #include "fd_host.h"
 
@@ -117,6 +119,13 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 // final O / l is invariant to the reference maximum).
 constexpr float ATT_RESCALE_THRESHOLD = 8.0f;
 
+// POLY: a share of the exponentials runs on the FMA pipe (cubic, relative error < 7e-4, always an UNDER-estimate).
+// That is fine for an inference-only forward, but when the log-sum-exp is kept for a backward the row sum l must be
+// the sum of the very probabilities the backward recomputes (ex2.approx of S - LSE): with the polynomial share the
+// recomputed row sums were off by ~1e-4, which is multiplied by the COMMON-MODE of dP and of the keys in
+// dQ = sum_j dS_j K_j and showed up as cos 0.979 (instead of 0.998) on the q/k LoRA gradients of deep, near-uniform
+// attention blocks at SDXL size (tests/test_sdxl_parity_gpu.py).  So the training forward (lse != NULL) is all-MUFU.
+template <bool POLY>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnKParams p) {
@@ -328,7 +337,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 for (int i = 0; i < 32; i += 2) {
                     const float2 x = ffma2(make_float2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), sc2, nm2);
                     float2 e;
-                    if (FD_ATTN_POLY_MOD > 0 && ((i >> 1) % (FD_ATTN_POLY_MOD > 0 ? FD_ATTN_POLY_MOD : 1)) == 1)
+                    if (POLY && FD_ATTN_POLY_MOD > 0 && ((i >> 1) % (FD_ATTN_POLY_MOD > 0 ? FD_ATTN_POLY_MOD : 1)) == 1)
                         e = exp2_poly2(x);
                     else
                         e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
@@ -417,6 +426,251 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
 }
 
+// ------------------------------------------------------------------------------------------ 2 CTAs / SM variant
+// One 128-query tile per CTA (10 warps, <= 96 registers, 82 KB shared memory, 256 TMEM columns) so that TWO CTAs are
+// resident per SM.  The two resident CTAs play the role of the two ping-ponged tiles of attn_fwd_kernel — while one
+// is in its softmax the other's MMAs run — and, unlike there, the prologue (barrier init, TMEM allocation, first
+// Q/K/V loads: ~3 us) and the epilogue (last P V, normalise, store, teardown, next block launch: ~3 us) of one CTA
+// overlap the main loop of its neighbour.  At 1024 keys (8 key tiles; 60 of SDXL's 70 attention blocks) those 6.3 us
+// were a third of a CTA's life (r01: 444 TFLOP/s at 1024 keys vs 665 at 4096).  Work items are half as large, so
+// the last partial wave is also half as long.  K/V tiles are staged per CTA (2-stage ring): twice the L2 -> smem
+// operand traffic of the shared ring, 64 B/clk/SM, still inside the budget.
+// TMEM: S [0,128)  O [128,192)  P [192,256) (bf16 pairs; A operand of O += P V read from TMEM).
+constexpr int ATT1_STAGES = 2;
+constexpr int ATT1_THREADS = 64 + 256;        // TMA warp, MMA warp, 2 column halves x 4 softmax warps
+constexpr int ATT1_SMEM = ATT_TILE_BYTES + 2 * ATT1_STAGES * ATT_TILE_BYTES + 256 + 2048 + 1024;
+
+template <bool POLY>
+__global__ void __launch_bounds__(ATT1_THREADS, 2)
+attn_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttnKParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + ATT_TILE_BYTES;
+    uint8_t* sV = sK + ATT1_STAGES * ATT_TILE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT1_STAGES * ATT_TILE_BYTES);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;                  // [ATT1_STAGES]
+    uint64_t* kv_empty = kv_full + ATT1_STAGES;    // [ATT1_STAGES]
+    uint64_t* s_full = kv_empty + ATT1_STAGES;     // S(j) written by the tensor core
+    uint64_t* s_free = s_full + 1;                 // S(j) copied to registers: S(j+1) may be issued
+    uint64_t* p_ready = s_free + 1;                // P(j) in TMEM
+    uint64_t* pv_done = p_ready + 1;               // O += P(j) V(j) complete
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(pv_done + 1);
+    float* mx_buf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [parity][half][128]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int q_blk = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
+    const int n_kv_tiles = (p.Nkv + ATT_BN - 1) / ATT_BN;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+    }
+    if (warp == 1 && lane == 0) {
+        mbar_init(q_full, 1);
+        for (int s = 0; s < ATT1_STAGES; ++s) {
+            mbar_init(&kv_full[s], 1);
+            mbar_init(&kv_empty[s], 1);
+        }
+        mbar_init(s_full, 1);
+        mbar_init(s_free, 256);
+        mbar_init(p_ready, 256);
+        mbar_init(pv_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(tmem_holder, 256);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
+            tma_load_3d(&tmQ, q_full, sQ, head * ATT_D, q_blk * 128, batch);
+            int st = 0;
+            uint32_t ph = 0;
+            for (int j = 0; j < n_kv_tiles; ++j) {
+                mbar_wait(&kv_empty[st], ph ^ 1u);
+                mbar_arrive_expect_tx(&kv_full[st], 2 * ATT_TILE_BYTES);
+                tma_load_3d(&tmK, &kv_full[st], sK + st * ATT_TILE_BYTES, head * ATT_D, j * ATT_BN, batch);
+                tma_load_3d(&tmV, &kv_full[st], sV + st * ATT_TILE_BYTES, head * ATT_D, j * ATT_BN, batch);
+                if (++st == ATT1_STAGES) {
+                    st = 0;
+                    ph ^= 1u;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_qk = make_idesc_bf16(128, ATT_BN, 0, 0);
+            constexpr uint32_t idesc_pv = make_idesc_bf16(128, ATT_D, 0, 1);  // B (=V) MN-major
+            const uint32_t q_addr = smem_u32(sQ);
+            auto issue_s = [&](int st) {
+                const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < ATT_D / 16; ++k)
+                    tc_mma_bf16(tmem_base, make_desc_k_sw128(q_addr + k * 32), make_desc_k_sw128(k_addr + k * 32),
+                                idesc_qk, k != 0 ? 1u : 0u);
+                tc_commit(s_full);
+            };
+            mbar_wait(q_full, 0);
+            mbar_wait(&kv_full[0], 0);
+            tc_fence_after();
+            issue_s(0);
+            for (int j = 0; j < n_kv_tiles; ++j) {
+                if (j + 1 < n_kv_tiles) {
+                    // S(j+1) as soon as S(j) sits in the softmax warps' registers and K(j+1) has landed
+                    mbar_wait(s_free, j & 1);
+                    const int stn = (j + 1) % ATT1_STAGES;
+                    mbar_wait(&kv_full[stn], ((j + 1) / ATT1_STAGES) & 1);
+                    tc_fence_after();
+                    issue_s(stn);
+                }
+                mbar_wait(p_ready, j & 1);
+                tc_fence_after();
+                const uint32_t v_addr = smem_u32(sV + (j % ATT1_STAGES) * ATT_TILE_BYTES);
+#pragma unroll
+                for (int k = 0; k < ATT_BN / 16; ++k)
+                    tc_mma_bf16_ts(tmem_base + 128, tmem_base + 192 + k * 8,
+                                   make_desc_mn_sw128(v_addr + k * 2048, 0, 1024), idesc_pv, (j | k) != 0 ? 1u : 0u);
+                tc_commit(pv_done);
+                tc_commit(&kv_empty[j % ATT1_STAGES]);
+            }
+        }
+    } else {
+        // 8 softmax warps: column half h (0/1) x TMEM lane quarter (= warp % 4); a thread owns 64 of its row's 128
+        // scores, the halves exchange their row maximum through shared memory once per key tile.
+        const int h = (warp - 2) >> 2;
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+        const uint32_t tmem_S = tmem_base + h * 64;
+        const uint32_t tmem_O = tmem_base + 128 + h * 32;
+        float m_used = -INFINITY, l_run = 0.f;
+        for (int j = 0; j < n_kv_tiles; ++j) {
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            const int kv_valid = min(ATT_BN, p.Nkv - j * ATT_BN) - h * 64;
+            uint32_t sr[2][32];
+            tmem_ld_32x32(tmem_S + lane_base, sr[0]);
+            tmem_ld_32x32(tmem_S + lane_base + 32, sr[1]);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(s_free);
+            if (kv_valid < 64) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c * 32 + i >= kv_valid) sr[c][i] = 0xff800000u;
+            }
+            float mxs[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int i = 0; i < 32; i += 2)
+                    mxs[c] = max3(mxs[c], __uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1]));
+            float mx = fmaxf(mxs[0], mxs[1]);
+            float* slot = mx_buf + (j & 1) * 256;
+            slot[h * 128 + row] = mx;
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mx = fmaxf(mx, slot[(h ^ 1) * 128 + row]);
+            const float m_new = mx * p.scale_log2;
+            const bool grow = m_new > m_used + ATT_RESCALE_THRESHOLD;
+            const float alpha = (grow && j > 0) ? fast_exp2(m_used - m_new) : 1.0f;
+            if (grow) m_used = m_new;
+            l_run *= alpha;
+            const float2 sc2 = make_float2(p.scale_log2, p.scale_log2);
+            const float2 nm2 = make_float2(-m_used, -m_used);
+            float2 ps2 = make_float2(0.f, 0.f);
+            uint32_t pk[2][16];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    const float2 x = ffma2(make_float2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), sc2, nm2);
+                    float2 e;
+                    if (POLY && FD_ATTN_POLY_MOD > 0 && ((i >> 1) % (FD_ATTN_POLY_MOD > 0 ? FD_ATTN_POLY_MOD : 1)) == 1)
+                        e = exp2_poly2(x);
+                    else
+                        e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
+                    ps2 = fadd2(ps2, e);
+                    pk[c][i >> 1] = pack_bf16x2(e.x, e.y);
+                }
+            }
+            l_run += ps2.x + ps2.y;
+            if (j > 0) {
+                mbar_wait(pv_done, (j - 1) & 1);
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, alpha != 1.0f)) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(tmem_O + lane_base, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                    tmem_st_32x32(tmem_O + lane_base, r);
+                    tmem_st_wait();
+                }
+            }
+            {
+                uint32_t pflat[32];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    pflat[i] = pk[0][i];
+                    pflat[16 + i] = pk[1][i];
+                }
+                tmem_st_32x32(tmem_base + 192 + h * 32 + lane_base, pflat);
+                tmem_st_wait();
+            }
+            tc_fence_before();
+            mbar_arrive(p_ready);
+        }
+        float* slot = mx_buf + (n_kv_tiles & 1) * 256;
+        slot[h * 128 + row] = l_run;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        l_run += slot[(h ^ 1) * 128 + row];
+        mbar_wait(pv_done, (n_kv_tiles - 1) & 1);
+        tc_fence_after();
+        const int q_row = q_blk * 128 + row;
+        const float inv_l = 1.f / l_run;
+        bf16* orow = p.o + (long long)batch * p.o_batch_stride + (long long)q_row * p.ldo + head * ATT_D + h * 32;
+        {
+            uint32_t r[32];
+            tmem_ld_32x32(tmem_O + lane_base, r);
+            tmem_ld_wait();
+            if (q_row < p.Nq) {
+#pragma unroll
+                for (int q4 = 0; q4 < 4; ++q4) {
+                    uint4 u;
+                    u.x = pack_bf16x2(__uint_as_float(r[8 * q4 + 0]) * inv_l, __uint_as_float(r[8 * q4 + 1]) * inv_l);
+                    u.y = pack_bf16x2(__uint_as_float(r[8 * q4 + 2]) * inv_l, __uint_as_float(r[8 * q4 + 3]) * inv_l);
+                    u.z = pack_bf16x2(__uint_as_float(r[8 * q4 + 4]) * inv_l, __uint_as_float(r[8 * q4 + 5]) * inv_l);
+                    u.w = pack_bf16x2(__uint_as_float(r[8 * q4 + 6]) * inv_l, __uint_as_float(r[8 * q4 + 7]) * inv_l);
+                    *reinterpret_cast<uint4*>(orow + q4 * 8) = u;
+                }
+            }
+        }
+        if (h == 0 && p.lse != nullptr && q_row < p.Nq)
+            p.lse[((long long)batch * p.H + head) * p.Nq + q_row] = (m_used + log2f(l_run)) * 0.69314718055994531f;
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 256);
+    }
+}
+
 static int make_qkv_tmap(CUtensorMap* m, const void* base, int H, int N, int B, int64_t ld,
                          int64_t batch_stride) {
     const uint64_t dims[3] = {(uint64_t)H * ATT_D, (uint64_t)N, (uint64_t)B};
@@ -450,12 +704,29 @@ extern "C" int fd_attn_fwd(const FdAttnArgs* a, void* stream_) {
     p.H = a->H;
     static bool attr_set = false;
     if (!attr_set) {
-        FD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        FD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        FD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        FD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT1_SMEM));
+        FD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT1_SMEM));
         attr_set = true;
     }
-    dim3 grid((a->Nq + ATT_BM - 1) / ATT_BM, a->H, a->B);
     ProfScope prof(stream, PROF_ATTN_FWD, 4.0 * (double)a->B * a->H * (double)a->Nq * (double)a->Nkv * ATT_D);
-    attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tq, tk, tv, p);
+    // FD_ATTN_V=2: the two-tiles-per-CTA kernel (1 CTA / SM); default: one tile per CTA, two CTAs per SM
+    static const int variant = getenv("FD_ATTN_V") ? atoi(getenv("FD_ATTN_V")) : 1;
+    if (variant == 1) {
+        dim3 grid((a->Nq + 127) / 128, a->H, a->B);
+        if (a->lse != nullptr)
+            attn_fwd1_kernel<false><<<grid, ATT1_THREADS, ATT1_SMEM, stream>>>(tq, tk, tv, p);
+        else
+            attn_fwd1_kernel<true><<<grid, ATT1_THREADS, ATT1_SMEM, stream>>>(tq, tk, tv, p);
+        FD_CHECK_LAUNCH();
+        return 0;
+    }
+    dim3 grid((a->Nq + ATT_BM - 1) / ATT_BM, a->H, a->B);
+    if (a->lse != nullptr)
+        attn_fwd_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tq, tk, tv, p);
+    else
+        attn_fwd_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tq, tk, tv, p);
     FD_CHECK_LAUNCH();
     return 0;
 }

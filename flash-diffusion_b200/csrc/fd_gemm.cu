@@ -46,6 +46,15 @@ struct GemmKParams {
     const float* rowscale;
     int rows_per_group_scale;
     long long ldrs;
+    // stream-K (pair kernel): the k-block units of all tiles are dealt evenly to the CTA pairs; a tile cut between two
+    // (or more) pairs is summed through `sk_ws` (fp32 partial accumulators, one slot per CTA) guarded by `sk_flags`.
+    int sk;               // 1: hybrid stream-K (tiles >= sk_first are cut along K between pairs)
+    int sk_first;         // first tile of the stream-K region (a multiple of the pair count)
+    float* sk_ws;
+    int* sk_flags;
+    int tail_first;       // sk == 0: tiles >= tail_first (the last, partial wave) are cut into tail_split column slices
+    int tail_split;
+    int tma_out;          // 1: bf16 output leaves through shared memory + TMA store (cp.async.bulk.tensor ... global)
 };
 
 template <int BN>
@@ -101,14 +110,32 @@ __device__ __forceinline__ void stats_of_bf16x2(uint32_t u, RowState& rs) {
     rs.s2 += f.x * f.x + f.y * f.y;
 }
 
-__device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int row, int col0,
-                                               uint32_t (&r)[32], RowState& rs) {
-    // r holds acc[row, col0 .. col0+31] as fp32 bit patterns
+// erf-GELU for the GEGLU epilogue: erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far below the bf16 output
+// rounding) — two MUFU ops (rcp, ex2) and ~12 FMA-pipe ops instead of erff()'s ~30-instruction branchy expansion.
+// The GEGLU GEMMs (8192x10240x1280, 32768x5120x640: 21 % of a teacher evaluation) evaluate it 128 times per thread
+// per tile, which made their epilogue as long as the K = 640 main loop.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    poly *= t;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
+    const float erf_abs = fmaf(-poly, e, 1.0f);                 // erf(|x|/sqrt2)
+    return 0.5f * fmaf(fabsf(x), erf_abs, x);                   // 0.5 x (1 + sign(x) erf(|x|/sqrt2))
+}
+
+// Epilogue stage 1: r = acc[row, col0 .. col0+31] (fp32 bit patterns) -> v = final fp32 outputs (LayerNorm fold, bias,
+// row vector, activation, gate, GEGLU, residual).  With GEGLU the 16 outputs are v[0..15] (output column col0/2 + j).
+// Every lane of the warp runs it (rows >= M compute on zero accumulators and read nothing).
+__device__ __forceinline__ void epilogue_values(const GemmKParams& p, int row, int col0, const uint32_t (&r)[32],
+                                                const RowState& rs, float (&v)[32]) {
     const bool row_ok = row < p.M;
     const int N = p.N;
-    if (col0 >= N) return;
     const bool full = (col0 + 32 <= N);
-    float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 
@@ -131,7 +158,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int row, in
                 if (col0 + j < N) v[j] = rs.ln_rstd * fmaf(nm, __ldg(p.ln_colsum + col0 + j), v[j]);
         }
     }
-
     if (p.bias != nullptr) {
         if (full) {
             const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
@@ -167,8 +193,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int row, in
                 if (col0 + j < N) v[j] += __ldg(rv + j);
         }
     }
-    if (!row_ok) return;
-
     if (p.act == 1) {   // gelu (tanh approximation): 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3)))
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -177,54 +201,41 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int row, in
             v[j] = 0.5f * x * (1.0f + tanhf(u));
         }
     }
-    if (p.rowscale != nullptr) {
+    if (p.rowscale != nullptr && row_ok) {
         const float* sv = p.rowscale + (long long)(row / p.rows_per_group_scale) * p.ldrs + col0;
 #pragma unroll
         for (int j = 0; j < 32; ++j)
             if (col0 + j < N) v[j] *= __ldg(sv + j);
     }
-
     if (p.geglu) {
-        // interleaved packing: cols [0,16) value, [16,32) gate -> 16 outputs at col0/2
+        // interleaved packing: cols [0,16) value, [16,32) gate -> 16 outputs at col0/2  (N % 32 == 0: always full)
         const int oc0 = col0 >> 1;
-        float o[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) o[j] = v[j] * gelu_erf(v[16 + j]);
-        if (p.residual != nullptr) {
-            const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + (long long)row * p.ldr + oc0);
+        for (int j = 0; j < 16; ++j) v[j] = v[j] * gelu_erf_fast(v[16 + j]);
+        if (p.residual != nullptr && row_ok) {
+            const bf16* rp = p.residual + (long long)row * p.ldr + oc0;
+            if ((p.ldr & 7) == 0) {
+                const uint4* r4 = reinterpret_cast<const uint4*>(rp);
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                uint4 u = __ldg(r4 + j);
-                float2 f;
-                f = unpack_bf16x2(u.x); o[8 * j + 0] += f.x; o[8 * j + 1] += f.y;
-                f = unpack_bf16x2(u.y); o[8 * j + 2] += f.x; o[8 * j + 3] += f.y;
-                f = unpack_bf16x2(u.z); o[8 * j + 4] += f.x; o[8 * j + 5] += f.y;
-                f = unpack_bf16x2(u.w); o[8 * j + 6] += f.x; o[8 * j + 7] += f.y;
-            }
-        }
-        if (p.out_fp32) {
-            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + oc0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o4[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-        } else {
-            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + oc0);
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const uint4 u = make_uint4(pack_bf16x2(o[8 * j], o[8 * j + 1]), pack_bf16x2(o[8 * j + 2], o[8 * j + 3]),
-                                           pack_bf16x2(o[8 * j + 4], o[8 * j + 5]), pack_bf16x2(o[8 * j + 6], o[8 * j + 7]));
-                o4[j] = u;
-                if (p.rowstats_out != nullptr) {
-                    stats_of_bf16x2(u.x, rs); stats_of_bf16x2(u.y, rs); stats_of_bf16x2(u.z, rs); stats_of_bf16x2(u.w, rs);
+                for (int j = 0; j < 2; ++j) {
+                    uint4 u = __ldg(r4 + j);
+                    float2 f;
+                    f = unpack_bf16x2(u.x); v[8 * j + 0] += f.x; v[8 * j + 1] += f.y;
+                    f = unpack_bf16x2(u.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
+                    f = unpack_bf16x2(u.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
+                    f = unpack_bf16x2(u.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
                 }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += __bfloat162float(rp[j]);
             }
         }
         return;
     }
-
-    const bool vec_ok = full && ((p.ldo & 7) == 0) && (p.residual == nullptr || (p.ldr & 7) == 0);
-    if (vec_ok) {
-        if (p.residual != nullptr) {
-            const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + (long long)row * p.ldr + col0);
+    if (p.residual != nullptr && row_ok) {
+        const bf16* rp = p.residual + (long long)row * p.ldr + col0;
+        if (full && (p.ldr & 7) == 0) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(rp);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 uint4 u = __ldg(r4 + j);
@@ -234,39 +245,83 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int row, in
                 f = unpack_bf16x2(u.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
                 f = unpack_bf16x2(u.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
             }
-        }
-        if (p.out_fp32) {
-            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + col0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         } else {
-            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + col0);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const uint4 u = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                           pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-                o4[j] = u;
-                if (p.rowstats_out != nullptr) {
-                    stats_of_bf16x2(u.x, rs); stats_of_bf16x2(u.y, rs); stats_of_bf16x2(u.z, rs); stats_of_bf16x2(u.w, rs);
-                }
+            for (int j = 0; j < 32; ++j)
+                if (col0 + j < N) v[j] += __bfloat162float(rp[j]);
+        }
+    }
+}
+
+// Epilogue stage 2 (bf16 outputs): round to bf16 pairs, accumulate the row statistics of the ROUNDED values (what
+// the next LayerNorm-folded GEMM will read), columns >= n_out count as zero.  nout = 32 (16 with GEGLU).
+template <int NOUT>
+__device__ __forceinline__ void epilogue_pack(const GemmKParams& p, bool row_ok, int oc0, int n_out, float (&v)[32],
+                                              uint32_t (&pk)[16], RowState& rs) {
+    if (oc0 + NOUT > n_out) {
+#pragma unroll
+        for (int j = 0; j < NOUT; ++j)
+            if (oc0 + j >= n_out) v[j] = 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < NOUT / 2; ++j) pk[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+    if (p.rowstats_out != nullptr && row_ok) {
+#pragma unroll
+        for (int j = 0; j < NOUT / 2; ++j) stats_of_bf16x2(pk[j], rs);
+    }
+}
+
+// Direct (register -> global) store of one chunk; used by the single-CTA kernel and whenever the output is fp32 or
+// its row stride is not a TMA-legal multiple of 16 bytes.
+__device__ __forceinline__ void epilogue_chunk(const GemmKParams& p, int row, int col0, const uint32_t (&r)[32],
+                                               RowState& rs) {
+    if (col0 >= p.N) return;
+    float v[32];
+    epilogue_values(p, row, col0, r, rs, v);
+    if (row >= p.M) return;
+    const int n_out = p.geglu ? (p.N >> 1) : p.N;
+    const int oc0 = p.geglu ? (col0 >> 1) : col0;
+    const int nout = p.geglu ? 16 : 32;
+    const bool full = oc0 + nout <= n_out;
+    if (p.out_fp32) {
+        float* orow = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + oc0;
+        if (full && (p.ldo & 3) == 0) {
+            float4* o4 = reinterpret_cast<float4*>(orow);
+            if (p.geglu) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (j < nout && oc0 + j < n_out) orow[j] = v[j];
+        }
+        return;
+    }
+    uint32_t pk[16];
+    if (p.geglu)
+        epilogue_pack<16>(p, true, oc0, n_out, v, pk, rs);
+    else
+        epilogue_pack<32>(p, true, oc0, n_out, v, pk, rs);
+    bf16* orow = reinterpret_cast<bf16*>(p.out) + (long long)row * p.ldo + oc0;
+    if (full && (p.ldo & 7) == 0) {
+        uint4* o4 = reinterpret_cast<uint4*>(orow);
+        o4[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        o4[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        if (!p.geglu) {
+            o4[2] = make_uint4(pk[8], pk[9], pk[10], pk[11]);
+            o4[3] = make_uint4(pk[12], pk[13], pk[14], pk[15]);
         }
     } else {
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-            if (col0 + j < N) {
-                float x = v[j];
-                if (p.residual != nullptr)
-                    x += __bfloat162float(p.residual[(long long)row * p.ldr + col0 + j]);
-                if (p.out_fp32)
-                    reinterpret_cast<float*>(p.out)[(long long)row * p.ldo + col0 + j] = x;
-                else {
-                    const bf16 xb = __float2bfloat16(x);
-                    reinterpret_cast<bf16*>(p.out)[(long long)row * p.ldo + col0 + j] = xb;
-                    const float xf = __bfloat162float(xb);
-                    rs.s1 += xf;
-                    rs.s2 += xf * xf;
-                }
+            if (j < nout && oc0 + j < n_out) {
+                const uint32_t w = pk[j >> 1];
+                const unsigned short h = (j & 1) ? (unsigned short)(w >> 16) : (unsigned short)(w & 0xffffu);
+                reinterpret_cast<unsigned short*>(orow)[j] = h;
             }
         }
     }
@@ -447,20 +502,115 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CU
 // (and L2->SM operand traffic) is half that of the single-CTA 128 x BN tile: 64 B/clk read + 64 B/clk TMA fill
 // at BN = 256 instead of 96 + 96.  The leader CTA (rank 0) issues every MMA; both CTAs run a TMA producer and an
 // epilogue for their own 128 accumulator rows (TMEM lanes).
+//
+// STREAM-K.  The work of a launch is U = tiles x k-blocks units, dealt evenly and CONTIGUOUSLY to the P pairs: pair p
+// owns units [p U / P, (p+1) U / P) — the tail of one tile, whole tiles, the head of another.  160 tiles on 74 pairs
+// (8192 x 1280 x K) therefore cost 2.16 tile-times instead of 3 waves.  A segment that does not start at k-block 0
+// is a PARTIAL: it is always the first thing its pair does, its raw fp32 accumulators go to the pair's workspace slot
+// and a flag is released.  The segment that starts at k-block 0 FINISHES the tile: it is the last thing ITS pair does
+// for that tile, so by then the partials of the following pair(s) have long been written; it acquires their flags,
+// adds their slots and runs the normal epilogue.  All CTAs are co-resident (grid <= SM count, 1 CTA / SM), so the
+// flag wait cannot dead-lock.  Flags are reset by the reader: the workspace stays all-zero between launches.
+//
+// EPILOGUE.  bf16 outputs leave through shared memory and the TMA store unit: every epilogue warp owns two 2 KB
+// staging buffers (32 rows x 64 B, 64-byte swizzle = conflict-free 16-byte stores), writes a 32 x 32 chunk, fences
+// the async proxy and one lane issues cp.async.bulk.tensor.2d.global.shared::cta; the tensor map clips rows >= M and
+// columns >= N, so ragged edges need no predicates.  fp32 outputs / non-TMA-legal strides use direct stores.
 template <int BN>
 struct PairCfg {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int BH_BYTES = (BN / 2) * BK * 2;
     static constexpr int STAGES = (BN == 256) ? 6 : (BN == 160 ? 7 : 8);
     static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;   // power of two >= 2 accumulator stages
-    static constexpr int SMEM_BYTES = STAGES * (A_BYTES + BH_BYTES) + 256 + 1024;
+    static constexpr int OUT_STAGE_BYTES = 8 * 2 * 2048;            // 8 epilogue warps x 2 buffers x (32 rows x 64 B)
+    static constexpr int SMEM_BYTES = STAGES * (A_BYTES + BH_BYTES) + OUT_STAGE_BYTES + 256 + 1024;
+};
+
+__device__ __forceinline__ void tma_store_2d(const void* tmap, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(tmap), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // 8 epilogue warps
+
+// first stream-K unit (k-block of the stream-K region) of pair q
+__device__ __forceinline__ long long sk_begin(long long total_units, int num_pairs, int q) {
+    return (total_units * q) / num_pairs;
+}
+
+// The sequence of work items of one CTA pair, identical in the producer, the MMA issuer and the epilogue warps:
+//   * whole tiles dealt round-robin (item i of pair p is tile p + i P: the P pairs work on P CONSECUTIVE tiles of the
+//     L2-friendly raster at any moment);
+//   * sk == 0: the tiles of the last, partial wave are cut into `tail_split` column slices (sub, nsub) so that the
+//     tail occupies ~all pairs for 1/nsub of a tile time instead of a few pairs for a whole one;
+//   * sk == 1: the tiles from sk_first on are a stream-K region: its k-blocks are dealt evenly and contiguously, pair
+//     p owning [p U / P, (p+1) U / P) — the tail of one tile, maybe a whole tile, the head of the next.
+struct WorkIter {
+    int pair_id, num_pairs, total_tiles, kb_total;
+    int sk, sk_first, tail_first, tail_split;
+    int i;
+    long long u, u_end, sk_units;
+    int tile, kb0, kb1, sub, nsub;
+    __device__ __forceinline__ void init(const GemmKParams& p, int pair_id_, int num_pairs_, int total_tiles_,
+                                         int kb_total_) {
+        pair_id = pair_id_; num_pairs = num_pairs_; total_tiles = total_tiles_; kb_total = kb_total_;
+        sk = p.sk; sk_first = p.sk_first; tail_first = p.tail_first; tail_split = p.tail_split;
+        i = 0;
+        sk_units = sk ? (long long)(total_tiles - sk_first) * kb_total : 0;
+        u = sk ? sk_begin(sk_units, num_pairs, pair_id) : 0;
+        u_end = sk ? sk_begin(sk_units, num_pairs, pair_id + 1) : 0;
+    }
+    __device__ __forceinline__ bool next() {
+        const int item = pair_id + i * num_pairs;
+        if (!sk) {
+            const int n_items = tail_first + (total_tiles - tail_first) * tail_split;
+            if (item >= n_items) return false;
+            ++i;
+            if (item < tail_first) {
+                tile = item; sub = 0; nsub = 1;
+            } else {
+                const int t = item - tail_first;
+                tile = tail_first + t / tail_split; sub = t % tail_split; nsub = tail_split;
+            }
+            kb0 = 0; kb1 = kb_total;
+            return true;
+        }
+        if (item < sk_first) {
+            ++i;
+            tile = item; sub = 0; nsub = 1; kb0 = 0; kb1 = kb_total;
+            return true;
+        }
+        if (u >= u_end) return false;
+        const int t = (int)(u / kb_total);
+        kb0 = (int)(u - (long long)t * kb_total);
+        kb1 = (int)min((long long)kb_total, kb0 + (u_end - u));
+        u += kb1 - kb0;
+        tile = sk_first + t; sub = 0; nsub = 1;
+        return true;
+    }
 };
 
 template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
-                 const GemmKParams p) {
+                 const __grid_constant__ CUtensorMap tmB1s, const __grid_constant__ CUtensorMap tmB2s,
+                 const __grid_constant__ CUtensorMap tmOut, const GemmKParams p) {
     using Cfg = PairCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -468,7 +618,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sB + STAGES * Cfg::BH_BYTES);
+    uint8_t* sOut = sB + STAGES * Cfg::BH_BYTES;                       // 1024-byte aligned (stage sizes are)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + Cfg::OUT_STAGE_BYTES);
     uint64_t* full = bars;               // used in the leader CTA only
     uint64_t* empty = bars + STAGES;     // per CTA
     uint64_t* tfull = bars + 2 * STAGES; // per CTA
@@ -487,6 +638,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
             tma_prefetch_desc(&tmA2);
             tma_prefetch_desc(&tmB2);
         }
+        if (p.tma_out) tma_prefetch_desc(&tmOut);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -517,14 +669,17 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     const int num_pairs = gridDim.x >> 1;
     GemmKParams pp = p;
     pp.num_m_tiles = num_m2;             // tile_coords works on pair tiles
+    WorkIter wi;
+    wi.init(p, pair_id, num_pairs, total_tiles, kb_total);
 
     if (warp == 0) {
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
+            while (wi.next()) {
+                const int kb0 = wi.kb0, kb1 = wi.kb1;
                 int mt2, nt;
-                tile_coords(pp, tile, mt2, nt);
+                tile_coords(pp, wi.tile, mt2, nt);
                 const int row0 = mt2 * 2 * BM + (int)rank * BM;
                 int n0 = 0, h0 = 0, w0 = 0;
                 if (p.conv_taps) {
@@ -534,12 +689,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
                     h0 = rem / p.W;
                     w0 = rem - h0 * p.W;
                 }
-                const int brow = nt * BN + (int)rank * (BN / 2);
-                for (int kb = 0; kb < kb_total; ++kb) {
+                // column slice `sub` of `nsub`: this CTA stages (BN / nsub) / 2 rows of B through the slice tensor maps
+                const int n_ext = BN / wi.nsub;
+                const int brow = nt * BN + wi.sub * n_ext + (int)rank * (n_ext / 2);
+                const bool sliced = wi.nsub > 1;
+                const CUtensorMap* mB1 = sliced ? &tmB1s : &tmB1;
+                const CUtensorMap* mB2 = sliced ? &tmB2s : &tmB2;
+                const uint32_t tx_bytes = 2u * (uint32_t)(Cfg::A_BYTES + Cfg::BH_BYTES / wi.nsub);
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty[stage], phase ^ 1u);
                     const uint32_t full_leader = mapa_u32(smem_u32(&full[stage]), 0);
                     if (leader)
-                        mbar_arrive_expect_tx(&full[stage], 2 * (Cfg::A_BYTES + Cfg::BH_BYTES));
+                        mbar_arrive_expect_tx(&full[stage], tx_bytes);
                     else
                         mbar_arrive_cluster(full_leader);
                     uint8_t* a_dst = sA + stage * Cfg::A_BYTES;
@@ -553,11 +714,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
                         } else {
                             tma_load_2d_pair(&tmA1, full_leader, a_dst, kb * BK, row0);
                         }
-                        tma_load_2d_pair(&tmB1, full_leader, b_dst, kb * BK, brow);
+                        tma_load_2d_pair(mB1, full_leader, b_dst, kb * BK, brow);
                     } else {
                         const int k2 = kb - p.kb1;
                         tma_load_2d_pair(&tmA2, full_leader, a_dst, k2 * BK, row0);
-                        tma_load_2d_pair(&tmB2, full_leader, b_dst, k2 * BK, brow);
+                        tma_load_2d_pair(mB2, full_leader, b_dst, k2 * BK, brow);
                     }
                     if (++stage == STAGES) {
                         stage = 0;
@@ -568,16 +729,17 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         }
     } else if (warp == 1) {
         if (leader && lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
+            while (wi.next()) {
+                const int kb0 = wi.kb0, kb1 = wi.kb1;
+                const uint32_t idesc = make_idesc_bf16(2 * BM, BN / wi.nsub);
                 mbar_wait(&tempty[acc], acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-                for (int kb = 0; kb < kb_total; ++kb) {
+                for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
@@ -585,7 +747,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k)
                         tc_mma_bf16_pair(d_tmem, make_desc_k_sw128(a_addr + k * 32),
-                                         make_desc_k_sw128(b_addr + k * 32), idesc, (kb | k) != 0 ? 1u : 0u);
+                                         make_desc_k_sw128(b_addr + k * 32), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     tc_commit_pair(&empty[stage]);
                     if (++stage == STAGES) {
                         stage = 0;
@@ -598,28 +760,129 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
             }
         }
     } else if (warp >= 4) {
-        const int q = (warp - 4) & 3;
-        const int half = (warp - 4) >> 2;
+        const int ew = warp - 4;          // epilogue warp 0..7
+        const int q = ew & 3;             // TMEM lane quarter == warp_id % 4
+        const int half = ew >> 2;         // which half of the tile's 32-column chunks this warp drains
+        constexpr int NCH = BN / 32;
+        uint8_t* my_stage = sOut + ew * 4096;
+        uint32_t n_stored = 0;            // TMA stores issued by this warp (buffer = n_stored & 1)
+        const int n_out = p.geglu ? (p.N >> 1) : p.N;
+        float* ws_mine = p.sk_ws + ((size_t)pair_id * 2 + rank) * (size_t)(BM * BN);
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = pair_id; tile < total_tiles; tile += num_pairs) {
+        while (wi.next()) {
+            const int tile = wi.tile, kb0 = wi.kb0, kb1 = wi.kb1;
             int mt2, nt;
             tile_coords(pp, tile, mt2, nt);
+            // a column slice has BN / nsub columns; its 32-column chunks are split between the two warp halves
+            const int nch = NCH / wi.nsub, split = (nch + 1) / 2;
+            const int c_lo = half ? split : 0, c_hi = half ? nch : split;
+            const int col_base = nt * BN + wi.sub * (BN / wi.nsub);
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
-            const int row = mt2 * 2 * BM + (int)rank * BM + q * 32 + lane;
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
-            RowState rs;
-            row_state_init(p, row, rs);
-            constexpr int NCH = BN / 32, SPLIT = (NCH + 1) / 2;
+            if (kb0 != 0) {
+                // PARTIAL segment: raw accumulators -> this CTA's workspace slot ([chunk][quarter][reg][lane]: every
+                // warp-wide store / later load is one contiguous 128-byte line), then release the flag.
 #pragma unroll 1
-            for (int c = half ? SPLIT : 0; c < (half ? NCH : SPLIT); ++c) {
-                uint32_t r[32];
-                tmem_ld_32x32(t_addr + c * 32, r);
-                tmem_ld_wait();
-                epilogue_chunk(p, row, nt * BN + c * 32, r, rs);
+                for (int c = c_lo; c < c_hi; ++c) {
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_addr + c * 32, r);
+                    tmem_ld_wait();
+                    float* dst = ws_mine + ((size_t)(c * 4 + q) * 32) * 32 + lane;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) __stcg(dst + j * 32, __uint_as_float(r[j]));
+                }
+                __threadfence();
+                epi_bar_sync();
+                if (ew == 0 && lane == 0) st_release_gpu(p.sk_flags + pair_id * 2 + rank, 1);
+            } else {
+                // FINISHER (or a whole tile).  Partials of this tile live in the slots of the following pairs.
+                int n_part = 0;
+                if (kb1 < kb_total) {
+                    const long long tile_end = (long long)(tile - wi.sk_first + 1) * kb_total;
+                    while (pair_id + 1 + n_part < num_pairs &&
+                           sk_begin(wi.sk_units, num_pairs, pair_id + 1 + n_part) < tile_end)
+                        ++n_part;
+                    if (ew == 0 && lane == 0) {
+                        for (int i = 0; i < n_part; ++i) {
+                            int* f = p.sk_flags + (pair_id + 1 + i) * 2 + rank;
+                            uint32_t spins = 0;
+                            while (ld_acquire_gpu(f) == 0) {
+                                if (++spins > FD_SPIN_LIMIT) {
+                                    printf("fd: stream-K flag timeout pair %d waits for %d\n", pair_id, pair_id + 1 + i);
+                                    __trap();
+                                }
+                            }
+                            *f = 0;       // reader resets: the workspace is all-zero again when the launch ends
+                        }
+                    }
+                    epi_bar_sync();
+                }
+                const int row = mt2 * 2 * BM + (int)rank * BM + q * 32 + lane;
+                const bool row_ok = row < p.M;
+                RowState rs;
+                row_state_init(p, row, rs);
+#pragma unroll 1
+                for (int c = c_lo; c < c_hi; ++c) {
+                    const int col0 = col_base + c * 32;
+                    if (col0 >= p.N) break;                       // warp-uniform
+                    uint32_t r[32];
+                    tmem_ld_32x32(t_addr + c * 32, r);
+                    tmem_ld_wait();
+                    for (int i = 0; i < n_part; ++i) {
+                        const float* src = p.sk_ws + ((size_t)(pair_id + 1 + i) * 2 + rank) * (size_t)(BM * BN) +
+                                           ((size_t)(c * 4 + q) * 32) * 32 + lane;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldcg(src + j * 32));
+                    }
+                    if (!p.tma_out) {
+                        epilogue_chunk(p, row, col0, r, rs);
+                        continue;
+                    }
+                    float v[32];
+                    epilogue_values(p, row, col0, r, rs, v);
+                    uint32_t pk[16];
+                    uint8_t* buf = my_stage + (n_stored & 1u) * 2048;
+                    if (n_stored >= 2) {                          // the store issued from this buffer has read it
+                        if (lane == 0) tma_store_wait_read<1>();
+                        __syncwarp();
+                    }
+                    if (p.geglu) {
+                        const int oc0 = col0 >> 1;
+                        epilogue_pack<16>(p, row_ok, oc0, n_out, v, pk, rs);
+                        // 32 rows x 32 B, 32-byte swizzle: 16-byte chunk index ^= bit 7 of the address = (row >> 2) & 1
+                        uint8_t* dst = buf + lane * 32;
+                        const int sw = (lane >> 2) & 1;
+                        *reinterpret_cast<uint4*>(dst + ((0 ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        *reinterpret_cast<uint4*>(dst + ((1 ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmOut, buf, oc0, row - lane);
+                            tma_store_commit();
+                        }
+                    } else {
+                        epilogue_pack<32>(p, row_ok, col0, n_out, v, pk, rs);
+                        // 32 rows x 64 B, 64-byte swizzle: chunk index ^= address bits [7,9) = (row >> 1) & 3
+                        uint8_t* dst = buf + lane * 64;
+                        const int sw = (lane >> 1) & 3;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<uint4*>(dst + ((j ^ sw) << 4)) =
+                                make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                        fence_proxy_async();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_2d(&tmOut, buf, col0, row - lane);
+                            tma_store_commit();
+                        }
+                    }
+                    ++n_stored;
+                }
+                row_state_flush(p, row, rs);
             }
-            row_state_flush(p, row, rs);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -631,6 +894,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
+        if (lane == 0) tma_store_wait_all();     // shared memory must outlive the bulk stores that read it
     }
 
     tc_fence_before();
@@ -643,10 +907,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
 
 // ------------------------------------------------------------------------------------------ host
 
-// Tile configuration: BN in {64,128,256} single-CTA (128-row tiles) or {128,256} CTA-pair (256-row tiles,
+// Tile configuration: BN in {64,128,256} single-CTA (128-row tiles) or {128,160,256} CTA-pair (256-row tiles,
 // returned as 512 + BN).  Cost = waves x (tile rows x BN) / efficiency, efficiencies from the smem-traffic
-// model calibrated on B200.
-static int choose_bn(int M, int N, int force) {
+// model calibrated on B200.  With a stream-K workspace the pair kernels pay FRACTIONAL waves.
+static int choose_bn(int M, int N, int force, bool streamk) {
+    force &= 1023;      // bits 1024 / 2048 of force_bn select the work split (see fd_gemm), not the tile
     if (force == 64 || force == 128 || force == 256 || force == 512 + 128 || force == 512 + 160 ||
         force == 512 + 256)
         return force;
@@ -661,8 +926,11 @@ static int choose_bn(int M, int N, int force) {
         const Cand& c = cands[i];
         const long long tiles = (long long)((M + c.rows - 1) / c.rows) * ((N + c.bn - 1) / c.bn);
         const int units = c.rows == 256 ? sms / 2 : sms;
-        const long long waves = (tiles + units - 1) / units;
-        const double cost = (double)waves * c.rows * c.bn / c.eff / (c.rows == 256 ? 2.0 : 1.0);
+        double waves = (double)((tiles + units - 1) / units);
+        (void)streamk;
+        if (c.rows == 256 && tiles > units && tiles % units != 0 && (tiles % units) * 2 <= units)
+            waves -= 0.5;                         // the partial wave runs as column slices (~half a tile time)
+        const double cost = waves * c.rows * c.bn / c.eff / (c.rows == 256 ? 2.0 : 1.0);
         if (cost < best_cost - 1e-9) {
             best_cost = cost;
             best = c.code;
@@ -685,7 +953,8 @@ static bool use_pdl() {
 
 template <int BN>
 static int launch_gemm_pair(const CUtensorMap& tA1, const CUtensorMap& tB1, const CUtensorMap& tA2,
-                            const CUtensorMap& tB2, const GemmKParams& p, cudaStream_t stream, bool pdl) {
+                            const CUtensorMap& tB2, const CUtensorMap& tB1s, const CUtensorMap& tB2s,
+                            const CUtensorMap& tOut, const GemmKParams& p, int pairs, cudaStream_t stream, bool pdl) {
     using Cfg = PairCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -693,9 +962,6 @@ static int launch_gemm_pair(const CUtensorMap& tA1, const CUtensorMap& tB1, cons
                                            Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    const int total = ((p.M + 2 * BM - 1) / (2 * BM)) * p.num_n_tiles;
-    int pairs = num_sms() / 2;
-    if (total < pairs) pairs = total;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3(2 * pairs);
@@ -711,7 +977,7 @@ static int launch_gemm_pair(const CUtensorMap& tA1, const CUtensorMap& tB1, cons
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 2 : 1;
-    FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<BN>, tA1, tB1, tA2, tB2, p));
+    FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<BN>, tA1, tB1, tA2, tB2, tB1s, tB2s, tOut, p));
     FD_CHECK_LAUNCH();
     return 0;
 }
@@ -746,6 +1012,11 @@ static int launch_gemm(const CUtensorMap& tA1, const CUtensorMap& tB1, const CUt
 
 }  // namespace fd
 
+extern "C" size_t fd_gemm_workspace_bytes(void) {
+    // 4 KB of flags + one 128 x 256 fp32 partial-accumulator slot per CTA of the persistent pair grid
+    return 4096 + (size_t)fd::num_sms() * (size_t)(fd::BM * 256) * sizeof(float);
+}
+
 extern "C" int fd_gemm(const FdGemmArgs* a, void* stream_) {
     using namespace fd;
     cudaStream_t stream = (cudaStream_t)stream_;
@@ -758,7 +1029,12 @@ extern "C" int fd_gemm(const FdGemmArgs* a, void* stream_) {
     FD_CHECK_ARG(!a->geglu || (a->N % 32 == 0), "fd_gemm: geglu needs N %% 32 == 0");
     FD_CHECK_ARG(!a->rowvec || a->rows_per_group > 0, "fd_gemm: rowvec needs rows_per_group");
 
-    const int code = choose_bn(a->M, a->N, a->force_bn);
+    // stream-K needs the caller's workspace (fd_gemm_workspace_bytes) and 16-byte alignment of it
+    static const bool env_no_sk = getenv("FD_NO_STREAMK") != nullptr;
+    static const bool env_no_tma_store = getenv("FD_NO_TMA_STORE") != nullptr;
+    const bool ws_ok = a->workspace != nullptr && a->workspace_bytes >= (long long)fd_gemm_workspace_bytes() &&
+                       ((uintptr_t)a->workspace & 15) == 0 && !env_no_sk;
+    const int code = choose_bn(a->M, a->N, a->force_bn, ws_ok);
     const bool pair = code >= 512;
     const int BN = pair ? code - 512 : code;
     const uint32_t b_box_rows = pair ? BN / 2 : BN;
@@ -865,6 +1141,70 @@ extern "C" int fd_gemm(const FdGemmArgs* a, void* stream_) {
         tA2 = tA1;
         tB2 = tB1;
     }
+    // pair kernel: work split (tail column slices or hybrid stream-K) and TMA-store epilogue
+    CUtensorMap tOut = tA1, tB1s = tB1, tB2s = tB2;
+    int pairs = 0;
+    if (pair) {
+        const int tiles = ((a->M + 2 * BM - 1) / (2 * BM)) * p.num_n_tiles;
+        const int kb_total = p.kb1 + p.kb2;
+        const int max_pairs = num_sms() / 2;
+        pairs = tiles < max_pairs ? tiles : max_pairs;
+        p.tail_first = tiles;
+        p.tail_split = 1;
+        const int rem = tiles % max_pairs;               // tiles of the last, partial wave
+        static const int env_tail = getenv("FD_TAIL_SPLIT") ? atoi(getenv("FD_TAIL_SPLIT")) : -1;   // 0 = off
+        static const int env_sk_min_ = getenv("FD_SK_MIN") ? atoi(getenv("FD_SK_MIN")) : 24;
+        // force_bn | 1024: stream-K whenever it is legal (tests); force_bn | 2048: whole tiles only, no slices
+        const int env_sk_min = (a->force_bn & 1024) ? 0 : env_sk_min_;
+        const bool plain = (a->force_bn & 2048) != 0;
+        // (1) hybrid stream-K pays for its partial-tile exchange (~4 us on the kernel's tail) only when the idle part of
+        //     the last wave is long: (1 - rem/P) tile-times of kb_total k-blocks each, in units of BN = 256 k-blocks
+        if (!plain && ws_ok && tiles > max_pairs && rem != 0 && kb_total >= 8 &&
+            (double)(max_pairs - rem) / max_pairs * kb_total * BN / 256.0 >= (double)env_sk_min) {
+            p.sk = 1;
+            p.sk_first = (tiles / max_pairs - 1) * max_pairs;      // last full wave + the partial wave are streamed
+            p.sk_flags = reinterpret_cast<int*>(a->workspace);
+            p.sk_ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a->workspace) + 4096);
+        } else if (!plain && rem != 0 && env_tail != 0) {
+            // (2) otherwise cut the tiles of the partial wave into column slices (multiples of 32 columns) while they
+            //     still fit one wave: the tail then lasts ~1/split of a tile time
+            int split = 1;
+            for (int sp = 2; sp <= 4; sp *= 2)
+                if (BN % (32 * sp) == 0 && (long long)rem * sp <= max_pairs) split = sp;
+            if (env_tail > 0 && BN % (32 * env_tail) == 0 && (long long)rem * env_tail <= max_pairs) split = env_tail;
+            if (split > 1) {
+                p.tail_first = tiles - rem;
+                p.tail_split = split;
+                if (tiles < max_pairs) pairs = rem * split;
+                const uint32_t rows = (uint32_t)(BN / split / 2);
+                {
+                    const uint64_t dims[2] = {(uint64_t)a->K1, (uint64_t)a->N};
+                    const uint64_t str[1] = {(uint64_t)a->ldb1 * 2};
+                    const uint32_t box[2] = {(uint32_t)BK, rows};
+                    rc = encode_tmap_bf16(&tB1s, a->b1, 2, dims, str, box);
+                    if (rc) return rc;
+                }
+                if (a->K2 > 0) {
+                    const uint64_t dims[2] = {(uint64_t)a->K2, (uint64_t)a->N};
+                    const uint64_t str[1] = {(uint64_t)a->ldb2 * 2};
+                    const uint32_t box[2] = {(uint32_t)BK, rows};
+                    rc = encode_tmap_bf16(&tB2s, a->b2, 2, dims, str, box);
+                    if (rc) return rc;
+                } else {
+                    tB2s = tB1s;
+                }
+            }
+        }
+        const int n_out = a->geglu ? a->N / 2 : a->N;
+        if (!a->out_fp32 && !env_no_tma_store && (a->ldo % 8) == 0 && ((uintptr_t)a->out & 15) == 0) {
+            const uint64_t dims[2] = {(uint64_t)n_out, (uint64_t)a->M};
+            const uint64_t str[1] = {(uint64_t)a->ldo * 2};
+            const uint32_t box[2] = {a->geglu ? 16u : 32u, 32u};
+            rc = encode_tmap_bf16_sw(&tOut, a->out, 2, dims, str, box, a->geglu ? 32 : 64);
+            if (rc) return rc;
+            p.tma_out = 1;
+        }
+    }
     ProfScope prof(stream, a->conv_taps > 0 ? PROF_CONV : PROF_GEMM,
                    2.0 * (double)a->M * (double)a->N *
                        ((a->conv_taps > 0 ? (double)a->conv_taps * a->C : (double)a->K1) + (double)a->K2),
@@ -872,9 +1212,9 @@ extern "C" int fd_gemm(const FdGemmArgs* a, void* stream_) {
     // the programmatic edge needs a KERNEL as the previous stream operation: not after the row-statistics memset
     const bool pdl = use_pdl() && a->rowstats_out == nullptr && !profiling_on();
     if (pair) {
-        if (BN == 256) return launch_gemm_pair<256>(tA1, tB1, tA2, tB2, p, stream, pdl);
-        if (BN == 160) return launch_gemm_pair<160>(tA1, tB1, tA2, tB2, p, stream, pdl);
-        return launch_gemm_pair<128>(tA1, tB1, tA2, tB2, p, stream, pdl);
+        if (BN == 256) return launch_gemm_pair<256>(tA1, tB1, tA2, tB2, tB1s, tB2s, tOut, p, pairs, stream, pdl);
+        if (BN == 160) return launch_gemm_pair<160>(tA1, tB1, tA2, tB2, tB1s, tB2s, tOut, p, pairs, stream, pdl);
+        return launch_gemm_pair<128>(tA1, tB1, tA2, tB2, tB1s, tB2s, tOut, p, pairs, stream, pdl);
     }
     if (BN == 256) return launch_gemm<256>(tA1, tB1, tA2, tB2, p, stream, pdl);
     if (BN == 128) return launch_gemm<128>(tA1, tB1, tA2, tB2, p, stream, pdl);

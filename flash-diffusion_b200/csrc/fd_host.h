@@ -46,6 +46,11 @@ void set_error(const char* fmt, ...);
 int encode_tmap_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                      const uint64_t* strides_bytes, const uint32_t* box);
 
+// same with an explicit swizzle span in bytes (32 / 64 / 128; 0 = none) — the TMA-store epilogue stages 32- and
+// 64-byte rows
+int encode_tmap_bf16_sw(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                        const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
+
 int num_sms();
 
 // launch accounting (fd_launch_count) and optional per-launch CUDA-event profiling (fd_profile_*)

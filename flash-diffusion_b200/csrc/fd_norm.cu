@@ -54,7 +54,30 @@ __global__ void gn_reduce_kernel(const bf16* __restrict__ x, const bf16* __restr
     }
     const int r_begin = blockIdx.x * rows_per_block;
     const int r_end = min(HW, r_begin + rows_per_block);
-    for (int r = r_begin + threadIdx.y; r < r_end; r += blockDim.y) {
+    int r = r_begin + threadIdx.y;
+    if (MODE == 0) {
+        // four independent 16-byte loads in flight per thread: the kernel is latency-bound otherwise (r01: 2.2 TB/s)
+        const int st = blockDim.y;
+        for (; r + 3 * st < r_end; r += 4 * st) {
+            uint4 u[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                u[k] = *reinterpret_cast<const uint4*>(x + ((long long)n * HW + r + k * st) * C + c0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 t = unpack_bf16x2(w[j]);
+                    a0[2 * j] += t.x;
+                    a1[2 * j] += t.x * t.x;
+                    a0[2 * j + 1] += t.y;
+                    a1[2 * j + 1] += t.y * t.y;
+                }
+            }
+        }
+    }
+    for (; r < r_end; r += blockDim.y) {
         const long long off = ((long long)n * HW + r) * C + c0;
         float xv[8];
         load8(x + off, xv);
@@ -100,11 +123,14 @@ __global__ void gn_finalize_kernel(const float* __restrict__ raw, float* __restr
     stats[2 * i + 1] = rsqrtf(var + eps);
 }
 
-// y = act((x - mean) * rstd * gamma + beta).  grid (row chunks, NB), block (nvec, rpi)
+// y = act((x - mean) * rstd * gamma + beta).  grid (row chunks, NB), block (nvec, rpi).
+// RAW: `stats` holds the raw (sum, sum of squares) of gn_reduce_kernel<0>; mean / rstd are formed here (the separate
+// finalize launch is gone) and, when stats_out != NULL, written once per image for the backward.
+template <bool RAW>
 __global__ void gn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ stats,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 bf16* __restrict__ y, int HW, int C, int G, int rows_per_block,
-                                int silu_act) {
+                                int silu_act, float inv_count, float eps, float* __restrict__ stats_out) {
     const int n = blockIdx.y;
     const int cpg = C / G;
     const int c0 = threadIdx.x * 8;
@@ -112,14 +138,49 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, const float* __restr
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int g = (c0 + j) / cpg;
-        const float mean = stats[(n * G + g) * 2 + 0];
-        const float rstd = stats[(n * G + g) * 2 + 1];
+        float mean = stats[(n * G + g) * 2 + 0];
+        float rstd = stats[(n * G + g) * 2 + 1];
+        if (RAW) {
+            mean *= inv_count;
+            rstd = rsqrtf(fmaxf(rstd * inv_count - mean * mean, 0.f) + eps);
+        }
         sc[j] = rstd * gamma[c0 + j];
         sh[j] = beta[c0 + j] - mean * sc[j];
     }
+    if (RAW && stats_out != nullptr && blockIdx.x == 0) {
+        for (int g = threadIdx.y * blockDim.x + threadIdx.x; g < G; g += blockDim.x * blockDim.y) {
+            const float mean = stats[(n * G + g) * 2 + 0] * inv_count;
+            const float var = fmaxf(stats[(n * G + g) * 2 + 1] * inv_count - mean * mean, 0.f);
+            stats_out[(n * G + g) * 2 + 0] = mean;
+            stats_out[(n * G + g) * 2 + 1] = rsqrtf(var + eps);
+        }
+    }
     const int r_begin = blockIdx.x * rows_per_block;
     const int r_end = min(HW, r_begin + rows_per_block);
-    for (int r = r_begin + threadIdx.y; r < r_end; r += blockDim.y) {
+    int r = r_begin + threadIdx.y;
+    {
+        const int st = blockDim.y;
+        for (; r + 3 * st < r_end; r += 4 * st) {       // four loads in flight per thread
+            uint4 u[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                u[k] = *reinterpret_cast<const uint4*>(x + ((long long)n * HW + r + k * st) * C + c0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 t = unpack_bf16x2(w[j]);
+                    const float t0 = t.x * sc[2 * j] + sh[2 * j], t1 = t.y * sc[2 * j + 1] + sh[2 * j + 1];
+                    v[2 * j] = silu_act ? silu(t0) : t0;
+                    v[2 * j + 1] = silu_act ? silu(t1) : t1;
+                }
+                store8(y + ((long long)n * HW + r + k * st) * C + c0, v);
+            }
+        }
+    }
+    for (; r < r_end; r += blockDim.y) {
         const long long off = ((long long)n * HW + r) * C + c0;
         float v[8];
         load8(x + off, v);
@@ -177,7 +238,7 @@ static void gn_geometry(int HW, int C, int NB, dim3& grid, dim3& block, int& row
     if (rpi < 1) rpi = 1;
     if (rpi > HW) rpi = HW;
     block = dim3(nvec, rpi);
-    int target_blocks = (4 * num_sms() + NB - 1) / NB;  // per image
+    int target_blocks = (8 * num_sms() + NB - 1) / NB;  // per image
     int max_chunks = (HW + rpi * 4 - 1) / (rpi * 4);    // at least 4 rows per thread
     if (max_chunks < 1) max_chunks = 1;
     int chunks = target_blocks < max_chunks ? target_blocks : max_chunks;
@@ -543,8 +604,27 @@ extern "C" int fd_groupnorm_apply(const void* x, const float* stats, const float
     dim3 grid, block;
     int rpb;
     gn_geometry(HW, C, NB, grid, block, rpb);
-    gn_apply_kernel<<<grid, block, 0, stream>>>((const bf16*)x, stats, gamma, beta, (bf16*)y, HW, C, G,
-                                                rpb, silu_act);
+    gn_apply_kernel<false><<<grid, block, 0, stream>>>((const bf16*)x, stats, gamma, beta, (bf16*)y, HW, C, G,
+                                                       rpb, silu_act, 0.f, 0.f, nullptr);
+    FD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int fd_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* raw,
+                                float* stats_out, int32_t NB, int32_t HW, int32_t C, int32_t G, float eps,
+                                int32_t silu_act, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FD_CHECK_ARG(C % 8 == 0 && C % G == 0 && C / 8 <= 1024, "fd_groupnorm_fwd: bad C=%d G=%d", C, G);
+    FD_CHECK_ARG(raw != nullptr && raw != stats_out, "fd_groupnorm_fwd: raw scratch must be a distinct buffer");
+    FD_CHECK_CUDA(cudaMemsetAsync(raw, 0, sizeof(float) * 2 * NB * G, stream));
+    dim3 grid, block;
+    int rpb;
+    gn_geometry(HW, C, NB, grid, block, rpb);
+    gn_reduce_kernel<0><<<grid, block, 2 * G * sizeof(float), stream>>>(
+        (const bf16*)x, nullptr, nullptr, nullptr, nullptr, raw, HW, C, G, rpb, 0);
+    FD_CHECK_LAUNCH();
+    gn_apply_kernel<true><<<grid, block, 0, stream>>>((const bf16*)x, raw, gamma, beta, (bf16*)y, HW, C, G, rpb,
+                                                      silu_act, 1.0f / ((float)HW * (C / G)), eps, stats_out);
     FD_CHECK_LAUNCH();
     return 0;
 }

@@ -36,6 +36,7 @@ class FdGemmArgs(Structure):
         ("rowstats_out", c_void_p),
         ("act", c_int32),
         ("rowscale", c_void_p), ("rows_per_group_scale", c_int32), ("ldrs", c_int64),
+        ("workspace", c_void_p), ("workspace_bytes", c_int64),
     ]
 
 
@@ -81,6 +82,7 @@ def load():
     lib.fd_last_error.restype = c_char_p
     lib.fd_version.restype = c_int32
     lib.fd_sm_arch.restype = c_int32
+    lib.fd_gemm_workspace_bytes.restype = ctypes.c_size_t
     _lib = lib
     return lib
 

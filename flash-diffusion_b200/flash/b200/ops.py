@@ -246,8 +246,7 @@ class _GroupNormFn(torch.autograd.Function):
     def forward(ctx, x, gamma, beta, geom, G, eps, silu):
         NB, H, W = geom
         C = x.shape[1]
-        stats = raw.groupnorm_stats(x, NB, H * W, C, G, eps)
-        y = raw.groupnorm_apply(x, stats, gamma, beta, NB, H * W, C, G, silu)
+        y, stats = raw.groupnorm_fwd(x, gamma, beta, NB, H * W, C, G, eps, silu, want_stats=True)
         ctx.save_for_backward(x, stats, gamma, beta)
         ctx.meta = (NB, H * W, C, G, silu)
         return y
@@ -268,8 +267,7 @@ def group_norm(x, geom, norm, silu):
         return _GroupNormFn.apply(x, gamma, beta, geom, norm.num_groups, norm.eps, silu)
     NB, H, W = geom
     C = x.shape[1]
-    stats = raw.groupnorm_stats(x, NB, H * W, C, norm.num_groups, norm.eps)
-    return raw.groupnorm_apply(x, stats, gamma, beta, NB, H * W, C, norm.num_groups, silu)
+    return raw.groupnorm_fwd(x, gamma, beta, NB, H * W, C, norm.num_groups, norm.eps, silu)
 
 
 class _LayerNormFn(torch.autograd.Function):

@@ -25,6 +25,23 @@ def _req(t, dtype, name):
         raise RuntimeError(f"{name}: expected {dtype}, got {t.dtype}")
 
 
+_GEMM_WS = {}
+
+
+def gemm_workspace(device):
+    """Caller-owned stream-K scratch of fd_gemm (include/flashb200.h): one zero-filled buffer per device.  Every GEMM
+    of a device runs stream-ordered on the compute stream (eager launches and CUDA-graph replays alike), so one
+    buffer is enough; it is created on the first call, which must not happen under stream capture."""
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    ws = _GEMM_WS.get(key)
+    if ws is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("fd_gemm workspace must be created before CUDA-graph capture (run one eager GEMM first)")
+        ws = torch.zeros(int(load().fd_gemm_workspace_bytes()), dtype=torch.uint8, device=device)
+        _GEMM_WS[key] = ws
+    return ws
+
+
 def gemm(a1, b1, *, a2=None, b2=None, bias=None, rowvec=None, rows_per_group=0, geglu=False,
          residual=None, out=None, out_fp32=False, conv=None, M=None, force_bn=0, ln=None, rowstats=None,
          act=0, rowscale=None, rows_per_group_scale=0):
@@ -90,6 +107,8 @@ def gemm(a1, b1, *, a2=None, b2=None, bias=None, rowvec=None, rows_per_group=0, 
     if rowstats is not None:
         assert rowstats.dtype == torch.float32 and rowstats.shape == (M, 2) and rowstats.is_contiguous()
         args.rowstats_out = ptr(rowstats)
+    ws = gemm_workspace(a1.device)
+    args.workspace, args.workspace_bytes = ptr(ws), ws.numel()
     check(lib.fd_gemm(byref(args), stream_ptr()), "fd_gemm")
     return out
 
@@ -110,6 +129,18 @@ def groupnorm_apply(x, stats, gamma, beta, NB, HW, C, G, silu):
                                  c_int32(C), c_int32(G), c_int32(1 if silu else 0), stream_ptr()),
           "fd_groupnorm_apply")
     return y
+
+
+def groupnorm_fwd(x, gamma, beta, NB, HW, C, G, eps, silu, want_stats=False):
+    """GroupNorm(+SiLU) forward in two launches (fd_groupnorm_fwd); returns y or (y, stats[NB,G,2] = mean, rstd)."""
+    lib = load(); _req(x, BF16, "x"); _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")
+    y = torch.empty_like(x)
+    raw_sums = torch.empty((NB, G, 2), device=x.device, dtype=torch.float32)
+    stats = torch.empty((NB, G, 2), device=x.device, dtype=torch.float32) if want_stats else None
+    check(lib.fd_groupnorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(y), ptr(raw_sums), ptr(stats), c_int32(NB),
+                               c_int32(HW), c_int32(C), c_int32(G), c_float(eps), c_int32(1 if silu else 0),
+                               stream_ptr()), "fd_groupnorm_fwd")
+    return (y, stats) if want_stats else y
 
 
 def groupnorm_bwd(x, stats, gamma, beta, dy, NB, HW, C, G, silu):

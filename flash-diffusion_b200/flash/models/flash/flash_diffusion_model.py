@@ -244,12 +244,19 @@ class FlashDiffusion(BaseModel):
             return {"loss": [None, gan_loss[1]], "teacher_output": None, "student_output": student_output,
                     "noisy_sample": noisy_sample_init, "start_timestep": start_t_host}
 
-        loss = self._distill_loss(student_output, teacher_output) * self.distill_loss_scale[K_step]
+        distill = self._distill_loss(student_output, teacher_output)
+        loss = distill * self.distill_loss_scale[K_step]
+        dmd = None
         if self.use_dmd_loss:
-            loss = loss + self._dmd_loss(student_output, student_conditioning, conditioning,
-                                         unconditional_conditioning, None, K, K_step, draws) * self.dmd_loss_scale[K_step]
+            dmd = self._dmd_loss(student_output, student_conditioning, conditioning, unconditional_conditioning, None,
+                                 K, K_step, draws)
+            loss = loss + dmd * self.dmd_loss_scale[K_step]
         gan_loss = self._gan_loss(z, batch, student_output, teacher_output, conditioning, None, step=step, draws=draws)
         loss = loss + self.adversarial_loss_scale[K_step] * gan_loss[0]
+        # un-scaled terms of the objective (detached; parity tests compare each against the oracle)
+        self.__dict__["last_loss_terms"] = {
+            k: (v.detach() if torch.is_tensor(v) else v)
+            for k, v in dict(distill=distill, dmd=dmd, gan_G=gan_loss[0], gan_D=gan_loss[1]).items()}
         return {"loss": [loss, gan_loss[1]], "teacher_output": teacher_output, "student_output": student_output,
                 "noisy_sample": noisy_sample_init, "start_timestep": start_t_host}
 

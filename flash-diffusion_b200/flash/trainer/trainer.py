@@ -23,11 +23,47 @@ from .training_config import TrainingConfig
 
 
 class _FlatGradBucket:
-    """All gradients of one optimizer as views into one contiguous fp32 buffer (single all-reduce)."""
+    """All gradients of one optimizer as views into one contiguous fp32 buffer.
 
-    def __init__(self, params: List[torch.nn.Parameter]):
+    Data parallel: the buffer is all-reduced (mean) across ranks.  On CUDA the reduction is OVERLAPPED
+    with the backward: the buffer is cut into `n_chunks` contiguous chunks; a post-accumulate hook on every parameter
+    counts the chunk's outstanding gradients and, when a chunk is complete (backward fills the buffer roughly back to
+    front), its NCCL all-reduce is enqueued on a side stream while the remaining dX / dA / dB kernels keep the compute
+    stream busy.  `finish()` reduces whatever is left, makes the compute stream wait for the side stream and divides by
+    the world size.  CUDA events bracket every chunk, so `stats()` can say how much of the all-reduce time was hidden
+    behind the backward and how much was exposed before `opt.step()`.  CPU tensors (gloo tests): one blocking
+    all-reduce in `finish()`."""
+
+    def __init__(self, params: List[torch.nn.Parameter], n_chunks: int = 4):
         self.params = params
         self.flat = None
+        self.n_chunks = n_chunks
+        self.chunks = []            # (lo, hi) element ranges of the flat buffer
+        self.chunk_of = {}          # id(param) -> chunk index
+        self.pending = []
+        self.launched = []
+        self.hooks_installed = False
+        self.side = None
+        self.events = []            # per step: (e_backward_end, [(e_start, e_end) per chunk])
+        self.overlap = True
+
+    @staticmethod
+    def _dp():
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def _layout(self):
+        n = sum(p.numel() for p in self.params)
+        target = max(1, (n + self.n_chunks - 1) // self.n_chunks)
+        self.chunks, self.chunk_of = [], {}
+        lo = off = 0
+        for p in self.params:
+            self.chunk_of[id(p)] = len(self.chunks)
+            off += p.numel()
+            if off - lo >= target:
+                self.chunks.append((lo, off))
+                lo = off
+        if off > lo:
+            self.chunks.append((lo, off))
 
     def attach(self):
         if not self.params:
@@ -36,17 +72,84 @@ class _FlatGradBucket:
         if self.flat is None or self.flat.device != dev:
             n = sum(p.numel() for p in self.params)
             self.flat = torch.zeros(n, device=dev, dtype=torch.float32)
+            self._layout()
         else:
             self.flat.zero_()
         off = 0
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
+        counts = [0] * len(self.chunks)
+        for p in self.params:
+            counts[self.chunk_of[id(p)]] += 1
+        self.pending, self.launched = counts, [False] * len(self.chunks)
+        self._cur = None
+        if self._dp() and self.flat.is_cuda and self.overlap:
+            if self.side is None:
+                self.side = torch.cuda.Stream(device=dev)
+            if not self.hooks_installed:
+                for p in self.params:
+                    p.register_post_accumulate_grad_hook(self._on_grad)
+                self.hooks_installed = True
+            self._cur = []
 
-    def all_reduce_mean(self):
-        if self.flat is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+    def _on_grad(self, p):
+        if self._cur is None or id(p) not in self.chunk_of:
+            return
+        c = self.chunk_of[id(p)]
+        self.pending[c] -= 1
+        if self.pending[c] == 0 and not self.launched[c]:
+            self._launch(c)
+
+    def _launch(self, c):
+        lo, hi = self.chunks[c]
+        self.launched[c] = True
+        main = torch.cuda.current_stream(self.flat.device)
+        self.side.wait_stream(main)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(self.side):
+            e0.record()
+            dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM)
+            e1.record()
+        self._cur.append((e0, e1))
+
+    def finish(self):
+        """all-reduce (mean) complete on the compute stream when this returns control to the optimizer step."""
+        if self.flat is None or not self._dp():
+            return
+        world = dist.get_world_size()
+        if self._cur is None:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            self.flat.div_(dist.get_world_size())
+            self.flat.div_(world)
+            return
+        main = torch.cuda.current_stream(self.flat.device)
+        e_bwd = torch.cuda.Event(enable_timing=True)
+        e_bwd.record(main)
+        for c in range(len(self.chunks)):
+            if not self.launched[c]:
+                self._launch(c)
+        main.wait_stream(self.side)
+        self.flat.div_(world)
+        self.events.append((e_bwd, self._cur))
+        if len(self.events) > 64:
+            self.events = self.events[-64:]
+        self._cur = None
+
+    all_reduce_mean = finish
+
+    def stats(self):
+        """{"steps", "ms_total", "ms_exposed"}: per-step means of the all-reduce time on the side stream and of the
+        part of it that ran after the backward had finished.  Synchronises the device."""
+        if not self.events:
+            return None
+        torch.cuda.synchronize()
+        tot = exp = 0.0
+        for e_bwd, pairs in self.events:
+            tot += sum(a.elapsed_time(b) for a, b in pairs)
+            exp += max(0.0, e_bwd.elapsed_time(pairs[-1][1])) if pairs else 0.0
+        n = len(self.events)
+        return {"steps": n, "ms_total": tot / n, "ms_exposed": exp / n, "chunks": len(self.chunks),
+                "bytes": 4 * self.flat.numel()}
 
 
 class TrainingPipeline(torch.nn.Module):
@@ -67,6 +170,14 @@ class TrainingPipeline(torch.nn.Module):
     @property
     def device(self):
         return next(self.model.parameters()).device
+
+    @property
+    def allreduce_stats(self):
+        """per optimizer: gradient all-reduce time per step, total vs exposed after the backward."""
+        if not self._buckets:
+            return None
+        out = [b.stats() for b in self._buckets]
+        return out if any(o is not None for o in out) else None
 
     # ---- reference :76-139
     def configure_optimizers(self):

@@ -84,7 +84,8 @@ typedef struct {
     int32_t geglu;
     const void* residual; int64_t ldr;
     void* out; int64_t ldo; int32_t out_fp32;
-    int32_t force_bn;   /* 0 = heuristic, else 64/128/256 single-CTA, 512+128 / 512+256 CTA-pair */
+    int32_t force_bn;   /* 0 = heuristic, else 64/128/256 single-CTA, 512+128 / 512+160 / 512+256 CTA-pair; | 1024: cut
+                         * tiles along K between CTA pairs (stream-K) whenever legal; | 2048: whole tiles only */
     /* LayerNorm fold */
     const float* ln_stats; const float* ln_colsum; float ln_inv_c; float ln_eps;
     float* rowstats_out;
@@ -93,8 +94,14 @@ typedef struct {
      * (UPSTREAM BasicTransformerBlock(ada_norm_single): hidden = gate * attn(...) + hidden). */
     int32_t act;
     const float* rowscale; int32_t rows_per_group_scale; int64_t ldrs;
+    /* Caller-owned scratch for the stream-K schedule of the CTA-pair kernels (tiles cut along K between CTA pairs,
+     * partial accumulators exchanged through it).  >= fd_gemm_workspace_bytes() bytes, 16-byte aligned, ZERO-FILLED
+     * once by the caller (the kernels leave it zero-flagged); calls that may run CONCURRENTLY (different streams)
+     * need different workspaces.  NULL: no K cuts (whole tiles per CTA pair, wave-quantised). */
+    void* workspace; int64_t workspace_bytes;
 } FdGemmArgs;
 int fd_gemm(const FdGemmArgs* args, void* stream);
+size_t fd_gemm_workspace_bytes(void);
 
 /* ------------------------------------------------------------------------------------------
  * Normalisation / elementwise (HBM-bound) kernels — NHWC bf16 activations.
@@ -108,6 +115,11 @@ int fd_groupnorm_stats(const void* x, float* stats, int32_t NB, int32_t HW, int3
 int fd_groupnorm_apply(const void* x, const float* stats, const float* gamma, const float* beta,
                        void* y, int32_t NB, int32_t HW, int32_t C, int32_t G, int32_t silu,
                        void* stream);
+/* Both of the above in two launches (reduce, then apply with the mean / rstd formed in the apply kernel): raw is a
+ * caller scratch [NB, G, 2] fp32 (zeroed by the call); stats_out (optional, [NB, G, 2]) receives (mean, rstd) for
+ * fd_groupnorm_bwd. */
+int fd_groupnorm_fwd(const void* x, const float* gamma, const float* beta, void* y, float* raw, float* stats_out,
+                     int32_t NB, int32_t HW, int32_t C, int32_t G, float eps, int32_t silu, void* stream);
 /* GroupNorm(+SiLU) backward: dx from dy (both bf16 [NB,HW,C]); recomputes from x and stats. */
 int fd_groupnorm_bwd(const void* x, const float* stats, const float* gamma, const float* beta,
                      const void* dy, void* dx, float* scratch /* [NB,G,2] */, int32_t NB,

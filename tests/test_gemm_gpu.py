@@ -126,3 +126,94 @@ def test_gemm_layernorm_fold_and_rowstats(raw, bn, geglu):
     colsum = wp.float().sum(1).contiguous()
     out = raw.gemm(x, wp, bias=bias.contiguous(), geglu=geglu, ln=(stats, colsum, C, 1e-5), out_fp32=True, force_bn=bn)
     assert _rel(out, ref) < 6e-3, _rel(out, ref)
+
+
+# ------------------------------------------------------------------------------------------ work split + TMA store
+SPLIT_MODES = {"auto": 0, "streamk": 1024, "whole_tiles": 2048}
+
+
+@pytest.mark.parametrize("M,N,K", [(8192, 1280, 1280),    # 160 tiles on 74 pairs: the in-situ shape (partial wave of 12 tiles)
+                                   (20000, 640, 1024),    # 79 x 3 tiles: ragged M, stream-K region of 1.2 waves
+                                   (4096, 640, 640),      # 48 tiles < 74 pairs: every tile cut into column slices
+                                   (616, 2560, 2048),     # 77-token K/V projection of the 2B teacher batch: ragged M
+                                   (1000, 200, 1000)])    # ragged everything (TMA store clips rows and columns)
+@pytest.mark.parametrize("bn", [0, 512 + 128, 512 + 160, 512 + 256])
+@pytest.mark.parametrize("mode", ["auto", "streamk", "whole_tiles"])
+def test_gemm_work_split_epilogues(raw, M, N, K, bn, mode):
+    """column slices of the partial wave / hybrid stream-K partial-tile exchange / whole tiles, each with the TMA-store
+    epilogue and every fused epilogue term, bf16 and fp32 outputs, repeated launches (the stream-K flags must be left
+    clean)."""
+    if bn == 0 and mode != "auto":
+        pytest.skip("work-split override needs an explicit tile")
+    fb = bn | SPLIT_MODES[mode]
+    torch.manual_seed(M * 7 + N)
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    b = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda").bfloat16()
+    ref = a.float() @ b.float().t() + bias + res.float()
+    for _ in range(3):
+        out = raw.gemm(a, b, bias=bias, residual=res, force_bn=fb)
+        assert _rel(out, ref) < 6e-3, _rel(out, ref)
+    out32 = raw.gemm(a, b, bias=bias, residual=res, out_fp32=True, force_bn=fb)
+    assert _rel(out32, ref) < 1e-5, _rel(out32, ref)
+    # row statistics of the stored bf16 output (LayerNorm-fold producer side)
+    stats = torch.empty(M, 2, device="cuda")
+    out = raw.gemm(a, b, bias=bias, residual=res, rowstats=stats, force_bn=fb)
+    of = out.float()
+    assert torch.allclose(stats[:, 0], of.sum(1), rtol=1e-3, atol=1e-2)
+    assert torch.allclose(stats[:, 1], (of * of).sum(1), rtol=1e-3, atol=1e-2)
+    # strided output view (fused qkv buffers are written through column slices)
+    big = torch.zeros(M, N + 64, device="cuda", dtype=torch.bfloat16)
+    raw.gemm(a, b, bias=bias, residual=res, out=big[:, 32:32 + N], force_bn=fb)
+    assert _rel(big[:, 32:32 + N], ref) < 6e-3
+    assert float(big[:, :32].abs().max()) == 0 and float(big[:, 32 + N:].abs().max()) == 0
+    ws = raw.gemm_workspace(a.device)
+    assert int(ws[:4096].view(torch.int32).abs().sum()) == 0          # flags reset by the readers
+
+
+@pytest.mark.parametrize("mode", ["auto", "streamk", "whole_tiles"])
+def test_gemm_work_split_geglu_lora(raw, mode):
+    torch.manual_seed(3)
+    M, C, r = 20480, 640, 64
+    x = torch.randn(M, C, device="cuda").bfloat16()
+    w = (torch.randn(2 * C, C, device="cuda") / C ** 0.5).bfloat16()
+    b = torch.randn(2 * C, device="cuda")
+    h = x.float() @ w.float().t() + b
+    val, gate = h.chunk(2, dim=-1)
+    ref = val * torch.nn.functional.gelu(gate)
+    wv, wg = w[:C].view(-1, 16, C), w[C:].view(-1, 16, C)
+    wi = torch.stack([wv, wg], dim=1).reshape(2 * C, C).contiguous()
+    bi = torch.stack([b[:C].view(-1, 16), b[C:].view(-1, 16)], dim=1).reshape(-1).contiguous()
+    for bn in (512 + 128, 512 + 256):
+        out = raw.gemm(x, wi, bias=bi, geglu=True, force_bn=bn | SPLIT_MODES[mode])     # 32-byte-row TMA store
+        assert _rel(out, ref) < 6e-3, (bn, _rel(out, ref))
+    # second K segment (LoRA) across a stream-K cut / inside column slices
+    t = torch.randn(M, r, device="cuda").bfloat16()
+    w2 = (torch.randn(1280, C, device="cuda") / C ** 0.5).bfloat16()
+    lb = (torch.randn(1280, r, device="cuda") * 0.05).bfloat16()
+    ref2 = x.float() @ w2.float().t() + t.float() @ lb.float().t()
+    for bn in (512 + 128, 512 + 160, 512 + 256):
+        out = raw.gemm(x, w2, a2=t, b2=lb, force_bn=bn | SPLIT_MODES[mode])
+        assert _rel(out, ref2) < 6e-3, (bn, _rel(out, ref2))
+
+
+@pytest.mark.parametrize("mode", ["auto", "streamk"])
+def test_conv3x3_work_split(raw, mode):
+    """implicit-GEMM conv through the same work splits (4-D TMA A operand, K = 9 taps x channels)."""
+    torch.manual_seed(5)
+    NB, H, W, Cin, Cout = 5, 64, 64, 128, 320             # M = 20480 rows: 80 x 2 tiles at BN = 160/256
+    x = torch.randn(NB, Cin, H, W, device="cuda").bfloat16()
+    w = (torch.randn(Cout, Cin, 3, 3, device="cuda") / (9 * Cin) ** 0.5).bfloat16()
+    bias = torch.randn(Cout, device="cuda")
+    torch.backends.cudnn.allow_tf32 = False
+    ref = torch.nn.functional.conv2d(x.float(), w.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(NB * H * W, Cout)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    cpad = (Cin + 63) // 64 * 64
+    wp = torch.zeros(Cout, 9, cpad, device="cuda")
+    wp[:, :, :Cin] = w.float().permute(0, 2, 3, 1).reshape(Cout, 9, Cin)
+    wp = wp.reshape(Cout, 9 * cpad).bfloat16()
+    for bn in (512 + 128, 512 + 160, 512 + 256):
+        out = raw.gemm(x_nhwc, wp, bias=bias, conv=dict(NB_in=NB, H=H, W=W, C=Cin, taps=raw.TAPS_3X3), M=NB * H * W,
+                       force_bn=bn | SPLIT_MODES[mode])
+        assert _rel(out, ref) < 6e-3, (bn, _rel(out, ref))

@@ -61,6 +61,10 @@ def test_groupnorm(raw, NB, HW, C, silu):
     if silu:
         ref = F.silu(ref)
     assert _rel(y, ref.transpose(1, 2)) < 6e-3
+    # the two-launch forward (statistics finalised inside the apply kernel) used by the engines
+    y2, stats2 = raw.groupnorm_fwd(x, gamma, beta, NB, HW, C, G, 1e-5, silu, want_stats=True)
+    assert _rel(y2, ref.transpose(1, 2)) < 6e-3
+    assert torch.allclose(stats2, stats, rtol=1e-4, atol=1e-5)
     dy = torch.randn(NB, HW, C, device="cuda").bfloat16()
     ref.backward(dy.float().transpose(1, 2))
     dx = raw.groupnorm_bwd(x, stats, gamma, beta, dy, NB, HW, C, G, silu)

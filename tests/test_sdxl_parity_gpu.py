@@ -1,0 +1,182 @@
+"""Parity at the BASELINE configuration (config 2: SDXL architecture, latent 128x128, LoRA r=64 on q/k/v/out) — the
+sizes where the BN=160/256 pair tiles, the 4096-token attention backward and the 10/20-head levels actually run.
+
+  * test_sdxl_student_backward_full_size   LoRA + input gradients of the full SDXL student, B=1, vs fp32 oracle autograd
+  * test_sdxl_step_terms_vs_oracle         one FlashDiffusion.forward per optimizer turn at config-2 shapes (K=4), every
+                                           term of the objective (distill / DMD / G / D) and the LoRA gradient of the
+                                           total generator loss vs oracle/flash_step.py (reference
+                                           flash_diffusion_model.py:179-366)
+
+Tolerances: bf16 UNet vs fp32 oracle rel-L2(student_output) <= 2e-2, each loss term <= 2e-2 relative,
+LoRA gradients cosine >= 0.999.  The per-tensor statistics are written to gpurun_out/sdxl_parity.json; the same
+quantities for the fp32 oracle under torch.autocast(bfloat16) — the precision the reference itself trains in
+(examples/train_flash_sdxl.py: Trainer(precision="bf16-mixed")) — are logged beside them as the noise floor.
+"""
+import copy
+import json
+import os
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-20)).item()
+
+
+def _cos(a, b):
+    a, b = a.float().reshape(-1), b.float().reshape(-1)
+    return (torch.dot(a, b) / (a.norm() * b.norm() + 1e-30)).item()
+
+
+def _log(name, payload):
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    path = os.path.join(out, "sdxl_parity.json")
+    data = {}
+    if os.path.exists(path):
+        try:
+            data = json.load(open(path))
+        except Exception:
+            data = {}
+    data[name] = payload
+    json.dump(data, open(path, "w"), indent=1)
+
+
+def _grad_stats(named_prod, named_ref):
+    cos, rel, num, den_a, den_b = {}, {}, 0.0, 0.0, 0.0
+    for n, g in named_prod.items():
+        r = named_ref[n]
+        cos[n], rel[n] = _cos(g, r), _rel(g, r)
+        num += torch.dot(g.float().reshape(-1), r.float().reshape(-1)).item()
+        den_a += g.float().pow(2).sum().item()
+        den_b += r.float().pow(2).sum().item()
+    vals = sorted(cos.values())
+    worst = sorted(cos.items(), key=lambda kv: kv[1])[:5]
+    return {"global_cos": num / (den_a ** 0.5 * den_b ** 0.5 + 1e-30), "min_cos": vals[0],
+            "p01_cos": vals[len(vals) // 100], "median_cos": vals[len(vals) // 2],
+            "frac_ge_0999": sum(v >= 0.999 for v in vals) / len(vals), "n_tensors": len(vals),
+            "max_rel": max(rel.values()), "worst": worst}
+
+
+def test_sdxl_student_backward_full_size():
+    from oracle.unet import SDXL_KWARGS
+    from test_unet_gpu import _inputs, _pair
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    prod, ora = _pair(SDXL_KWARGS, lora=True, seed=1234)
+    x, t, cond = _inputs(1, 128, 128, 2048, 2816)
+    g = torch.randn(1, 4, 128, 128, device="cuda")
+    xp = x.clone().requires_grad_(True)
+    out = prod(xp, t, cond)
+    (out * g).sum().backward()
+    gp = {n: p.grad.detach().clone() for n, p in prod.named_parameters() if "lora_" in n}
+    assert all(p.grad is None for n, p in prod.named_parameters() if "lora_" not in n)
+    xo = x.clone().requires_grad_(True)
+    ref = ora(xo, t, cond)
+    (ref * g).sum().backward()
+    go = {n: p.grad.detach().clone() for n, p in ora.named_parameters() if "lora_" in n}
+    stats = _grad_stats(gp, go)
+    stats["out_rel"], stats["input_grad_cos"] = _rel(out, ref), _cos(xp.grad, xo.grad)
+    # noise floor: the SAME fp32 oracle under bf16 autocast (the reference's training precision) against itself in fp32
+    for p in ora.parameters():
+        p.grad = None
+    xa = x.clone().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        ref_ac = ora(xa, t, cond)
+    (ref_ac.float() * g).sum().backward()
+    ga = {n: p.grad.detach().clone() for n, p in ora.named_parameters() if "lora_" in n}
+    floor = _grad_stats(ga, go)
+    floor["out_rel"], floor["input_grad_cos"] = _rel(ref_ac, ref), _cos(xa.grad, xo.grad)
+    _log("student_backward_B1", {"b200_kernels_vs_fp32_oracle": stats, "autocast_bf16_oracle_vs_fp32_oracle": floor})
+    assert len(gp) == 1120                                  # 560 adapted linears x (A, B)  
+    assert stats["out_rel"] < 2e-2, stats
+    assert stats["input_grad_cos"] > 0.999, stats
+    assert stats["global_cos"] > 0.999, stats
+    assert stats["min_cos"] > 0.999, stats
+
+
+def _oracle_twins(model):
+    from oracle.unet import SDXL_KWARGS, LoraConfig, UNet2DConditionOracle
+    with torch.device("cuda"):
+        teacher = UNet2DConditionOracle(**SDXL_KWARGS)
+    student = copy.deepcopy(teacher)
+    student.add_adapter(LoraConfig(r=64, lora_alpha=64, init_lora_weights="gaussian",
+                                   target_modules=["to_k", "to_q", "to_v", "to_out.0"]))
+    teacher.load_state_dict(model.teacher_denoiser.state_dict())
+    student.load_state_dict(model.student_denoiser.state_dict())
+    student = student.cuda()
+    for p in teacher.parameters():
+        p.requires_grad = False
+    return teacher, student
+
+
+def test_sdxl_step_terms_vs_oracle():
+    from flash import recipes
+    from oracle import flash_step as OF
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    dev = torch.device("cuda")
+    B = 2
+    model, pipe = recipes.build_sdxl_distillation(dev, K=4, lora_b_std=0.02)
+    batch = recipes.synthetic_batch(B, 128, 77, 2048, 1280, seed=7, device=dev)
+    g = torch.Generator(device=dev).manual_seed(11)
+    shape = (B, 4, 128, 128)
+    draws = dict(noise=torch.randn(shape, device=dev, generator=g), start_idx=1, guidance=5.0,
+                 dmd_noise=torch.randn(shape, device=dev, generator=g), dmd_timestep=torch.tensor([700, 120], device=dev),
+                 dmd_guidance=4.0, gan_noise=torch.randn(shape, device=dev, generator=g),
+                 gan_timesteps=torch.tensor([250, 750], device=dev))
+    scales = (model.distill_loss_scale[0], model.dmd_loss_scale[0], model.adversarial_loss_scale[0])
+    results = {}
+    prod = {}
+    for step in (0, 1):
+        for p in model.parameters():
+            p.grad = None
+        out = model(batch, step=step, draws=draws)
+        terms = dict(model.last_loss_terms)
+        if step == 0:
+            out["loss"][0].backward()
+            prod_g = {n: p.grad.detach().clone() for n, p in model.student_denoiser.named_parameters() if "lora_" in n}
+        prod[step] = dict(student_output=out["student_output"].detach().clone(),
+                          teacher_output=out["teacher_output"].detach().clone(),
+                          loss=[float(out["loss"][0]), float(out["loss"][1])],
+                          terms={k: (float(v) if v is not None else None) for k, v in terms.items()})
+        del out
+    torch.cuda.empty_cache()
+    teacher, student = _oracle_twins(model)
+    disc = model.discriminator
+    cond = model.conditioner(batch, set_ucg_rate_zero=True)
+    unc = model.conditioner(batch, ucg_keys=model.ucg_keys)
+    for step in (0, 1):
+        for p in student.parameters():
+            p.grad = None
+        ref = OF.flash_forward(student, teacher, disc, batch["image"], cond, unc, draws, K=4, step=step,
+                               gan_loss_type="lsgan", scales=scales)
+        r = {"student_output_rel": _rel(prod[step]["student_output"], ref["student_output"]),
+             "teacher_output_rel": _rel(prod[step]["teacher_output"], ref["teacher_output"])}
+        pairs = {"distill": (prod[step]["terms"]["distill"], float(ref["distill"])),
+                 "dmd": (prod[step]["terms"]["dmd"], float(ref["dmd"])),
+                 "loss_G_total": (prod[step]["loss"][0], float(ref["loss_G"]))}
+        if step == 0:
+            pairs["gan_G"] = (prod[step]["terms"]["gan_G"], float(ref["gan_G"]))
+            ref["loss_G"].backward()
+            ref_g = {n: p.grad.detach().clone() for n, p in student.named_parameters() if "lora_" in n}
+            r["lora_grad"] = _grad_stats(prod_g, ref_g)
+        else:
+            pairs["loss_D"] = (prod[step]["loss"][1], float(ref["loss_D"]))
+        for k, (a, b) in pairs.items():
+            r[k] = {"b200": a, "oracle": b, "rel_err": abs(a - b) / (abs(b) + 1e-30)}
+        results[f"step{step}"] = r
+        del ref
+    _log("step_terms_B2_K4", results)
+    for step in (0, 1):
+        r = results[f"step{step}"]
+        assert r["student_output_rel"] < 2e-2, r
+        assert r["teacher_output_rel"] < 2e-2, r
+        for k in ("distill", "dmd", "loss_G_total") + (("gan_G",) if step == 0 else ("loss_D",)):
+            assert r[k]["rel_err"] < 2e-2, (k, r[k])
+    assert results["step0"]["lora_grad"]["global_cos"] > 0.999, results["step0"]["lora_grad"]
