@@ -440,7 +440,7 @@ constexpr int ATT1_STAGES = 2;
 constexpr int ATT1_THREADS = 64 + 256;        // TMA warp, MMA warp, 2 column halves x 4 softmax warps
 constexpr int ATT1_SMEM = ATT_TILE_BYTES + 2 * ATT1_STAGES * ATT_TILE_BYTES + 256 + 2048 + 1024;
 
-template <bool POLY>
+template <int POLY>     // 0: every exponential on the MUFU; m > 0: every m-th pair of scores on the FMA pipe (cubic)
 __global__ void __launch_bounds__(ATT1_THREADS, 2)
 attn_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttnKParams p) {
@@ -599,7 +599,7 @@ attn_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 for (int i = 0; i < 32; i += 2) {
                     const float2 x = ffma2(make_float2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), sc2, nm2);
                     float2 e;
-                    if (POLY && FD_ATTN_POLY_MOD > 0 && ((i >> 1) % (FD_ATTN_POLY_MOD > 0 ? FD_ATTN_POLY_MOD : 1)) == 1)
+                    if (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == (POLY > 1 ? 1 : 0))
                         e = exp2_poly2(x);
                     else
                         e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
@@ -706,8 +706,10 @@ extern "C" int fd_attn_fwd(const FdAttnArgs* a, void* stream_) {
     if (!attr_set) {
         FD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         FD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        FD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd1_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT1_SMEM));
-        FD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd1_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT1_SMEM));
+        FD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd1_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT1_SMEM));
+        FD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd1_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT1_SMEM));
+        FD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd1_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT1_SMEM));
+        FD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT1_SMEM));
         attr_set = true;
     }
     ProfScope prof(stream, PROF_ATTN_FWD, 4.0 * (double)a->B * a->H * (double)a->Nq * (double)a->Nkv * ATT_D);
@@ -715,10 +717,16 @@ extern "C" int fd_attn_fwd(const FdAttnArgs* a, void* stream_) {
     static const int variant = getenv("FD_ATTN_V") ? atoi(getenv("FD_ATTN_V")) : 1;
     if (variant == 1) {
         dim3 grid((a->Nq + 127) / 128, a->H, a->B);
-        if (a->lse != nullptr)
-            attn_fwd1_kernel<false><<<grid, ATT1_THREADS, ATT1_SMEM, stream>>>(tq, tk, tv, p);
+        // share of the exponentials on the FMA pipe in the inference forward (FD_ATTN_POLY = 4: 25 %, 3: 33 %, 2: 50 %)
+        static const int poly = getenv("FD_ATTN_POLY") ? atoi(getenv("FD_ATTN_POLY")) : 4;
+        if (a->lse != nullptr || poly == 0)
+            attn_fwd1_kernel<0><<<grid, ATT1_THREADS, ATT1_SMEM, stream>>>(tq, tk, tv, p);
+        else if (poly == 2)
+            attn_fwd1_kernel<2><<<grid, ATT1_THREADS, ATT1_SMEM, stream>>>(tq, tk, tv, p);
+        else if (poly == 3)
+            attn_fwd1_kernel<3><<<grid, ATT1_THREADS, ATT1_SMEM, stream>>>(tq, tk, tv, p);
         else
-            attn_fwd1_kernel<true><<<grid, ATT1_THREADS, ATT1_SMEM, stream>>>(tq, tk, tv, p);
+            attn_fwd1_kernel<4><<<grid, ATT1_THREADS, ATT1_SMEM, stream>>>(tq, tk, tv, p);
         FD_CHECK_LAUNCH();
         return 0;
     }

@@ -313,6 +313,82 @@ __global__ void student_output_kernel(const float* __restrict__ x_t, const float
     }
 }
 
+
+// ---------------------------------------------------------------------------- row softmax (large-head attention)
+// The VAE mid-block attention has ONE head of 512 channels (UPSTREAM AutoencoderKL: Attention(heads=1, dim_head=512)):
+// its O accumulator alone would fill the 512 TMEM columns, so it runs as two tcgen05 GEMMs (S = Q K^T, O = P V) around
+// this row softmax instead of the fused FlashAttention kernels.  One block per row, fp32 math, 16-byte accesses; the
+// row is read three times (max, sum, write) out of L1/L2.
+__device__ __forceinline__ float block_reduce(float v, float* sm, bool is_max) {
+    v = is_max ? warp_max(v) : warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (l == 0) sm[w] = v;
+    __syncthreads();
+    float r = is_max ? -INFINITY : 0.f;
+    for (int i = 0; i < nw; ++i) r = is_max ? fmaxf(r, sm[i]) : r + sm[i];
+    return r;
+}
+
+__global__ void softmax_rows_kernel(const bf16* __restrict__ x, long long ldx, bf16* __restrict__ y, long long ldy,
+                                    int L, float scale_log2) {
+    __shared__ float sm[32];
+    const bf16* xr = x + (long long)blockIdx.x * ldx;
+    bf16* yr = y + (long long)blockIdx.x * ldy;
+    const int nvec = L >> 3;
+    float mx = -INFINITY;
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+        float f[8];
+        ld8(xr + v * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mx = fmaxf(mx, f[j]);
+    }
+    mx = block_reduce(mx, sm, true) * scale_log2;
+    float sum = 0.f;
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+        float f[8];
+        ld8(xr + v * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += exp2f(fmaf(f[j], scale_log2, -mx));
+    }
+    sum = block_reduce(sum, sm, false);
+    const float inv = 1.f / sum;
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+        float f[8];
+        ld8(xr + v * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = exp2f(fmaf(f[j], scale_log2, -mx)) * inv;
+        st8(yr + v * 8, f);
+    }
+}
+
+// ds = p * (dp - sum_j p_j dp_j) * scale   (backward of y = softmax(scale * x) given p = y)
+__global__ void softmax_rows_bwd_kernel(const bf16* __restrict__ p, const bf16* __restrict__ dp, bf16* __restrict__ ds,
+                                        long long ld, int L, float scale) {
+    __shared__ float sm[32];
+    const bf16* pr = p + (long long)blockIdx.x * ld;
+    const bf16* dr = dp + (long long)blockIdx.x * ld;
+    bf16* sr = ds + (long long)blockIdx.x * ld;
+    const int nvec = L >> 3;
+    float dot = 0.f;
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+        float a[8], b[8];
+        ld8(pr + v * 8, a);
+        ld8(dr + v * 8, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dot += a[j] * b[j];
+    }
+    dot = block_reduce(dot, sm, false);
+    for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+        float a[8], b[8];
+        ld8(pr + v * 8, a);
+        ld8(dr + v * 8, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = a[j] * (b[j] - dot) * scale;
+        st8(sr + v * 8, a);
+    }
+}
+
 }  // namespace fd
 
 using namespace fd;
@@ -478,6 +554,24 @@ extern "C" int fd_patchify(const float* dy, void* dx, int32_t NB, int32_t h, int
     FD_CHECK_ARG(Ckeep <= Cout && p > 0, "fd_patchify: bad channels");
     const long long total = (long long)NB * h * w * p * p * Cout;
     patchify_kernel<<<grid_for(total), 256, 0, (cudaStream_t)stream>>>(dy, (bf16*)dx, NB, h, w, p, Cout, Ckeep);
+    FD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int fd_softmax_rows(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t L, float scale,
+                               void* stream) {
+    FD_CHECK_ARG(rows > 0 && L > 0 && L % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "fd_softmax_rows: L / strides must be multiples of 8");
+    fd::softmax_rows_kernel<<<rows, L >= 2048 ? 256 : 128, 0, (cudaStream_t)stream>>>(
+        (const fd::bf16*)x, ldx, (fd::bf16*)y, ldy, L, scale * 1.4426950408889634f);
+    FD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int fd_softmax_rows_bwd(const void* p, const void* dp, void* ds, int64_t ld, int32_t rows, int32_t L,
+                                   float scale, void* stream) {
+    FD_CHECK_ARG(rows > 0 && L > 0 && L % 8 == 0 && ld % 8 == 0, "fd_softmax_rows_bwd: L / stride must be multiples of 8");
+    fd::softmax_rows_bwd_kernel<<<rows, L >= 2048 ? 256 : 128, 0, (cudaStream_t)stream>>>(
+        (const fd::bf16*)p, (const fd::bf16*)dp, (fd::bf16*)ds, ld, L, scale);
     FD_CHECK_LAUNCH();
     return 0;
 }

@@ -201,6 +201,10 @@ __device__ __forceinline__ void epilogue_values(const GemmKParams& p, int row, i
             v[j] = 0.5f * x * (1.0f + tanhf(u));
         }
     }
+    if (p.act == 2) {   // ReLU (VGG16 feature stack of the LPIPS distillation loss)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    }
     if (p.rowscale != nullptr && row_ok) {
         const float* sv = p.rowscale + (long long)(row / p.rows_per_group_scale) * p.ldrs + col0;
 #pragma unroll
@@ -1070,7 +1074,8 @@ extern "C" int fd_gemm(const FdGemmArgs* a, void* stream_) {
     FD_CHECK_ARG(!a->rowscale || a->rows_per_group_scale > 0, "fd_gemm: rowscale needs rows_per_group_scale");
     FD_CHECK_ARG(!a->ln_stats || (a->ln_colsum && a->K2 == 0), "fd_gemm: LayerNorm fold needs ln_colsum and no K2 segment");
     FD_CHECK_ARG(!a->rowstats_out || !a->out_fp32, "fd_gemm: rowstats_out needs a bf16 output");
-    if (a->rowstats_out) FD_CHECK_CUDA(cudaMemsetAsync(a->rowstats_out, 0, sizeof(float) * 2 * (size_t)a->M, stream));
+    if (a->rowstats_out && !a->rowstats_prezeroed)
+        FD_CHECK_CUDA(cudaMemsetAsync(a->rowstats_out, 0, sizeof(float) * 2 * (size_t)a->M, stream));
 
     CUtensorMap tA1, tB1, tA2, tB2;
     int rc;

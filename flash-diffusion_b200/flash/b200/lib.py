@@ -33,7 +33,7 @@ class FdGemmArgs(Structure):
         ("out", c_void_p), ("ldo", c_int64), ("out_fp32", c_int32),
         ("force_bn", c_int32),
         ("ln_stats", c_void_p), ("ln_colsum", c_void_p), ("ln_inv_c", c_float), ("ln_eps", c_float),
-        ("rowstats_out", c_void_p),
+        ("rowstats_out", c_void_p), ("rowstats_prezeroed", c_int32),
         ("act", c_int32),
         ("rowscale", c_void_p), ("rows_per_group_scale", c_int32), ("ldrs", c_int64),
         ("workspace", c_void_p), ("workspace_bytes", c_int64),

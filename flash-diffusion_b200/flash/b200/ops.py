@@ -103,20 +103,28 @@ def _s2_taps(NB):
     return taps
 
 
-def _conv_fwd_raw(x, geom, wpack, bias, rowvec, residual, shortcut, stride, Cin, out_fp32=False):
+def _s2_taps_asym(NB):
+    """taps of diffusers' Downsample2D(padding=0) (the VAE encoder): F.pad(x, (0, 1, 0, 1)) then a 3x3 stride-2 conv
+    without padding — input row 2*ho + kh: phase kh & 1, row offset kh >> 1 (the TMA zero-fill supplies the pad)."""
+    return [(((kh & 1) * 2 + (kw & 1)) * NB, kh >> 1, kw >> 1) for kh in range(3) for kw in range(3)]
+
+
+def _conv_fwd_raw(x, geom, wpack, bias, rowvec, residual, shortcut, stride, Cin, out_fp32=False, pad_mode="same",
+                  act=0):
     NB, H, W = geom
     if stride == 1:
         conv = dict(NB_in=NB, H=H, W=W, C=Cin, taps=raw.TAPS_3X3)
         a1, M, rpg = x, NB * H * W, H * W
     else:
         a1 = raw.space_to_depth(x, NB, H, W, Cin)
-        conv = dict(NB_in=4 * NB, H=H // 2, W=W // 2, C=Cin, taps=_s2_taps(NB))
+        conv = dict(NB_in=4 * NB, H=H // 2, W=W // 2, C=Cin,
+                    taps=_s2_taps(NB) if pad_mode == "same" else _s2_taps_asym(NB))
         M, rpg = NB * (H // 2) * (W // 2), (H // 2) * (W // 2)
     a2 = b2 = None
     if shortcut is not None:
         a2, b2 = shortcut
     return raw.gemm(a1, wpack, a2=a2, b2=b2, bias=bias, rowvec=rowvec, rows_per_group=rpg, residual=residual,
-                    conv=conv, M=M, out_fp32=out_fp32)
+                    conv=conv, M=M, out_fp32=out_fp32, act=act)
 
 
 class _ConvFn(torch.autograd.Function):
@@ -167,13 +175,17 @@ def conv_dgrad(dy, geom, mod, stride):
     return raw.depth_to_space(out, NB, H, W, mod.cin)
 
 
-def conv3x3(x, geom, mod, *, rowvec=None, residual=None, x2=None, stride=1, out_fp32=False):
-    """y = conv3x3(x) + bias (+ rowvec per image) (+ residual) (+ x2 @ W_shortcut^T).  `mod` is a ConvPack."""
+def conv3x3(x, geom, mod, *, rowvec=None, residual=None, x2=None, stride=1, out_fp32=False, pad_mode="same", act=0):
+    """y = conv3x3(x) + bias (+ rowvec per image) (+ residual) (+ x2 @ W_shortcut^T).  `mod` is a ConvPack.
+    pad_mode="asym" (stride 2 only): the VAE encoder's Downsample2D(padding=0).  act=2: ReLU epilogue (no-grad only)."""
     if _grad_on(x, residual, x2):
+        if pad_mode != "same" or act:
+            raise NotImplementedError("gradients through the asymmetric stride-2 conv / fused ReLU are not needed by the "
+                                      "hot path (the VAE encoder is frozen and runs without a graph)")
         return _ConvFn.apply(x, residual, x2, mod, geom, stride, rowvec, out_fp32)
     p = mod.pack()
     shortcut = (x2, mod.pack_shortcut()) if x2 is not None else None
-    return _conv_fwd_raw(x, geom, p["w"], p["b"], rowvec, residual, shortcut, stride, mod.cin, out_fp32)
+    return _conv_fwd_raw(x, geom, p["w"], p["b"], rowvec, residual, shortcut, stride, mod.cin, out_fp32, pad_mode, act)
 
 
 class ConvPack:
@@ -512,7 +524,24 @@ def _lora_weight_grads(pack, lp, x, t, dy, dt):
     return grads
 
 
-def linear(x, pack: LinearPack, residual=None, want_stats=None, act=0, out_fp32=False):
+class StatsArena:
+    """Row-statistics buffers of one denoiser evaluation carved out of a few large zero-filled blocks: one memset per
+    block instead of one per producing GEMM (~210 per SDXL evaluation)."""
+
+    def __init__(self, device, block_rows=1 << 21):
+        self.device, self.block_rows = device, block_rows
+        self.block, self.off = None, 0
+
+    def take(self, M):
+        if self.block is None or self.off + M > self.block.shape[0]:
+            self.block = torch.zeros((max(self.block_rows, M), 2), device=self.device, dtype=torch.float32)
+            self.off = 0
+        out = self.block[self.off:self.off + M]
+        self.off += M
+        return out
+
+
+def linear(x, pack: LinearPack, residual=None, want_stats=None, act=0, out_fp32=False, arena: "StatsArena" = None):
     """y = act(x W^T + b (+LoRA)) (+residual).  want_stats None: return y.  True/False: return (y, stats) where stats
     are the [M,2] row statistics of y (fused into the GEMM epilogue) when requested and the no-grad, LoRA-free path is
     taken, else None."""
@@ -522,6 +551,10 @@ def linear(x, pack: LinearPack, residual=None, want_stats=None, act=0, out_fp32=
         return y if want_stats is None else (y, None)
     if want_stats and not pack.has_lora:
         p = pack.pack()
+        if arena is not None:
+            stats = arena.take(x.shape[0])
+            return raw.gemm(x, p["w"], bias=p["b"], residual=residual, rowstats=stats, act=act,
+                            rowstats_prezeroed=True), stats
         stats = torch.empty((x.shape[0], 2), device=x.device, dtype=torch.float32)
         return raw.gemm(x, p["w"], bias=p["b"], residual=residual, rowstats=stats, act=act), stats
     y = _linear_fwd_raw(x, pack, residual, act=act, out_fp32=out_fp32)[0]
@@ -708,6 +741,48 @@ def attention_cross(q, kv, H, head_dim=64, scale=None, kv_len=None):
         return _AttnCrossFn.apply(q, kv, H, head_dim, scale, kv_len)
     inner = H * head_dim
     return raw.attention_fwd(q, kv[..., :inner], kv[..., inner:], H, scale=scale, head_dim=head_dim, kv_len=kv_len)
+
+
+class _AttnBigHeadFn(torch.autograd.Function):
+    """Single-head attention with a head dim beyond the fused kernels' TMEM budget (the VAE mid block: 512 channels):
+    per image S = Q K^T and O = P V on fd_gemm around the row-softmax kernel; backward = the five matching GEMMs."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, B, scale):
+        rows, C = q.shape
+        N = rows // B
+        outs, probs = [], []
+        keep = any(ctx.needs_input_grad[:3])
+        for b in range(B):
+            sl = slice(b * N, (b + 1) * N)
+            P = raw.softmax_rows(raw.gemm(q[sl], k[sl]), scale)                # [N, N]
+            outs.append(raw.gemm(P, raw.transpose(v[sl].contiguous())))        # [N, C]
+            if keep:
+                probs.append(P)
+        ctx.meta = (B, N, scale)
+        ctx.save_for_backward(q, k, v, *probs)
+        return torch.cat(outs, dim=0) if B > 1 else outs[0]
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v, *probs = ctx.saved_tensors
+        B, N, scale = ctx.meta
+        do = do.contiguous()
+        dq, dk, dv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        for b in range(B):
+            sl = slice(b * N, (b + 1) * N)
+            P, dob = probs[b], do[sl]
+            dP = raw.gemm(dob, v[sl])                                           # dO V^T   [N, N]
+            raw.gemm(raw.transpose(P), raw.transpose(dob), out=dv[sl])          # P^T dO   [N, C]
+            dS = raw.softmax_rows_bwd(P, dP, scale)
+            raw.gemm(dS, raw.transpose(k[sl].contiguous()), out=dq[sl])         # dS K
+            raw.gemm(raw.transpose(dS), raw.transpose(q[sl].contiguous()), out=dk[sl])   # dS^T Q
+        return dq, dk, dv, None, None
+
+
+def attention_bighead(q, k, v, B, scale):
+    """q, k, v [B*N, C] bf16 (views with unit column stride) -> [B*N, C]; one head of C channels."""
+    return _AttnBigHeadFn.apply(q, k, v, B, scale)
 
 
 # ------------------------------------------------------------------------------------------------

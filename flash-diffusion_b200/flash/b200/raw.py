@@ -44,7 +44,7 @@ def gemm_workspace(device):
 
 def gemm(a1, b1, *, a2=None, b2=None, bias=None, rowvec=None, rows_per_group=0, geglu=False,
          residual=None, out=None, out_fp32=False, conv=None, M=None, force_bn=0, ln=None, rowstats=None,
-         act=0, rowscale=None, rows_per_group_scale=0):
+         act=0, rowscale=None, rows_per_group_scale=0, rowstats_prezeroed=False):
     """acc = a1 @ b1.T (+ a2 @ b2.T) with the fused epilogue of fd_gemm (include/flashb200.h).
 
     a1: [M, K1] bf16 (or, with conv=dict(NB_in,H,W,C,taps), an NHWC tensor), b1: [N, K1] bf16.
@@ -107,6 +107,7 @@ def gemm(a1, b1, *, a2=None, b2=None, bias=None, rowvec=None, rows_per_group=0, 
     if rowstats is not None:
         assert rowstats.dtype == torch.float32 and rowstats.shape == (M, 2) and rowstats.is_contiguous()
         args.rowstats_out = ptr(rowstats)
+        args.rowstats_prezeroed = 1 if rowstats_prezeroed else 0
     ws = gemm_workspace(a1.device)
     args.workspace, args.workspace_bytes = ptr(ws), ws.numel()
     check(lib.fd_gemm(byref(args), stream_ptr()), "fd_gemm")
@@ -318,6 +319,25 @@ def attention_bwd(q, k, v, o, lse, do, H, scale=None, dq=None, dk=None, dv=None,
             assert kv_len.dtype == torch.int32 and kv_len.numel() == B and kv_len.is_cuda
         check(lib.fd_attn_bwd_generic(byref(a), c_int32(head_dim), ptr(kv_len), stream_ptr()), "fd_attn_bwd_generic")
     return dq, dk, dv
+
+
+def softmax_rows(x, scale=1.0):
+    """bf16 [rows, L] -> softmax(scale * x) over the last dim (fd_softmax_rows)."""
+    lib = load(); _req(x, BF16, "x")
+    assert x.dim() == 2 and x.stride(1) == 1
+    y = torch.empty((x.shape[0], x.shape[1]), device=x.device, dtype=BF16)
+    check(lib.fd_softmax_rows(ptr(x), c_int64(x.stride(0)), ptr(y), c_int64(y.stride(0)), c_int32(x.shape[0]),
+                              c_int32(x.shape[1]), c_float(scale), stream_ptr()), "fd_softmax_rows")
+    return y
+
+
+def softmax_rows_bwd(p, dp, scale=1.0):
+    lib = load(); _req(p, BF16, "p"); _req(dp, BF16, "dp")
+    assert p.is_contiguous() and dp.is_contiguous() and p.shape == dp.shape
+    ds = torch.empty_like(p)
+    check(lib.fd_softmax_rows_bwd(ptr(p), ptr(dp), ptr(ds), c_int64(p.stride(0)), c_int32(p.shape[0]),
+                                  c_int32(p.shape[1]), c_float(scale), stream_ptr()), "fd_softmax_rows_bwd")
+    return ds
 
 
 # ------------------------------------------------------------------ layout / elementwise

@@ -94,6 +94,7 @@ class FlashDiffusion(BaseModel):
         # when on, those are skipped (loss[0] is returned as None) and the student runs without an autograd graph.
         self.elide_unused_generator_pass = False
         self.batch_cfg = True            # cond+uncond as one 2B call (output-preserving)
+        self.cache_teacher_kv = True     # cross-attention K/V of the text conditioning computed once per rollout
         self.dedupe_conditioning = True  # one conditioner pass when every ucg_rate is 0 (output-preserving)
 
     # ------------------------------------------------------------------ helpers (reference :127-177,:687-752)
@@ -160,9 +161,16 @@ class FlashDiffusion(BaseModel):
         return denoiser(sample=sample, timestep=timestep, conditioning=conditioning, **kw)
 
     def _teacher_pair(self, denoiser, sample, timestep, cond, uncond, clone=True, **kw):
-        """eps_cond, eps_uncond of the frozen teacher; one 2B call when batching is on."""
+        """eps_cond, eps_uncond of the frozen teacher; one 2B call when batching is on.  Consecutive calls with the same
+        conditioning objects (the K-step rollout, then the DMD teacher pair) re-use the cross-attention K/V projections
+        of the first one (`kv_cache`, output-preserving: they depend on the text conditioning only)."""
         if self.batch_cfg and cond is not None:
             B = sample.shape[0]
+            if (self.cache_teacher_kv and getattr(denoiser, "supports_kv_cache", False) and sample.is_cuda
+                    and not torch.is_grad_enabled() and "crossattn" in cond["cond"]):
+                key = (id(denoiser), id(cond["cond"]["crossattn"]), id(uncond["cond"]["crossattn"]), B)
+                kw = dict(kw, kv_cache="reuse" if self.__dict__.get("_kv_key") == key else "fill")
+                self.__dict__["_kv_key"] = key
             both = self._call_frozen(denoiser, torch.cat([sample, sample], dim=0),
                                      torch.cat([timestep, timestep], dim=0), _cat_conditioning(cond, uncond),
                                      clone=clone, **kw)
@@ -176,6 +184,7 @@ class FlashDiffusion(BaseModel):
         draws = draws or {}
         kwargs.pop("device", None)
         self.iter_steps += 1
+        self.__dict__["_kv_key"] = None          # new batch: cached teacher K/V are stale
         z = self._encode_inputs(batch) if self.vae is not None else batch[self.input_key]
 
         conditioning = self._get_conditioning(batch, set_ucg_rate_zero=True)
@@ -388,6 +397,7 @@ class FlashDiffusion(BaseModel):
     def sample(self, z, num_steps=20, guidance_scale=1.0, teacher_guidance_scale=5.0, conditioner_inputs=None,
                uncond_conditioner_inputs=None, max_samples=None, verbose=False, log_teacher_samples=False,
                adapter_conditioning_scale=1.0, generator=None):
+        self.__dict__["_kv_key"] = None          # cached K/V never outlive one call
         self.teacher_noise_scheduler.set_timesteps(num_steps)
         try:
             self.sampling_noise_scheduler.set_timesteps(timesteps=self.teacher_noise_scheduler.timesteps)
@@ -427,6 +437,7 @@ class FlashDiffusion(BaseModel):
                 eps = teacher_guidance_scale * eps_c + (1 - teacher_guidance_scale) * eps_u
                 ref = ts_sched.step(eps, t, ref, return_dict=False)[0]
             decoded_ref = self.vae.decode(ref) if self.vae is not None else ref
+        self.__dict__["_kv_key"] = None
         return decoded, decoded_ref
 
     # ------------------------------------------------------------------ sample logging (reference :917-1019)

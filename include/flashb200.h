@@ -89,7 +89,8 @@ typedef struct {
     /* LayerNorm fold */
     const float* ln_stats; const float* ln_colsum; float ln_inv_c; float ln_eps;
     float* rowstats_out;
-    /* DiT epilogue: act (0 none, 1 gelu-tanh) after the bias, then acc *= rowscale[row / rows_per_group_scale, :N]
+    int32_t rowstats_prezeroed;   /* 1: the caller already zeroed rowstats_out (one memset for a whole arena of them) */
+    /* DiT epilogue: act (0 none, 1 gelu-tanh, 2 ReLU) after the bias, then acc *= rowscale[row / rows_per_group_scale, :N]
      * (fp32, row stride ldrs) before the residual add — the AdaLN gate of PixArt / SD3 blocks
      * (UPSTREAM BasicTransformerBlock(ada_norm_single): hidden = gate * attn(...) + hidden). */
     int32_t act;
@@ -189,6 +190,14 @@ int fd_attn_bwd(const FdAttnBwdArgs* args, void* stream);
  * (Nq*Nkv <= 2^20), for which dq_accum is a scratch of 2*B*H*Nq*Nkv floats.  kv_len as in the forward.  Student LoRA backward of the SD1.5 UNet and the PixArt-alpha DiT (reference unets/unet.py:108-119,
  * transformers/tranformers.py:58-92). */
 int fd_attn_bwd_generic(const FdAttnBwdArgs* args, int32_t head_dim, const int32_t* kv_len, void* stream);
+
+/* Row softmax y = softmax(scale * x) over the last dim of a bf16 [rows, L] matrix (row strides ldx / ldy, L % 8 == 0)
+ * and its backward ds = p * (dp - sum(p * dp)) * scale.  Together with two fd_gemm calls (S = Q K^T, O = P V) this is
+ * the single-head, 512-channel attention of the VAE mid block (UPSTREAM diffusers AutoencoderKL, reference
+ * src/flash/models/vae/autoencoderKL.py:52-128), whose head dim is beyond what the fused attention kernels hold in TMEM. */
+int fd_softmax_rows(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t rows, int32_t L, float scale, void* stream);
+int fd_softmax_rows_bwd(const void* p, const void* dp, void* ds, int64_t ld, int32_t rows, int32_t L, float scale,
+                        void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Layout / small elementwise helpers.

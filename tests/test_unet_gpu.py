@@ -137,3 +137,26 @@ def test_sd15_lora_student_forward():
     x, t, cond = _inputs(2, 32, 32, 96, 0)
     with torch.no_grad():
         assert _rel(prod(x, t, cond), ora(x, t, cond)) < 2e-2
+
+
+def test_teacher_kv_cache_is_output_preserving():
+    """cross-attention K/V of the text conditioning computed by a "fill" evaluation and re-read by "reuse" evaluations
+    (the teacher's CFG rollout): same outputs as recomputing them, eagerly and through CUDA-graph replays."""
+    from flash.b200.graphs import GraphedDenoiser
+    prod, _ = _pair(SMALL)
+    prod.freeze()
+    x, t, cond = _inputs(2, 32, 32, 96, 48)
+    x2, t2, _ = _inputs(2, 32, 32, 96, 48, seed=9)
+    with torch.no_grad():
+        ref1, ref2 = prod(x, t, cond), prod(x2, t2, cond)
+        a = prod(x, t, cond, kv_cache="fill")
+        b = prod(x2, t2, cond, kv_cache="reuse")
+        assert _rel(a, ref1) < 1e-3 and _rel(b, ref2) < 1e-3, (_rel(a, ref1), _rel(b, ref2))
+        g = GraphedDenoiser(prod)
+        ga = g(x, t, cond, kv_cache="fill")
+        gb = g(x2, t2, cond, kv_cache="reuse")
+        gb2 = g(x2, t2, cond, kv_cache="reuse")
+        assert _rel(ga, ref1) < 1e-3 and _rel(gb, ref2) < 1e-3 and _rel(gb2, ref2) < 1e-3
+        assert len(g.graphs) == 2
+    with pytest.raises(ValueError):
+        prod(x, t, cond, kv_cache="bogus")
