@@ -717,8 +717,11 @@ extern "C" int fd_attn_fwd(const FdAttnArgs* a, void* stream_) {
     static const int variant = getenv("FD_ATTN_V") ? atoi(getenv("FD_ATTN_V")) : 1;
     if (variant == 1) {
         dim3 grid((a->Nq + 127) / 128, a->H, a->B);
-        // share of the exponentials on the FMA pipe in the inference forward (FD_ATTN_POLY = 4: 25 %, 3: 33 %, 2: 50 %)
-        static const int poly = getenv("FD_ATTN_POLY") ? atoi(getenv("FD_ATTN_POLY")) : 4;
+        // share of the exponentials on the FMA pipe in the inference forward (FD_ATTN_POLY = 4: 25 %, 3: 33 %, 2: 50 %).
+        // Measured on B200 (profiles/r02_attention.txt): with two CTAs per SM the all-MUFU loop is the fastest (531 /
+        // 710 TFLOP/s at 1024 / 4096 keys vs 507 / 690 at 25 %, and the 50 % variant falls off the register cliff),
+        // so the default is 0 and the training and inference forwards are the same kernel.
+        static const int poly = getenv("FD_ATTN_POLY") ? atoi(getenv("FD_ATTN_POLY")) : 0;
         if (a->lse != nullptr || poly == 0)
             attn_fwd1_kernel<0><<<grid, ATT1_THREADS, ATT1_SMEM, stream>>>(tq, tk, tv, p);
         else if (poly == 2)

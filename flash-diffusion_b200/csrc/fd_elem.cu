@@ -389,6 +389,173 @@ __global__ void softmax_rows_bwd_kernel(const bf16* __restrict__ p, const bf16* 
     }
 }
 
+
+// ---------------------------------------------------------------------------- LPIPS pieces (VGG16 feature stack)
+// 2x2 / stride-2 max pooling on NHWC bf16 (torchvision VGG16 `MaxPool2d(2, 2)`), 8 channels per thread.
+__global__ void maxpool2x2_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int NB, int H, int W, int C) {
+    const int Ho = H >> 1, Wo = W >> 1, nv = C >> 3;
+    const long long total = (long long)NB * Ho * Wo * nv;
+    FD_GRID_STRIDE(i, total) {
+        const int v = (int)(i % nv);
+        long long p = i / nv;
+        const int wo = (int)(p % Wo); p /= Wo;
+        const int ho = (int)(p % Ho);
+        const int n = (int)(p / Ho);
+        const bf16* base = x + (((long long)n * H + 2 * ho) * W + 2 * wo) * C + v * 8;
+        float a[8], b[8], c[8], d[8];
+        ld8(base, a); ld8(base + C, b); ld8(base + (long long)W * C, c); ld8(base + (long long)W * C + C, d);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = fmaxf(fmaxf(a[j], b[j]), fmaxf(c[j], d[j]));
+        st8(y + (((long long)n * Ho + ho) * Wo + wo) * C + v * 8, a);
+    }
+}
+// gradient of the above: dy goes to the FIRST maximum of each window in row-major order (torch's tie rule)
+__global__ void maxpool2x2_bwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, bf16* __restrict__ dx,
+                                      int NB, int H, int W, int C) {
+    const int Ho = H >> 1, Wo = W >> 1, nv = C >> 3;
+    const long long total = (long long)NB * Ho * Wo * nv;
+    FD_GRID_STRIDE(i, total) {
+        const int v = (int)(i % nv);
+        long long p = i / nv;
+        const int wo = (int)(p % Wo); p /= Wo;
+        const int ho = (int)(p % Ho);
+        const int n = (int)(p / Ho);
+        const long long o00 = (((long long)n * H + 2 * ho) * W + 2 * wo) * C + v * 8;
+        const long long offs[4] = {o00, o00 + C, o00 + (long long)W * C, o00 + (long long)W * C + C};
+        float f[4][8], g[8], out[4][8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ld8(x + offs[k], f[k]);
+        ld8(dy + (((long long)n * Ho + ho) * Wo + wo) * C + v * 8, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int best = 0;
+            float m = f[0][j];
+#pragma unroll
+            for (int k = 1; k < 4; ++k)
+                if (f[k][j] > m) { m = f[k][j]; best = k; }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) out[k][j] = (k == best) ? g[j] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) st8(dx + offs[k], out[k]);
+    }
+}
+// dx = dy where the ReLU output y is positive
+__global__ void relu_bwd_kernel(const bf16* __restrict__ y, const bf16* __restrict__ dy, bf16* __restrict__ dx,
+                                long long nvec) {
+    FD_GRID_STRIDE(i, nvec) {
+        float a[8], g[8];
+        ld8(y + i * 8, a);
+        ld8(dy + i * 8, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = a[j] > 0.f ? g[j] : 0.f;
+        st8(dx + i * 8, g);
+    }
+}
+
+// One LPIPS layer: out[n] += (1 / HW) sum_pixels sum_c w_c (f0_c / (|f0| + eps) - f1_c / (|f1| + eps))^2.
+// One warp per pixel (C <= 512: 16 channels per lane), block-level partial sums, one atomic per block and image.
+constexpr int LP_MAXV = 2;   // 8-channel vectors per lane: C <= 512
+__global__ void lpips_layer_kernel(const bf16* __restrict__ f0, const bf16* __restrict__ f1, const float* __restrict__ w,
+                                   float* __restrict__ out, int HW, int C, float inv_hw) {
+    __shared__ float sm[32];
+    const int n = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int nv = C >> 3;
+    float acc = 0.f;
+    for (int pix = blockIdx.x * nw + warp; pix < HW; pix += gridDim.x * nw) {
+        const long long off = ((long long)n * HW + pix) * C;
+        float a[LP_MAXV][8], b[LP_MAXV][8];
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < LP_MAXV; ++k) {
+            const int v = lane + k * 32;
+            if (v < nv) {
+                ld8(f0 + off + v * 8, a[k]);
+                ld8(f1 + off + v * 8, b[k]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { s0 += a[k][j] * a[k][j]; s1 += b[k][j] * b[k][j]; }
+            }
+        }
+        s0 = warp_sum(s0); s1 = warp_sum(s1);
+        const float i0 = 1.f / (sqrtf(s0) + 1e-10f), i1 = 1.f / (sqrtf(s1) + 1e-10f);
+#pragma unroll
+        for (int k = 0; k < LP_MAXV; ++k) {
+            const int v = lane + k * 32;
+            if (v < nv) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float d = a[k][j] * i0 - b[k][j] * i1;
+                    acc += __ldg(w + v * 8 + j) * d * d;
+                }
+            }
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) sm[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < nw; ++i) t += sm[i];
+        atomicAdd(out + n, t * inv_hw);
+    }
+}
+// gradient with respect to f0: with u = f0 / s, s = |f0| + eps, a_c = 2 w_c (u_c - g_c) gout[n] / HW:
+//   df0 = (a - u (a . u) s / |f0|) / s
+__global__ void lpips_layer_bwd_kernel(const bf16* __restrict__ f0, const bf16* __restrict__ f1,
+                                       const float* __restrict__ w, const float* __restrict__ gout,
+                                       bf16* __restrict__ df0, int HW, int C, float inv_hw) {
+    const int n = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int nv = C >> 3;
+    const float go = gout[n] * inv_hw;
+    for (int pix = blockIdx.x * nw + warp; pix < HW; pix += gridDim.x * nw) {
+        const long long off = ((long long)n * HW + pix) * C;
+        float a[LP_MAXV][8], b[LP_MAXV][8];
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < LP_MAXV; ++k) {
+            const int v = lane + k * 32;
+            if (v < nv) {
+                ld8(f0 + off + v * 8, a[k]);
+                ld8(f1 + off + v * 8, b[k]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { s0 += a[k][j] * a[k][j]; s1 += b[k][j] * b[k][j]; }
+            }
+        }
+        s0 = warp_sum(s0); s1 = warp_sum(s1);
+        const float n0 = sqrtf(s0);
+        const float i0 = 1.f / (n0 + 1e-10f), i1 = 1.f / (sqrtf(s1) + 1e-10f);
+        float dot = 0.f;
+#pragma unroll
+        for (int k = 0; k < LP_MAXV; ++k) {
+            const int v = lane + k * 32;
+            if (v < nv) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float u = a[k][j] * i0;
+                    const float g = 2.f * __ldg(w + v * 8 + j) * (u - b[k][j] * i1) * go;
+                    b[k][j] = g;              // a_c
+                    a[k][j] = u;              // u_c
+                    dot += g * u;
+                }
+            }
+        }
+        dot = warp_sum(dot);
+        const float corr = n0 > 0.f ? dot / (n0 * i0) : 0.f;       // (a . u) s / |f0|
+#pragma unroll
+        for (int k = 0; k < LP_MAXV; ++k) {
+            const int v = lane + k * 32;
+            if (v < nv) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = (b[k][j] - a[k][j] * corr) * i0;
+                st8(df0 + off + v * 8, o);
+            }
+        }
+    }
+}
+
 }  // namespace fd
 
 using namespace fd;
@@ -572,6 +739,52 @@ extern "C" int fd_softmax_rows_bwd(const void* p, const void* dp, void* ds, int6
     FD_CHECK_ARG(rows > 0 && L > 0 && L % 8 == 0 && ld % 8 == 0, "fd_softmax_rows_bwd: L / stride must be multiples of 8");
     fd::softmax_rows_bwd_kernel<<<rows, L >= 2048 ? 256 : 128, 0, (cudaStream_t)stream>>>(
         (const fd::bf16*)p, (const fd::bf16*)dp, (fd::bf16*)ds, ld, L, scale);
+    FD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int fd_maxpool2x2(const void* x, void* y, int32_t NB, int32_t H, int32_t W, int32_t C, void* stream) {
+    FD_CHECK_ARG(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "fd_maxpool2x2: C %% 8, even H / W");
+    const long long total = (long long)NB * (H / 2) * (W / 2) * (C / 8);
+    fd::maxpool2x2_kernel<<<fd::grid_for(total), 256, 0, (cudaStream_t)stream>>>((const fd::bf16*)x, (fd::bf16*)y, NB, H, W, C);
+    FD_CHECK_LAUNCH();
+    return 0;
+}
+extern "C" int fd_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int32_t NB, int32_t H, int32_t W, int32_t C,
+                                 void* stream) {
+    FD_CHECK_ARG(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "fd_maxpool2x2_bwd: C %% 8, even H / W");
+    const long long total = (long long)NB * (H / 2) * (W / 2) * (C / 8);
+    fd::maxpool2x2_bwd_kernel<<<fd::grid_for(total), 256, 0, (cudaStream_t)stream>>>(
+        (const fd::bf16*)x, (const fd::bf16*)dy, (fd::bf16*)dx, NB, H, W, C);
+    FD_CHECK_LAUNCH();
+    return 0;
+}
+extern "C" int fd_relu_bwd(const void* y, const void* dy, void* dx, int64_t n, void* stream) {
+    FD_CHECK_ARG(n % 8 == 0, "fd_relu_bwd: n %% 8");
+    fd::relu_bwd_kernel<<<fd::grid_for(n / 8), 256, 0, (cudaStream_t)stream>>>((const fd::bf16*)y, (const fd::bf16*)dy,
+                                                                               (fd::bf16*)dx, n / 8);
+    FD_CHECK_LAUNCH();
+    return 0;
+}
+extern "C" int fd_lpips_layer(const void* f0, const void* f1, const float* w, float* out, int32_t NB, int32_t HW,
+                              int32_t C, void* stream) {
+    FD_CHECK_ARG(C % 8 == 0 && C <= 8 * 32 * fd::LP_MAXV, "fd_lpips_layer: C=%d must be a multiple of 8, <= 512", C);
+    int gx = (HW + 7) / 8;
+    const int cap = (fd::num_sms() * 8 + NB - 1) / NB;
+    if (gx > cap) gx = cap;
+    fd::lpips_layer_kernel<<<dim3(gx, NB), 256, 0, (cudaStream_t)stream>>>((const fd::bf16*)f0, (const fd::bf16*)f1, w, out,
+                                                                           HW, C, 1.0f / (float)HW);
+    FD_CHECK_LAUNCH();
+    return 0;
+}
+extern "C" int fd_lpips_layer_bwd(const void* f0, const void* f1, const float* w, const float* gout, void* df0,
+                                  int32_t NB, int32_t HW, int32_t C, void* stream) {
+    FD_CHECK_ARG(C % 8 == 0 && C <= 8 * 32 * fd::LP_MAXV, "fd_lpips_layer_bwd: C=%d must be a multiple of 8, <= 512", C);
+    int gx = (HW + 7) / 8;
+    const int cap = (fd::num_sms() * 8 + NB - 1) / NB;
+    if (gx > cap) gx = cap;
+    fd::lpips_layer_bwd_kernel<<<dim3(gx, NB), 256, 0, (cudaStream_t)stream>>>(
+        (const fd::bf16*)f0, (const fd::bf16*)f1, w, gout, (fd::bf16*)df0, HW, C, 1.0f / (float)HW);
     FD_CHECK_LAUNCH();
     return 0;
 }

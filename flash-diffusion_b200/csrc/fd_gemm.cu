@@ -55,6 +55,7 @@ struct GemmKParams {
     int tail_first;       // sk == 0: tiles >= tail_first (the last, partial wave) are cut into tail_split column slices
     int tail_split;
     int tma_out;          // 1: bf16 output leaves through shared memory + TMA store (cp.async.bulk.tensor ... global)
+    int tma_res;          // 1: the residual chunk is TMA-loaded into the output staging buffer ahead of its use
 };
 
 template <int BN>
@@ -132,7 +133,7 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
 // row vector, activation, gate, GEGLU, residual).  With GEGLU the 16 outputs are v[0..15] (output column col0/2 + j).
 // Every lane of the warp runs it (rows >= M compute on zero accumulators and read nothing).
 __device__ __forceinline__ void epilogue_values(const GemmKParams& p, int row, int col0, const uint32_t (&r)[32],
-                                                const RowState& rs, float (&v)[32]) {
+                                                const RowState& rs, float (&v)[32], bool skip_residual = false) {
     const bool row_ok = row < p.M;
     const int N = p.N;
     const bool full = (col0 + 32 <= N);
@@ -216,7 +217,7 @@ __device__ __forceinline__ void epilogue_values(const GemmKParams& p, int row, i
         const int oc0 = col0 >> 1;
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = v[j] * gelu_erf_fast(v[16 + j]);
-        if (p.residual != nullptr && row_ok) {
+        if (p.residual != nullptr && row_ok && !skip_residual) {
             const bf16* rp = p.residual + (long long)row * p.ldr + oc0;
             if ((p.ldr & 7) == 0) {
                 const uint4* r4 = reinterpret_cast<const uint4*>(rp);
@@ -236,7 +237,7 @@ __device__ __forceinline__ void epilogue_values(const GemmKParams& p, int row, i
         }
         return;
     }
-    if (p.residual != nullptr && row_ok) {
+    if (p.residual != nullptr && row_ok && !skip_residual) {
         const bf16* rp = p.residual + (long long)row * p.ldr + col0;
         if (full && (p.ldr & 7) == 0) {
             const uint4* r4 = reinterpret_cast<const uint4*>(rp);
@@ -527,7 +528,7 @@ struct PairCfg {
     static constexpr int STAGES = (BN == 256) ? 6 : (BN == 160 ? 7 : 8);
     static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;   // power of two >= 2 accumulator stages
     static constexpr int OUT_STAGE_BYTES = 8 * 2 * 2048;            // 8 epilogue warps x 2 buffers x (32 rows x 64 B)
-    static constexpr int SMEM_BYTES = STAGES * (A_BYTES + BH_BYTES) + OUT_STAGE_BYTES + 256 + 1024;
+    static constexpr int SMEM_BYTES = STAGES * (A_BYTES + BH_BYTES) + OUT_STAGE_BYTES + 512 + 1024;
 };
 
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* src, int c0, int c1) {
@@ -614,7 +615,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1,
                  const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                  const __grid_constant__ CUtensorMap tmB1s, const __grid_constant__ CUtensorMap tmB2s,
-                 const __grid_constant__ CUtensorMap tmOut, const GemmKParams p) {
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmRes,
+                 const GemmKParams p) {
     using Cfg = PairCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -629,6 +631,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     uint64_t* tfull = bars + 2 * STAGES; // per CTA
     uint64_t* tempty = tfull + 2;        // used in the leader CTA only
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + 2);
+    uint64_t* res_bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(bars) + 256);   // [8 warps][2 buffers]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -643,6 +646,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
             tma_prefetch_desc(&tmB2);
         }
         if (p.tma_out) tma_prefetch_desc(&tmOut);
+        if (p.tma_res) tma_prefetch_desc(&tmRes);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -653,6 +657,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
             mbar_init(&tfull[a], 1);
             mbar_init(&tempty[a], 16);   // one arrival per epilogue warp (8) of each CTA
         }
+        for (int a = 0; a < 16; ++a) mbar_init(&res_bars[a], 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -770,6 +775,17 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         constexpr int NCH = BN / 32;
         uint8_t* my_stage = sOut + ew * 4096;
         uint32_t n_stored = 0;            // TMA stores issued by this warp (buffer = n_stored & 1)
+        // RESIDUAL PREFETCH (tma_res): the residual chunk a store will need is TMA-loaded into that store's staging
+        // buffer ahead of time — the first chunk of a tile before the wait for the accumulator (i.e. during the main
+        // loop), chunk c+1 while chunk c is processed — so the epilogue never sits on a global-load latency (ncu r02:
+        // 12-25 % of the samples of the residual GEMMs were long-scoreboard stalls on exactly that load).
+        uint64_t* my_res = res_bars + ew * 2;
+        uint32_t res_phase = 0;           // bit b: parity to wait for on my_res[b]
+        auto issue_res = [&](uint32_t k, int col0, int row0) {     // lane 0: residual of stored-chunk number k
+            const uint32_t b = k & 1u;
+            mbar_arrive_expect_tx(&my_res[b], 2048);
+            tma_load_2d(&tmRes, &my_res[b], my_stage + b * 2048, col0, row0);
+        };
         const int n_out = p.geglu ? (p.N >> 1) : p.N;
         float* ws_mine = p.sk_ws + ((size_t)pair_id * 2 + rank) * (size_t)(BM * BN);
         int acc = 0;
@@ -782,6 +798,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
             const int nch = NCH / wi.nsub, split = (nch + 1) / 2;
             const int c_lo = half ? split : 0, c_hi = half ? nch : split;
             const int col_base = nt * BN + wi.sub * (BN / wi.nsub);
+            const int row0 = mt2 * 2 * BM + (int)rank * BM + q * 32;
+            if (p.tma_res && kb0 == 0 && c_lo < c_hi && col_base + c_lo * 32 < p.N) {
+                if (lane == 0) {
+                    tma_store_wait_read<1>();                    // the store that last used this buffer has read it
+                    issue_res(n_stored, col_base + c_lo * 32, row0);
+                }
+            }
             mbar_wait(&tfull[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
@@ -845,11 +868,31 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
                         epilogue_chunk(p, row, col0, r, rs);
                         continue;
                     }
+                    if (p.tma_res && lane == 0 && c + 1 < c_hi && col0 + 32 < p.N) {
+                        tma_store_wait_read<0>();                 // store n_stored-1 has read the other buffer
+                        issue_res(n_stored + 1, col0 + 32, row0);
+                    }
                     float v[32];
-                    epilogue_values(p, row, col0, r, rs, v);
+                    epilogue_values(p, row, col0, r, rs, v, p.tma_res != 0);
                     uint32_t pk[16];
                     uint8_t* buf = my_stage + (n_stored & 1u) * 2048;
-                    if (n_stored >= 2) {                          // the store issued from this buffer has read it
+                    if (p.tma_res) {
+                        const uint32_t b = n_stored & 1u;
+                        mbar_wait(&my_res[b], (res_phase >> b) & 1u);
+                        res_phase ^= 1u << b;
+                        const uint8_t* src = buf + lane * 64;
+                        const int sw = (lane >> 1) & 3;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 u = *reinterpret_cast<const uint4*>(src + ((j ^ sw) << 4));
+                            float2 f;
+                            f = unpack_bf16x2(u.x); v[8 * j + 0] += f.x; v[8 * j + 1] += f.y;
+                            f = unpack_bf16x2(u.y); v[8 * j + 2] += f.x; v[8 * j + 3] += f.y;
+                            f = unpack_bf16x2(u.z); v[8 * j + 4] += f.x; v[8 * j + 5] += f.y;
+                            f = unpack_bf16x2(u.w); v[8 * j + 6] += f.x; v[8 * j + 7] += f.y;
+                        }
+                        __syncwarp();                             // every lane has read before anyone overwrites
+                    } else if (n_stored >= 2) {                   // the store issued from this buffer has read it
                         if (lane == 0) tma_store_wait_read<1>();
                         __syncwarp();
                     }
@@ -958,7 +1001,8 @@ static bool use_pdl() {
 template <int BN>
 static int launch_gemm_pair(const CUtensorMap& tA1, const CUtensorMap& tB1, const CUtensorMap& tA2,
                             const CUtensorMap& tB2, const CUtensorMap& tB1s, const CUtensorMap& tB2s,
-                            const CUtensorMap& tOut, const GemmKParams& p, int pairs, cudaStream_t stream, bool pdl) {
+                            const CUtensorMap& tOut, const CUtensorMap& tRes, const GemmKParams& p, int pairs,
+                            cudaStream_t stream, bool pdl) {
     using Cfg = PairCfg<BN>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -981,7 +1025,7 @@ static int launch_gemm_pair(const CUtensorMap& tA1, const CUtensorMap& tB1, cons
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 2 : 1;
-    FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<BN>, tA1, tB1, tA2, tB2, tB1s, tB2s, tOut, p));
+    FD_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_pair_kernel<BN>, tA1, tB1, tA2, tB2, tB1s, tB2s, tOut, tRes, p));
     FD_CHECK_LAUNCH();
     return 0;
 }
@@ -1147,7 +1191,7 @@ extern "C" int fd_gemm(const FdGemmArgs* a, void* stream_) {
         tB2 = tB1;
     }
     // pair kernel: work split (tail column slices or hybrid stream-K) and TMA-store epilogue
-    CUtensorMap tOut = tA1, tB1s = tB1, tB2s = tB2;
+    CUtensorMap tOut = tA1, tRes = tA1, tB1s = tB1, tB2s = tB2;
     int pairs = 0;
     if (pair) {
         const int tiles = ((a->M + 2 * BM - 1) / (2 * BM)) * p.num_n_tiles;
@@ -1208,6 +1252,13 @@ extern "C" int fd_gemm(const FdGemmArgs* a, void* stream_) {
             rc = encode_tmap_bf16_sw(&tOut, a->out, 2, dims, str, box, a->geglu ? 32 : 64);
             if (rc) return rc;
             p.tma_out = 1;
+            static const bool env_no_tma_res = getenv("FD_NO_TMA_RES") != nullptr;
+            if (a->residual && !a->geglu && !env_no_tma_res && (a->ldr % 8) == 0 && ((uintptr_t)a->residual & 15) == 0) {
+                const uint64_t rstr[1] = {(uint64_t)a->ldr * 2};
+                rc = encode_tmap_bf16_sw(&tRes, a->residual, 2, dims, rstr, box, 64);
+                if (rc) return rc;
+                p.tma_res = 1;
+            }
         }
     }
     ProfScope prof(stream, a->conv_taps > 0 ? PROF_CONV : PROF_GEMM,
@@ -1217,9 +1268,9 @@ extern "C" int fd_gemm(const FdGemmArgs* a, void* stream_) {
     // the programmatic edge needs a KERNEL as the previous stream operation: not after the row-statistics memset
     const bool pdl = use_pdl() && a->rowstats_out == nullptr && !profiling_on();
     if (pair) {
-        if (BN == 256) return launch_gemm_pair<256>(tA1, tB1, tA2, tB2, tB1s, tB2s, tOut, p, pairs, stream, pdl);
-        if (BN == 160) return launch_gemm_pair<160>(tA1, tB1, tA2, tB2, tB1s, tB2s, tOut, p, pairs, stream, pdl);
-        return launch_gemm_pair<128>(tA1, tB1, tA2, tB2, tB1s, tB2s, tOut, p, pairs, stream, pdl);
+        if (BN == 256) return launch_gemm_pair<256>(tA1, tB1, tA2, tB2, tB1s, tB2s, tOut, tRes, p, pairs, stream, pdl);
+        if (BN == 160) return launch_gemm_pair<160>(tA1, tB1, tA2, tB2, tB1s, tB2s, tOut, tRes, p, pairs, stream, pdl);
+        return launch_gemm_pair<128>(tA1, tB1, tA2, tB2, tB1s, tB2s, tOut, tRes, p, pairs, stream, pdl);
     }
     if (BN == 256) return launch_gemm<256>(tA1, tB1, tA2, tB2, p, stream, pdl);
     if (BN == 128) return launch_gemm<128>(tA1, tB1, tA2, tB2, p, stream, pdl);

@@ -340,6 +340,48 @@ def softmax_rows_bwd(p, dp, scale=1.0):
     return ds
 
 
+def maxpool2x2(x, NB, H, W, C):
+    lib = load(); _req(x, BF16, "x")
+    assert x.is_contiguous()
+    y = torch.empty((NB * (H // 2) * (W // 2), C), device=x.device, dtype=BF16)
+    check(lib.fd_maxpool2x2(ptr(x), ptr(y), c_int32(NB), c_int32(H), c_int32(W), c_int32(C), stream_ptr()), "fd_maxpool2x2")
+    return y
+
+
+def maxpool2x2_bwd(x, dy, NB, H, W, C):
+    lib = load(); _req(x, BF16, "x"); _req(dy, BF16, "dy")
+    assert x.is_contiguous() and dy.is_contiguous()
+    dx = torch.empty_like(x)
+    check(lib.fd_maxpool2x2_bwd(ptr(x), ptr(dy), ptr(dx), c_int32(NB), c_int32(H), c_int32(W), c_int32(C), stream_ptr()),
+          "fd_maxpool2x2_bwd")
+    return dx
+
+
+def relu_bwd(y, dy):
+    lib = load(); _req(y, BF16, "y"); _req(dy, BF16, "dy")
+    assert y.is_contiguous() and dy.is_contiguous() and y.shape == dy.shape
+    dx = torch.empty_like(y)
+    check(lib.fd_relu_bwd(ptr(y), ptr(dy), ptr(dx), c_int64(y.numel()), stream_ptr()), "fd_relu_bwd")
+    return dx
+
+
+def lpips_layer(f0, f1, w, out, NB, HW, C):
+    """out[n] += LPIPS distance of one feature layer (out fp32 [NB], accumulated in place)."""
+    lib = load(); _req(f0, BF16, "f0"); _req(f1, BF16, "f1"); _req(w, torch.float32, "w"); _req(out, torch.float32, "out")
+    assert f0.is_contiguous() and f1.is_contiguous() and f0.shape == f1.shape and w.numel() == C and out.numel() == NB
+    check(lib.fd_lpips_layer(ptr(f0), ptr(f1), ptr(w), ptr(out), c_int32(NB), c_int32(HW), c_int32(C), stream_ptr()),
+          "fd_lpips_layer")
+    return out
+
+
+def lpips_layer_bwd(f0, f1, w, gout, NB, HW, C):
+    lib = load(); _req(f0, BF16, "f0"); _req(f1, BF16, "f1"); _req(gout, torch.float32, "gout")
+    df0 = torch.empty_like(f0)
+    check(lib.fd_lpips_layer_bwd(ptr(f0), ptr(f1), ptr(w), ptr(gout.contiguous()), ptr(df0), c_int32(NB), c_int32(HW),
+                                 c_int32(C), stream_ptr()), "fd_lpips_layer_bwd")
+    return df0
+
+
 # ------------------------------------------------------------------ layout / elementwise
 def nchw_to_nhwc(x, Cpad):
     lib = load(); _req(x, torch.float32, "x")

@@ -69,9 +69,12 @@ class FlashDiffusion(BaseModel):
             self.use_adversarial_loss = False
         self.disc_backbone = self.teacher_denoiser
         if self.distill_loss_type == "lpips":
-            raise NotImplementedError(
-                "distill_loss_type='lpips' needs LPIPS-VGG + VAE decoder weights that are not available offline "
-                "(SURVEY.md §8f-2, NEXT row); use 'l2' or 'l1'")
+            # reference :102-103 `lpips.LPIPS(net="vgg")`; here the VGG16 stack runs on the B200 conv kernels.  The
+            # published VGG / lin weights are not available offline: random-init unless a state dict is loaded.
+            from ..lpips import LPIPS
+            if self.vae is None:
+                raise ValueError("distill_loss_type='lpips' decodes the latents: a VAE is required (reference :393-394)")
+            self.lpips = LPIPS(net="vgg")
         if adapter is not None:
             raise NotImplementedError("T2I adapters are out of scope of the B200 hot path (SURVEY.md §2 row 7)")
         self.K_steps = np.cumsum(self.num_iterations_per_K)
@@ -166,7 +169,7 @@ class FlashDiffusion(BaseModel):
         of the first one (`kv_cache`, output-preserving: they depend on the text conditioning only)."""
         if self.batch_cfg and cond is not None:
             B = sample.shape[0]
-            if (self.cache_teacher_kv and getattr(denoiser, "supports_kv_cache", False) and sample.is_cuda
+            if (getattr(self, "cache_teacher_kv", False) and getattr(denoiser, "supports_kv_cache", False) and sample.is_cuda
                     and not torch.is_grad_enabled() and "crossattn" in cond["cond"]):
                 key = (id(denoiser), id(cond["cond"]["crossattn"]), id(uncond["cond"]["crossattn"]), B)
                 kw = dict(kw, kv_cache="reuse" if self.__dict__.get("_kv_key") == key else "fill")
@@ -297,6 +300,16 @@ class FlashDiffusion(BaseModel):
             return torch.mean(((student_output - teacher_output) ** 2).reshape(student_output.shape[0], -1), 1).mean()
         if self.distill_loss_type == "l1":
             return torch.mean(torch.abs(student_output - teacher_output).reshape(student_output.shape[0], -1), 1).mean()
+        if self.distill_loss_type == "lpips":
+            # reference :383-397 — center crop 64x64 latents, decode both, clamp, LPIPS-VGG, mean
+            ch = (student_output.shape[2] - 64) // 2
+            cw = (student_output.shape[3] - 64) // 2
+            s_crop = student_output[:, :, ch:ch + 64, cw:cw + 64]
+            t_crop = teacher_output[:, :, ch:ch + 64, cw:cw + 64]
+            decoded_student = self.vae.decode(s_crop).clamp(-1, 1)
+            with torch.no_grad():
+                decoded_teacher = self.vae.decode(t_crop).clamp(-1, 1)
+            return self.lpips(decoded_student, decoded_teacher).mean()
         raise NotImplementedError(f"Loss type {self.distill_loss_type} not implemented")
 
     def _dmd_loss(self, student_output, student_conditioning, conditioning, unconditional_conditioning,

@@ -199,6 +199,21 @@ int fd_softmax_rows(const void* x, int64_t ldx, void* y, int64_t ldy, int32_t ro
 int fd_softmax_rows_bwd(const void* p, const void* dp, void* ds, int64_t ld, int32_t rows, int32_t L, float scale,
                         void* stream);
 
+/* LPIPS-VGG pieces of the `distill_loss_type="lpips"` objective (reference flash_diffusion_model.py:102-103,383-397;
+ * lpips==0.1.4 restated in oracle/lpips.py): the VGG16 convolutions run on fd_gemm (conv mode, act = 2 ReLU), these are
+ * the rest.  NHWC bf16 feature maps.
+ *   fd_maxpool2x2 / _bwd   2x2 stride-2 max pooling and its gradient (first maximum wins, as torch)
+ *   fd_relu_bwd            dx = dy where the ReLU output y > 0
+ *   fd_lpips_layer         out[n] += mean_pixels sum_c w[c] (f0/(|f0|+1e-10) - f1/(|f1|+1e-10))^2   (out is NOT zeroed)
+ *   fd_lpips_layer_bwd     df0 given gout[n] = dL/dout[n] */
+int fd_maxpool2x2(const void* x, void* y, int32_t NB, int32_t H, int32_t W, int32_t C, void* stream);
+int fd_maxpool2x2_bwd(const void* x, const void* dy, void* dx, int32_t NB, int32_t H, int32_t W, int32_t C, void* stream);
+int fd_relu_bwd(const void* y, const void* dy, void* dx, int64_t n, void* stream);
+int fd_lpips_layer(const void* f0, const void* f1, const float* w, float* out, int32_t NB, int32_t HW, int32_t C,
+                   void* stream);
+int fd_lpips_layer_bwd(const void* f0, const void* f1, const float* w, const float* gout, void* df0, int32_t NB,
+                       int32_t HW, int32_t C, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Layout / small elementwise helpers.
  * ------------------------------------------------------------------------------------------ */

