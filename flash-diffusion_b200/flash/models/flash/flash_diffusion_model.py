@@ -185,22 +185,23 @@ class FlashDiffusion(BaseModel):
     def forward(self, batch: Dict[str, Any], batch_idx=0, step=0, draws: Optional[Dict[str, Any]] = None,
                 *args, **kwargs):
         draws = draws or {}
-        kwargs.pop("device", None)
+        device = kwargs.pop("device", None)
+        ckw = {} if device is None else {"device": device}     # the text conditioners take the device (reference :188-205)
         self.iter_steps += 1
         self.__dict__["_kv_key"] = None          # new batch: cached teacher K/V are stale
         z = self._encode_inputs(batch) if self.vae is not None else batch[self.input_key]
 
-        conditioning = self._get_conditioning(batch, set_ucg_rate_zero=True)
+        conditioning = self._get_conditioning(batch, set_ucg_rate_zero=True, **ckw)
         if self.dedupe_conditioning and self._ucg_is_deterministic():
             student_conditioning = conditioning
         else:
-            student_conditioning = self._get_conditioning(batch)
+            student_conditioning = self._get_conditioning(batch, **ckw)
         if self.use_empty_prompt and "text" in self.ucg_keys:
-            uncond_batch = deepcopy(batch)
+            uncond_batch = dict(batch)
             uncond_batch["text"] = [""] * len(batch["text"])
-            unconditional_conditioning = self._get_conditioning(uncond_batch, set_ucg_rate_zero=True)
+            unconditional_conditioning = self._get_conditioning(uncond_batch, set_ucg_rate_zero=True, **ckw)
         else:
-            unconditional_conditioning = self._get_conditioning(batch, ucg_keys=self.ucg_keys)
+            unconditional_conditioning = self._get_conditioning(batch, ucg_keys=self.ucg_keys, **ckw)
 
         if self.iter_steps > self.K_steps[-1]:
             K_step = len(self.K) - 1
@@ -417,11 +418,11 @@ class FlashDiffusion(BaseModel):
         except Exception:
             self.sampling_noise_scheduler.set_timesteps(num_steps)
         sample = z
-        conditioning = self._get_conditioning(conditioner_inputs, set_ucg_rate_zero=True)
+        conditioning = self._get_conditioning(conditioner_inputs, set_ucg_rate_zero=True, device=z.device)
         if uncond_conditioner_inputs is not None:
-            unconditional = self._get_conditioning(uncond_conditioner_inputs, set_ucg_rate_zero=True)
+            unconditional = self._get_conditioning(uncond_conditioner_inputs, set_ucg_rate_zero=True, device=z.device)
         else:
-            unconditional = self._get_conditioning(conditioner_inputs, ucg_keys=self.ucg_keys)
+            unconditional = self._get_conditioning(conditioner_inputs, ucg_keys=self.ucg_keys, device=z.device)
         if max_samples is not None:
             sample = sample[:max_samples]
             if conditioning:

@@ -319,6 +319,67 @@ class LCMScheduler(_SchedulerBase):
         return (prev, denoised)
 
 
+class EulerDiscreteScheduler(_SchedulerBase):
+    """diffusers `EulerDiscreteScheduler` (epsilon prediction) — the `TEACHER_SAMPLING_SCHEDULER` of the example yamls,
+    used only to draw the teacher's reference samples in `log_samples` (reference flash_diffusion_model.py:866-913):
+    sigma_i = sqrt((1 - abar_t) / abar_t) on the spaced timesteps, final sigma 0; the sample lives in sigma space
+    (`init_noise_sigma = sqrt(sigma_max^2 + 1)` for leading/trailing spacing, `scale_model_input` divides by
+    sqrt(sigma^2 + 1)); step: x += (sigma_next - sigma) * eps."""
+
+    def __init__(self, timestep_spacing="leading", **kw):
+        super().__init__(timestep_spacing=timestep_spacing, **kw)
+        self._step_index = None
+        self.set_timesteps(self.config.num_train_timesteps)
+
+    def set_timesteps(self, num_inference_steps=None, device=None, timesteps=None):
+        if timesteps is not None:
+            ts = np.array(timesteps, dtype=np.int64)
+        else:
+            ts = np.clip(_spaced_timesteps(self.config.num_train_timesteps, num_inference_steps,
+                                           self.config.timestep_spacing, self.config.steps_offset),
+                         0, self.config.num_train_timesteps - 1)
+        self.num_inference_steps = len(ts)
+        ac = self.alphas_cumprod.double().numpy()
+        sig = np.sqrt((1 - ac) / ac)[ts]
+        self.sigmas = torch.from_numpy(np.concatenate([sig, [0.0]]))
+        self.timesteps = torch.from_numpy(ts)
+        smax = float(self.sigmas.max())
+        self.init_noise_sigma = smax if self.config.timestep_spacing == "linspace" else (smax * smax + 1.0) ** 0.5
+        self._step_index = None
+
+    def _idx(self, timestep):
+        if self._step_index is None:
+            hits = (self.timesteps == int(timestep)).nonzero()
+            self._step_index = int(hits[0]) if len(hits) else 0
+        return self._step_index
+
+    def scale_model_input(self, sample, timestep=None):
+        s = float(self.sigmas[self._idx(timestep)])
+        return sample / (s * s + 1.0) ** 0.5
+
+    def step(self, model_output, timestep, sample, return_dict=False, generator=None, **kw):
+        i = self._idx(timestep)
+        s, s_next = float(self.sigmas[i]), float(self.sigmas[i + 1])
+        prev = sample + (s_next - s) * model_output
+        self._step_index = i + 1
+        return (prev,)
+
+
+class EulerAncestralDiscreteScheduler(EulerDiscreteScheduler):
+    """ancestral variant: deterministic step to sigma_down, then fresh noise of scale sigma_up."""
+
+    def step(self, model_output, timestep, sample, return_dict=False, generator=None, **kw):
+        i = self._idx(timestep)
+        s, s_next = float(self.sigmas[i]), float(self.sigmas[i + 1])
+        up = (s_next ** 2 * (s ** 2 - s_next ** 2) / s ** 2) ** 0.5 if s > 0 else 0.0
+        down = (s_next ** 2 - up ** 2) ** 0.5
+        prev = sample + (down - s) * model_output
+        if up > 0:
+            prev = prev + up * torch.randn(sample.shape, generator=generator, device=sample.device, dtype=sample.dtype)
+        self._step_index = i + 1
+        return (prev,)
+
+
 class FlowMatchEulerDiscreteScheduler:
     """Rectified-flow Euler scheduler used by the SD3 recipe (reference examples/train_flash_sd3.py:123-141,
     consumed at src/flash/models/flash_sd3/flash_diffusion_model.py:253-324 and :1043-1060).
