@@ -472,6 +472,32 @@ def run_ours(args):
         cnt = (ctypes.c_longlong * 4)()
         lib.fd_profile_summary(ms, fl, cnt, 4)
         g_ms, g_fl, g_n = ms[0] + ms[1], fl[0] + fl[1], cnt[0] + cnt[1]
+        # the r01 definition, for comparison: the GEMM / conv launches of ONE 2B teacher evaluation (the op that is
+        # ~83 % of a step), eager, same event pairs
+        teacher_eval = None
+        if hasattr(model, "_teacher_pair") and hasattr(model, "conditioner") and args.config == "sdxl":
+            if had is not None:
+                model.use_cuda_graphs = False
+            lib.fd_profile_enable(1)
+            with torch.no_grad():
+                b0 = resident[0]
+                cond = model.conditioner(b0, set_ucg_rate_zero=True)
+                unc = model.conditioner(b0, ucg_keys=model.ucg_keys)
+                model.__dict__["_kv_key"] = None
+                model._teacher_pair(model.teacher_denoiser, b0["image"], torch.full((B,), 500, device=dev), cond, unc)
+            torch.cuda.synchronize()
+            lib.fd_profile_enable(0)
+            if had is not None:
+                model.use_cuda_graphs = had
+            ms2 = (ctypes.c_double * 4)()
+            fl2 = (ctypes.c_double * 4)()
+            cnt2 = (ctypes.c_longlong * 4)()
+            lib.fd_profile_summary(ms2, fl2, cnt2, 4)
+            t_ms, t_fl = ms2[0] + ms2[1], fl2[0] + fl2[1]
+            if t_ms > 0:
+                teacher_eval = {"achieved_tflops": t_fl / (t_ms / 1e3) / 1e12, "frac": t_fl / (t_ms / 1e3) / 1e12 / peak_tf,
+                                "launches": int(cnt2[0] + cnt2[1]),
+                                "attention_fwd_tflops": (fl2[2] / (ms2[2] / 1e3) / 1e12) if ms2[2] > 0 else None}
         ach = g_fl / (g_ms / 1e3) / 1e12 if g_ms > 0 else 0.0
         traffic = None
         try:
@@ -493,6 +519,7 @@ def run_ours(args):
                                   "launches": int(cnt[2]), "frac": (fl[2] / (ms[2] / 1e3) / 1e12 / peak_tf) if ms[2] > 0 else None},
                 "attention_bwd": {"achieved_tflops": (fl[3] / (ms[3] / 1e3) / 1e12) if ms[3] > 0 else None,
                                   "launches": int(cnt[3])},
+                "teacher_evaluation": teacher_eval,
                 "tensor_core_flops_in_profiled_step": step_flops_profiled,
                 "per_launch_csv": os.path.relpath(dump, ROOT) if dump else None}
         if args.config == "sdxl":

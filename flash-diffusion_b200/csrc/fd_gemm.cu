@@ -116,17 +116,18 @@ __device__ __forceinline__ void stats_of_bf16x2(uint32_t u, RowState& rs) {
 // The GEGLU GEMMs (8192x10240x1280, 32768x5120x640: 21 % of a teacher evaluation) evaluate it 128 times per thread
 // per tile, which made their epilogue as long as the K = 640 main loop.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
-    const float z = fabsf(x) * 0.70710678118654752440f;
-    const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+    // x Phi(x) with Phi by A&S 26.2.17 (= 7.1.26 at x / sqrt2): t = 1 / (1 + p |x| / sqrt2), Phi(|x|) = 1 - poly(t) e^{-x^2/2}
+    const float ax = fabsf(x);
+    float t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.23164190f, ax, 1.0f)));      // 0.3275911 / sqrt(2)
     float poly = fmaf(1.061405429f, t, -1.453152027f);
     poly = fmaf(poly, t, 1.421413741f);
     poly = fmaf(poly, t, -0.284496736f);
     poly = fmaf(poly, t, 0.254829592f);
     poly *= t;
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * z * z));
-    const float erf_abs = fmaf(-poly, e, 1.0f);                 // erf(|x|/sqrt2)
-    return 0.5f * fmaf(fabsf(x), erf_abs, x);                   // 0.5 x (1 + sign(x) erf(|x|/sqrt2))
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752f));             // e^{-x^2/2}
+    const float erf_abs = fmaf(-poly, e, 1.0f);                 // erf(|x| / sqrt2)
+    return 0.5f * fmaf(ax, erf_abs, x);                         // 0.5 x (1 + sign(x) erf(|x| / sqrt2))
 }
 
 // Epilogue stage 1: r = acc[row, col0 .. col0+31] (fp32 bit patterns) -> v = final fp32 outputs (LayerNorm fold, bias,
@@ -140,6 +141,21 @@ __device__ __forceinline__ void epilogue_values(const GemmKParams& p, int row, i
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
 
+    if (p.ln_stats != nullptr && p.bias != nullptr && full) {
+        // LayerNorm(x) W^T + b' = rstd * acc + (-rstd * mean * colsum(W') + b'): two FMAs per element
+        const float rstd = rs.ln_rstd, nmr = -rs.ln_mean * rs.ln_rstd;
+        const float4* c4 = reinterpret_cast<const float4*>(p.ln_colsum + col0);
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 c = __ldg(c4 + j);
+            const float4 b = __ldg(b4 + j);
+            v[4 * j + 0] = fmaf(v[4 * j + 0], rstd, fmaf(nmr, c.x, b.x));
+            v[4 * j + 1] = fmaf(v[4 * j + 1], rstd, fmaf(nmr, c.y, b.y));
+            v[4 * j + 2] = fmaf(v[4 * j + 2], rstd, fmaf(nmr, c.z, b.z));
+            v[4 * j + 3] = fmaf(v[4 * j + 3], rstd, fmaf(nmr, c.w, b.w));
+        }
+    } else {
     if (p.ln_stats != nullptr) {
         // LayerNorm(x) W^T = rstd * (x W'^T - mean * colsum(W'))
         const float nm = -rs.ln_mean;
@@ -175,6 +191,7 @@ __device__ __forceinline__ void epilogue_values(const GemmKParams& p, int row, i
             for (int j = 0; j < 32; ++j)
                 if (col0 + j < N) v[j] += __ldg(p.bias + col0 + j);
         }
+    }
     }
     if (p.rowvec != nullptr && row_ok) {
         const float* rv = p.rowvec + (long long)(row / p.rows_per_group) * p.ldrv + col0;
