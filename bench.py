@@ -649,8 +649,13 @@ def run_sample(args):
         except torch.cuda.OutOfMemoryError:
             break
         ms = e0.elapsed_time(e1) / n
-        bytes_alg = 4 * wbytes + 4 * 2 * (2 * B) * shape[0] * shape[1] * shape[2] * 4
-        rows.append({"batch": B, "latency_ms": ms, "images_per_s": B / ms * 1e3, "tflops": 8 * B * fwd / ms / 1e9,
+        calls = 4                                   # one (2B- or B-batched) denoiser call per step
+        bytes_alg = calls * wbytes + calls * 2 * (2 * B) * shape[0] * shape[1] * shape[2] * 4
+        # denoiser evaluations per sample(): 4 steps x (cond + uncond) as the reference's loop does; the SD3 class skips the
+        # unconditional branch when guidance_scale == 1 (it is multiplied by exactly 0): 4 evaluations
+        n_eval = 4 if which == "sd3" else 8
+        rows.append({"batch": B, "latency_ms": ms, "images_per_s": B / ms * 1e3, "tflops": n_eval * B * fwd / ms / 1e9,
+                     "denoiser_evaluations": n_eval,
                      "hbm_gbs": bytes_alg / ms / 1e6, "hbm_frac_of_peak": bytes_alg / ms / 1e6 / peak_hbm})
     launches = lib.fd_launch_count() + graphs.REPLAYED_LAUNCHES - l0
     r1 = rows[0]
