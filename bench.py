@@ -468,18 +468,21 @@ def run_ours(args):
     # every tensor-core launch of the step — teacher rollout, DMD, GAN backbone, LoRA student forward AND backward —
     # sits between two CUDA events on its launch stream (fd_profile_enable).  Same kernels, same shapes, same data as
     # the timed steps; the graph replays of the timed steps cannot carry per-kernel events.
+    # EVERY rank runs this step (its gradient all-reduce is a collective); only rank 0 carries the event pairs.
     roof = None
+    had = getattr(model, "use_cuda_graphs", None)
+    if had is not None:
+        model.use_cuda_graphs = False
+    if rank == 0:
+        lib.fd_profile_enable(1)
+    step(resident[0], 3)
+    torch.cuda.synchronize()
+    if rank == 0:
+        lib.fd_profile_enable(0)
+    if had is not None:
+        model.use_cuda_graphs = had
     if rank == 0:
         peak_tf, peak_hbm, peak_src = peaks()
-        had = getattr(model, "use_cuda_graphs", None)
-        if had is not None:
-            model.use_cuda_graphs = False
-        lib.fd_profile_enable(1)
-        step(resident[0], 3)
-        torch.cuda.synchronize()
-        lib.fd_profile_enable(0)
-        if had is not None:
-            model.use_cuda_graphs = had
         dump = os.path.join(ROOT, "gpurun_out", f"bench_launches_{args.config}.csv")
         try:
             os.makedirs(os.path.dirname(dump), exist_ok=True)

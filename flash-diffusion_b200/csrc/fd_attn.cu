@@ -45,6 +45,7 @@ struct AttnKParams {
     long long ldo, o_batch_stride;
     float* lse;  // [B,H,Nq] or null
     int H;
+    int bar_all;  // attn_fwd1: 1 = one 256-thread barrier for the row-maximum exchange (r02 A/B, FD_ATTN_BAR256)
 };
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -582,7 +583,12 @@ attn_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             float mx = fmaxf(mxs[0], mxs[1]);
             float* slot = mx_buf + (j & 1) * 256;
             slot[h * 128 + row] = mx;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            // only the two warps of one lane quarter exchange: a 64-thread barrier per quarter, so a quarter never
+            // waits for the slowest of the eight warps
+            if (p.bar_all)
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            else
+                asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
             mx = fmaxf(mx, slot[(h ^ 1) * 128 + row]);
             const float m_new = mx * p.scale_log2;
             const bool grow = m_new > m_used + ATT_RESCALE_THRESHOLD;
@@ -636,7 +642,7 @@ attn_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         }
         float* slot = mx_buf + (n_kv_tiles & 1) * 256;
         slot[h * 128 + row] = l_run;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
         l_run += slot[(h ^ 1) * 128 + row];
         mbar_wait(pv_done, (n_kv_tiles - 1) & 1);
         tc_fence_after();
@@ -702,6 +708,8 @@ extern "C" int fd_attn_fwd(const FdAttnArgs* a, void* stream_) {
     p.o_batch_stride = a->o_batch_stride;
     p.lse = a->lse;
     p.H = a->H;
+    static const int bar_all = getenv("FD_ATTN_BAR256") != nullptr;
+    p.bar_all = bar_all;
     static bool attr_set = false;
     if (!attr_set) {
         FD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));

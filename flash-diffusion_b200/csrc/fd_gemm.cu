@@ -56,6 +56,8 @@ struct GemmKParams {
     int tail_split;
     int tma_out;          // 1: bf16 output leaves through shared memory + TMA store (cp.async.bulk.tensor ... global)
     int tma_res;          // 1: the residual chunk is TMA-loaded into the output staging buffer ahead of its use
+    float* colstats_out;  // [M / colstats_rows, N, 2] per-image column (sum, sum of squares) for the next GroupNorm
+    int colstats_rows;
 };
 
 template <int BN>
@@ -291,6 +293,39 @@ __device__ __forceinline__ void epilogue_pack(const GemmKParams& p, bool row_ok,
 #pragma unroll
         for (int j = 0; j < NOUT / 2; ++j) stats_of_bf16x2(pk[j], rs);
     }
+}
+
+// GroupNorm statistics from the producer: the warp holds a 32-row x 32-column block of ROUNDED outputs (lane = row,
+// pk = 16 bf16 pairs).  A butterfly of 31 shuffles per quantity leaves lane l with the sum over the 32 rows of column
+// col0 + l (stage `o` keeps the half of the columns whose bit `o` equals the lane's), then one 8-byte reduction per
+// lane into colstats[image][col0 + lane] — the reduction pass of the following GroupNorm over the whole activation
+// (gn_reduce_kernel: 16-33 us per call, 61 calls per SDXL evaluation) disappears.
+__device__ __forceinline__ void colstats_accumulate(const GemmKParams& p, bool row_ok, int row_base, int col0,
+                                                    const uint32_t (&pk)[16], int lane) {
+    float s[32], q[32];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const float2 f = unpack_bf16x2(pk[j]);
+        const float a = row_ok ? f.x : 0.f, b = row_ok ? f.y : 0.f;
+        s[2 * j] = a;
+        s[2 * j + 1] = b;
+        q[2 * j] = a * a;
+        q[2 * j + 1] = b * b;
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        const bool up = (lane & o) != 0;
+#pragma unroll
+        for (int i = 0; i < o; ++i) {
+            const float ks = up ? s[i + o] : s[i], ss = up ? s[i] : s[i + o];
+            const float kq = up ? q[i + o] : q[i], sq = up ? q[i] : q[i + o];
+            s[i] = ks + __shfl_xor_sync(0xffffffffu, ss, o);
+            q[i] = kq + __shfl_xor_sync(0xffffffffu, sq, o);
+        }
+    }
+    const int img = row_base / p.colstats_rows;
+    float2* dst = reinterpret_cast<float2*>(p.colstats_out) + (long long)img * p.N + col0 + lane;
+    atomicAdd(dst, make_float2(s[0], q[0]));
 }
 
 // Direct (register -> global) store of one chunk; used by the single-CTA kernel and whenever the output is fp32 or
@@ -942,6 +977,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
                             tma_store_2d(&tmOut, buf, col0, row - lane);
                             tma_store_commit();
                         }
+                        if (p.colstats_out != nullptr && row - lane < p.M)
+                            colstats_accumulate(p, row_ok, row - lane, col0, pk, lane);
                     }
                     ++n_stored;
                 }
@@ -1099,7 +1136,15 @@ extern "C" int fd_gemm(const FdGemmArgs* a, void* stream_) {
     static const bool env_no_tma_store = getenv("FD_NO_TMA_STORE") != nullptr;
     const bool ws_ok = a->workspace != nullptr && a->workspace_bytes >= (long long)fd_gemm_workspace_bytes() &&
                        ((uintptr_t)a->workspace & 15) == 0 && !env_no_sk;
-    const int code = choose_bn(a->M, a->N, a->force_bn, ws_ok);
+    int code = choose_bn(a->M, a->N, a->force_bn, ws_ok);
+    if (a->colstats_out != nullptr) {
+        // the column statistics live in the TMA-store epilogue of the CTA-pair kernel only
+        FD_CHECK_ARG(!a->out_fp32 && !a->geglu && a->N % 32 == 0 && a->colstats_rows > 0 && a->colstats_rows % 32 == 0 &&
+                         a->M % a->colstats_rows == 0 && (a->ldo % 8) == 0 && ((uintptr_t)a->out & 15) == 0 &&
+                         !env_no_tma_store,
+                     "fd_gemm: colstats_out needs a bf16 TMA-storable output, N %% 32 == 0, rows per image %% 32 == 0");
+        if (code < 512) code = 512 + 128;
+    }
     const bool pair = code >= 512;
     const int BN = pair ? code - 512 : code;
     const uint32_t b_box_rows = pair ? BN / 2 : BN;
@@ -1128,6 +1173,8 @@ extern "C" int fd_gemm(const FdGemmArgs* a, void* stream_) {
     p.ln_inv_c = a->ln_inv_c;
     p.ln_eps = a->ln_eps;
     p.rowstats_out = a->rowstats_out;
+    p.colstats_out = a->colstats_out;
+    p.colstats_rows = a->colstats_rows;
     p.act = a->act;
     p.rowscale = a->rowscale;
     p.rows_per_group_scale = a->rows_per_group_scale;

@@ -126,7 +126,10 @@ __global__ void gn_finalize_kernel(const float* __restrict__ raw, float* __restr
 // y = act((x - mean) * rstd * gamma + beta).  grid (row chunks, NB), block (nvec, rpi).
 // RAW: `stats` holds the raw (sum, sum of squares) of gn_reduce_kernel<0>; mean / rstd are formed here (the separate
 // finalize launch is gone) and, when stats_out != NULL, written once per image for the backward.
-template <bool RAW>
+// RAW == 2: `stats` holds PER-CHANNEL sums [NB, C, 2] left by the epilogue of the GEMM / conv that produced x
+// (FdGemmArgs.colstats_out); every block first folds them into the G group sums in shared memory (eight partial sums per
+// group, fixed order: deterministic), so no reduction pass over x is needed at all.
+template <int RAW>
 __global__ void gn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ stats,
                                 const float* __restrict__ gamma, const float* __restrict__ beta,
                                 bf16* __restrict__ y, int HW, int C, int G, int rows_per_block,
@@ -134,12 +137,43 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, const float* __restr
     const int n = blockIdx.y;
     const int cpg = C / G;
     const int c0 = threadIdx.x * 8;
+    if (RAW == 2) {
+        extern __shared__ float gsum[];           // [G][2] group sums, then [G * 8][2] partial sums
+        float* part = gsum + 2 * G;
+        const int tid = threadIdx.y * blockDim.x + threadIdx.x, nthr = blockDim.x * blockDim.y;
+        const float2* cs = reinterpret_cast<const float2*>(stats) + (long long)n * C;
+        for (int t = tid; t < G * 8; t += nthr) {
+            const int g = t >> 3, sub = t & 7;
+            float a = 0.f, b = 0.f;
+            for (int c = sub; c < cpg; c += 8) {
+                const float2 v = __ldg(cs + g * cpg + c);
+                a += v.x;
+                b += v.y;
+            }
+            part[2 * t] = a;
+            part[2 * t + 1] = b;
+        }
+        __syncthreads();
+        for (int g = tid; g < G; g += nthr) {
+            float a = 0.f, b = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                a += part[2 * (g * 8 + k)];
+                b += part[2 * (g * 8 + k) + 1];
+            }
+            gsum[2 * g] = a;
+            gsum[2 * g + 1] = b;
+        }
+        __syncthreads();
+    }
+    extern __shared__ float gsum_[];
+    const float* gst = (RAW == 2) ? gsum_ : stats + (long long)n * G * 2;     // this image's [G][2]
     float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int g = (c0 + j) / cpg;
-        float mean = stats[(n * G + g) * 2 + 0];
-        float rstd = stats[(n * G + g) * 2 + 1];
+        float mean = gst[g * 2 + 0];
+        float rstd = gst[g * 2 + 1];
         if (RAW) {
             mean *= inv_count;
             rstd = rsqrtf(fmaxf(rstd * inv_count - mean * mean, 0.f) + eps);
@@ -149,8 +183,8 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, const float* __restr
     }
     if (RAW && stats_out != nullptr && blockIdx.x == 0) {
         for (int g = threadIdx.y * blockDim.x + threadIdx.x; g < G; g += blockDim.x * blockDim.y) {
-            const float mean = stats[(n * G + g) * 2 + 0] * inv_count;
-            const float var = fmaxf(stats[(n * G + g) * 2 + 1] * inv_count - mean * mean, 0.f);
+            const float mean = gst[g * 2 + 0] * inv_count;
+            const float var = fmaxf(gst[g * 2 + 1] * inv_count - mean * mean, 0.f);
             stats_out[(n * G + g) * 2 + 0] = mean;
             stats_out[(n * G + g) * 2 + 1] = rsqrtf(var + eps);
         }
@@ -604,7 +638,7 @@ extern "C" int fd_groupnorm_apply(const void* x, const float* stats, const float
     dim3 grid, block;
     int rpb;
     gn_geometry(HW, C, NB, grid, block, rpb);
-    gn_apply_kernel<false><<<grid, block, 0, stream>>>((const bf16*)x, stats, gamma, beta, (bf16*)y, HW, C, G,
+    gn_apply_kernel<0><<<grid, block, 0, stream>>>((const bf16*)x, stats, gamma, beta, (bf16*)y, HW, C, G,
                                                        rpb, silu_act, 0.f, 0.f, nullptr);
     FD_CHECK_LAUNCH();
     return 0;
@@ -623,8 +657,24 @@ extern "C" int fd_groupnorm_fwd(const void* x, const float* gamma, const float* 
     gn_reduce_kernel<0><<<grid, block, 2 * G * sizeof(float), stream>>>(
         (const bf16*)x, nullptr, nullptr, nullptr, nullptr, raw, HW, C, G, rpb, 0);
     FD_CHECK_LAUNCH();
-    gn_apply_kernel<true><<<grid, block, 0, stream>>>((const bf16*)x, raw, gamma, beta, (bf16*)y, HW, C, G, rpb,
+    gn_apply_kernel<1><<<grid, block, 0, stream>>>((const bf16*)x, raw, gamma, beta, (bf16*)y, HW, C, G, rpb,
                                                       silu_act, 1.0f / ((float)HW * (C / G)), eps, stats_out);
+    FD_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int fd_groupnorm_apply_cols(const void* x, const float* colstats, const float* gamma, const float* beta,
+                                       void* y, float* stats_out, int32_t NB, int32_t HW, int32_t C, int32_t G,
+                                       float eps, int32_t silu_act, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    FD_CHECK_ARG(C % 8 == 0 && C % G == 0 && C / 8 <= 1024 && G <= 512,
+                 "fd_groupnorm_apply_cols: bad C=%d G=%d", C, G);
+    dim3 grid, block;
+    int rpb;
+    gn_geometry(HW, C, NB, grid, block, rpb);
+    gn_apply_kernel<2><<<grid, block, 18 * G * sizeof(float), stream>>>((const bf16*)x, colstats, gamma, beta, (bf16*)y,
+                                                                       HW, C, G, rpb, silu_act,
+                                                                       1.0f / ((float)HW * (C / G)), eps, stats_out);
     FD_CHECK_LAUNCH();
     return 0;
 }

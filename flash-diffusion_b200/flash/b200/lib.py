@@ -37,6 +37,7 @@ class FdGemmArgs(Structure):
         ("act", c_int32),
         ("rowscale", c_void_p), ("rows_per_group_scale", c_int32), ("ldrs", c_int64),
         ("workspace", c_void_p), ("workspace_bytes", c_int64),
+        ("colstats_out", c_void_p), ("colstats_rows", c_int32),
     ]
 
 

@@ -9,6 +9,8 @@ Flash-Diffusion step (reference: examples/train_flash_sdxl.py:206-219, src/flash
 
 Activations are channels-last bf16 matrices [NB*H*W, C]; `geom` = (NB, H, W).
 """
+import os
+
 import torch
 
 from . import raw
@@ -110,7 +112,7 @@ def _s2_taps_asym(NB):
 
 
 def _conv_fwd_raw(x, geom, wpack, bias, rowvec, residual, shortcut, stride, Cin, out_fp32=False, pad_mode="same",
-                  act=0):
+                  act=0, colstats=None):
     NB, H, W = geom
     if stride == 1:
         conv = dict(NB_in=NB, H=H, W=W, C=Cin, taps=raw.TAPS_3X3)
@@ -124,7 +126,7 @@ def _conv_fwd_raw(x, geom, wpack, bias, rowvec, residual, shortcut, stride, Cin,
     if shortcut is not None:
         a2, b2 = shortcut
     return raw.gemm(a1, wpack, a2=a2, b2=b2, bias=bias, rowvec=rowvec, rows_per_group=rpg, residual=residual,
-                    conv=conv, M=M, out_fp32=out_fp32, act=act)
+                    conv=conv, M=M, out_fp32=out_fp32, act=act, colstats=colstats)
 
 
 class _ConvFn(torch.autograd.Function):
@@ -175,9 +177,26 @@ def conv_dgrad(dy, geom, mod, stride):
     return raw.depth_to_space(out, NB, H, W, mod.cin)
 
 
-def conv3x3(x, geom, mod, *, rowvec=None, residual=None, x2=None, stride=1, out_fp32=False, pad_mode="same", act=0):
+_NO_COLSTATS = os.environ.get("FD_NO_COLSTATS") is not None
+
+
+def colstats_of(t):
+    """Per-image column sums [NB, C, 2] the producing GEMM / conv attached to its output (None if it did not)."""
+    return getattr(t, "_fd_colstats", None)
+
+
+def _take_colstats(arena, NB, rows_per_image, N, out_fp32=False):
+    if arena is None or _NO_COLSTATS or out_fp32 or N % 32 or rows_per_image % 32:
+        return None
+    return arena.take(NB * N).view(NB, N, 2)
+
+
+def conv3x3(x, geom, mod, *, rowvec=None, residual=None, x2=None, stride=1, out_fp32=False, pad_mode="same", act=0,
+            arena=None):
     """y = conv3x3(x) + bias (+ rowvec per image) (+ residual) (+ x2 @ W_shortcut^T).  `mod` is a ConvPack.
-    pad_mode="asym" (stride 2 only): the VAE encoder's Downsample2D(padding=0).  act=2: ReLU epilogue (no-grad only)."""
+    pad_mode="asym" (stride 2 only): the VAE encoder's Downsample2D(padding=0).  act=2: ReLU epilogue (no-grad only).
+    arena (no-grad only): the epilogue also leaves the per-image column sums of y for a following GroupNorm
+    (`colstats_of(y)`, consumed by `group_norm`)."""
     if _grad_on(x, residual, x2):
         if pad_mode != "same" or act:
             raise NotImplementedError("gradients through the asymmetric stride-2 conv / fused ReLU are not needed by the "
@@ -185,7 +204,13 @@ def conv3x3(x, geom, mod, *, rowvec=None, residual=None, x2=None, stride=1, out_
         return _ConvFn.apply(x, residual, x2, mod, geom, stride, rowvec, out_fp32)
     p = mod.pack()
     shortcut = (x2, mod.pack_shortcut()) if x2 is not None else None
-    return _conv_fwd_raw(x, geom, p["w"], p["b"], rowvec, residual, shortcut, stride, mod.cin, out_fp32, pad_mode, act)
+    NB, H, W = geom
+    cs = _take_colstats(arena, NB, (H // stride) * (W // stride), mod.cout, out_fp32)
+    y = _conv_fwd_raw(x, geom, p["w"], p["b"], rowvec, residual, shortcut, stride, mod.cin, out_fp32, pad_mode, act,
+                      colstats=cs)
+    if cs is not None:
+        y._fd_colstats = cs
+    return y
 
 
 class ConvPack:
@@ -279,6 +304,9 @@ def group_norm(x, geom, norm, silu):
         return _GroupNormFn.apply(x, gamma, beta, geom, norm.num_groups, norm.eps, silu)
     NB, H, W = geom
     C = x.shape[1]
+    cs = colstats_of(x)
+    if cs is not None:
+        return raw.groupnorm_apply_cols(x, cs, gamma, beta, NB, H * W, C, norm.num_groups, norm.eps, silu)
     return raw.groupnorm_fwd(x, gamma, beta, NB, H * W, C, norm.num_groups, norm.eps, silu)
 
 
@@ -541,14 +569,24 @@ class StatsArena:
         return out
 
 
-def linear(x, pack: LinearPack, residual=None, want_stats=None, act=0, out_fp32=False, arena: "StatsArena" = None):
+def linear(x, pack: LinearPack, residual=None, want_stats=None, act=0, out_fp32=False, arena: "StatsArena" = None,
+           colstats_images=0):
     """y = act(x W^T + b (+LoRA)) (+residual).  want_stats None: return y.  True/False: return (y, stats) where stats
     are the [M,2] row statistics of y (fused into the GEMM epilogue) when requested and the no-grad, LoRA-free path is
-    taken, else None."""
+    taken, else None.  colstats_images = NB > 0 (no-grad, LoRA-free, with an arena): the epilogue leaves the per-image
+    column sums of y for a following GroupNorm (`colstats_of(y)`)."""
     lora_params = pack.lora_params() if pack.has_lora else []
     if _grad_on(x, residual, *lora_params):
         y = _LinearFn.apply(x, residual, pack, act, out_fp32, *lora_params)
         return y if want_stats is None else (y, None)
+    if colstats_images and not pack.has_lora and want_stats is None and not pack.geglu:
+        p = pack.pack()
+        N = p["w"].shape[0]
+        cs = _take_colstats(arena, colstats_images, x.shape[0] // colstats_images, N, out_fp32)
+        if cs is not None and x.shape[0] % colstats_images == 0:
+            y = raw.gemm(x, p["w"], bias=p["b"], residual=residual, act=act, colstats=cs)
+            y._fd_colstats = cs
+            return y
     if want_stats and not pack.has_lora:
         p = pack.pack()
         if arena is not None:
@@ -803,7 +841,11 @@ class _ConcatFn(torch.autograd.Function):
 def concat(a, b):
     if _grad_on(a, b):
         return _ConcatFn.apply(a, b)
-    return raw.concat_channels(a, b)
+    y = raw.concat_channels(a, b)
+    ca, cb = colstats_of(a), colstats_of(b)
+    if ca is not None and cb is not None:
+        y._fd_colstats = torch.cat([ca, cb], dim=1)
+    return y
 
 
 class _UpsampleFn(torch.autograd.Function):

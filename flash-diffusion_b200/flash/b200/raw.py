@@ -44,8 +44,11 @@ def gemm_workspace(device):
 
 def gemm(a1, b1, *, a2=None, b2=None, bias=None, rowvec=None, rows_per_group=0, geglu=False,
          residual=None, out=None, out_fp32=False, conv=None, M=None, force_bn=0, ln=None, rowstats=None,
-         act=0, rowscale=None, rows_per_group_scale=0, rowstats_prezeroed=False):
+         act=0, rowscale=None, rows_per_group_scale=0, rowstats_prezeroed=False, colstats=None):
     """acc = a1 @ b1.T (+ a2 @ b2.T) with the fused epilogue of fd_gemm (include/flashb200.h).
+
+    colstats: ZERO-FILLED [images, N, 2] fp32 — per-image column (sum, sum of squares) of the stored output, the
+    statistics `groupnorm_apply_cols` of the following GroupNorm consumes (FdGemmArgs.colstats_out).
 
     a1: [M, K1] bf16 (or, with conv=dict(NB_in,H,W,C,taps), an NHWC tensor), b1: [N, K1] bf16.
     """
@@ -108,6 +111,10 @@ def gemm(a1, b1, *, a2=None, b2=None, bias=None, rowvec=None, rows_per_group=0, 
         assert rowstats.dtype == torch.float32 and rowstats.shape == (M, 2) and rowstats.is_contiguous()
         args.rowstats_out = ptr(rowstats)
         args.rowstats_prezeroed = 1 if rowstats_prezeroed else 0
+    if colstats is not None:
+        assert colstats.dtype == torch.float32 and colstats.is_contiguous() and colstats.dim() == 3
+        assert colstats.shape[1:] == (N, 2) and M % colstats.shape[0] == 0, (colstats.shape, M, N)
+        args.colstats_out, args.colstats_rows = ptr(colstats), M // colstats.shape[0]
     ws = gemm_workspace(a1.device)
     args.workspace, args.workspace_bytes = ptr(ws), ws.numel()
     check(lib.fd_gemm(byref(args), stream_ptr()), "fd_gemm")
@@ -142,6 +149,18 @@ def groupnorm_fwd(x, gamma, beta, NB, HW, C, G, eps, silu, want_stats=False):
                                c_int32(HW), c_int32(C), c_int32(G), c_float(eps), c_int32(1 if silu else 0),
                                stream_ptr()), "fd_groupnorm_fwd")
     return (y, stats) if want_stats else y
+
+
+def groupnorm_apply_cols(x, colstats, gamma, beta, NB, HW, C, G, eps, silu):
+    """GroupNorm(+SiLU) forward in ONE launch from the per-image column sums [NB, C, 2] the producing GEMM / conv left
+    (gemm(colstats=...)): no reduction pass over x."""
+    lib = load(); _req(x, BF16, "x"); _req(gamma, torch.float32, "gamma"); _req(beta, torch.float32, "beta")
+    assert colstats.dtype == torch.float32 and colstats.shape == (NB, C, 2) and colstats.is_contiguous()
+    y = torch.empty_like(x)
+    check(lib.fd_groupnorm_apply_cols(ptr(x), ptr(colstats), ptr(gamma), ptr(beta), ptr(y), None, c_int32(NB),
+                                      c_int32(HW), c_int32(C), c_int32(G), c_float(eps), c_int32(1 if silu else 0),
+                                      stream_ptr()), "fd_groupnorm_apply_cols")
+    return y
 
 
 def groupnorm_bwd(x, stats, gamma, beta, dy, NB, HW, C, G, silu):

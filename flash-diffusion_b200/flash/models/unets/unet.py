@@ -307,12 +307,15 @@ class DiffusersUNet2DCondWrapper(nn.Module):
     def _resnet(self, r, x, geom, trow):
         c1 = self._pack(("c1", id(r)), lambda: ConvPack(r.conv1))
         c2 = self._pack(("c2", id(r)), lambda: ConvPack(r.conv2, r.conv_shortcut))
+        # `arena`: the conv epilogues leave the per-image column sums of their outputs, so the GroupNorm that follows
+        # (norm2 here, norm1 / Transformer2DModel.norm / conv_norm_out of the next block) needs no reduction pass
+        arena = self.__dict__.get("_arena")
         h = ops.group_norm(x, geom, r.norm1, silu=True)
-        h = ops.conv3x3(h, geom, c1, rowvec=trow)
+        h = ops.conv3x3(h, geom, c1, rowvec=trow, arena=arena)
         h = ops.group_norm(h, geom, r.norm2, silu=True)
         if r.conv_shortcut is not None:
-            return ops.conv3x3(h, geom, c2, x2=x)
-        return ops.conv3x3(h, geom, c2, residual=x)
+            return ops.conv3x3(h, geom, c2, x2=x, arena=arena)
+        return ops.conv3x3(h, geom, c2, residual=x, arena=arena)
 
     def _attention(self, a, x, ctx, B, residual, norm, stats):
         """x: the residual stream (un-normalised), `norm` its LayerNorm.  When the producer GEMM left row statistics
@@ -370,7 +373,8 @@ class DiffusersUNet2DCondWrapper(nn.Module):
                 g = ops.geglu(ops.layer_norm(h, blk.norm3), ff1)
             h, st = ops.linear(g, self._pack(("ff2", id(blk)), lambda: LinearPack(blk.ff.net[2])), residual=h,
                                want_stats=(i + 1 < n), arena=arena)
-        return ops.linear(h, self._pack(("po", id(t)), lambda: LinearPack(t.proj_out)), residual=x)
+        return ops.linear(h, self._pack(("po", id(t)), lambda: LinearPack(t.proj_out)), residual=x, arena=arena,
+                          colstats_images=B)
 
     supports_kv_cache = True
 
@@ -414,7 +418,8 @@ class DiffusersUNet2DCondWrapper(nn.Module):
 
         conv_in = self._pack("conv_in", lambda: ConvPack(self.conv_in))
         geom = (NB, H, W)
-        x = ops.conv3x3(ops.to_nhwc(sample, conv_in.cin), geom, conv_in)
+        arena = self.__dict__.get("_arena")
+        x = ops.conv3x3(ops.to_nhwc(sample, conv_in.cin), geom, conv_in, arena=arena)
         skips = [(x, geom)]
         for blk in self.down_blocks:
             for i, r in enumerate(blk.resnets):
@@ -424,7 +429,7 @@ class DiffusersUNet2DCondWrapper(nn.Module):
                 skips.append((x, geom))
             if blk.downsamplers is not None:
                 ds = blk.downsamplers[0]
-                x = ops.conv3x3(x, geom, self._pack(("ds", id(ds)), lambda: ConvPack(ds.conv)), stride=2)
+                x = ops.conv3x3(x, geom, self._pack(("ds", id(ds)), lambda: ConvPack(ds.conv)), stride=2, arena=arena)
                 geom = (NB, geom[1] // 2, geom[2] // 2)
                 skips.append((x, geom))
         mb = self.mid_block
@@ -445,7 +450,7 @@ class DiffusersUNet2DCondWrapper(nn.Module):
                 us = blk.upsamplers[0]
                 x = ops.upsample2x(x, geom)
                 geom = (NB, geom[1] * 2, geom[2] * 2)
-                x = ops.conv3x3(x, geom, self._pack(("us", id(us)), lambda: ConvPack(us.conv)))
+                x = ops.conv3x3(x, geom, self._pack(("us", id(us)), lambda: ConvPack(us.conv)), arena=arena)
         x = ops.group_norm(x, geom, self.conv_norm_out, silu=True)
         conv_out = self._pack("conv_out", lambda: ConvPack(self.conv_out))
         y = ops.conv3x3(x, geom, conv_out, out_fp32=True)

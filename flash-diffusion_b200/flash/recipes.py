@@ -121,6 +121,7 @@ def build_distillation(unet_kwargs, discriminator, device, *, lora_rank=64, K=32
     teacher = teacher.to_empty(device=device)
     init_random_(teacher, seed)
     student = copy.deepcopy(teacher)
+    torch.manual_seed(seed + 3)          # LoRA A draws from the global generator: pin it to the recipe's seed
     student.add_adapter(LoraConfig(r=lora_rank, lora_alpha=lora_rank, init_lora_weights="gaussian",
                                    target_modules=["to_k", "to_q", "to_v", "to_out.0"]))
     if lora_b_std > 0:

@@ -100,6 +100,12 @@ typedef struct {
      * once by the caller (the kernels leave it zero-flagged); calls that may run CONCURRENTLY (different streams)
      * need different workspaces.  NULL: no K cuts (whole tiles per CTA pair, wave-quantised). */
     void* workspace; int64_t workspace_bytes;
+    /* GroupNorm statistics from the producer: colstats_out [M / colstats_rows, N, 2] fp32 += per-image (sum, sum of
+     * squares) of every stored (bf16-rounded) output column, accumulated by the epilogue (one 8-byte reduction per
+     * column per 32 rows) — what fd_groupnorm_apply_cols of the FOLLOWING GroupNorm consumes instead of a reduction
+     * pass over the activation.  The caller zero-fills it.  Needs bf16 output, N % 32 == 0, colstats_rows % 32 == 0,
+     * no GEGLU; the call then always takes the CTA-pair kernel.  NULL: off. */
+    float* colstats_out; int32_t colstats_rows;
 } FdGemmArgs;
 int fd_gemm(const FdGemmArgs* args, void* stream);
 size_t fd_gemm_workspace_bytes(void);
@@ -107,6 +113,14 @@ size_t fd_gemm_workspace_bytes(void);
 /* ------------------------------------------------------------------------------------------
  * Normalisation / elementwise (HBM-bound) kernels — NHWC bf16 activations.
  * ------------------------------------------------------------------------------------------ */
+
+/* GroupNorm apply from producer-side column statistics (FdGemmArgs.colstats_out of the GEMM / conv that wrote x):
+ * colstats [NB, C, 2] fp32 (sum, sum of squares per image and channel) -> group mean / rstd formed per block,
+ * y = act((x - mean) * rstd * gamma + beta).  One pass over x (read + write) and no reduction launch.
+ * stats_out (optional) [NB, G, 2] (mean, rstd). */
+int fd_groupnorm_apply_cols(const void* x, const float* colstats, const float* gamma, const float* beta, void* y,
+                            float* stats_out, int32_t NB, int32_t HW, int32_t C, int32_t G, float eps,
+                            int32_t silu_act, void* stream);
 
 /* GroupNorm statistics: x [NB, HW, C] bf16 -> stats [NB, G, 2] fp32 (mean, rstd).
  * UPSTREAM torch.nn.GroupNorm inside ResnetBlock2D / Transformer2DModel. */

@@ -47,11 +47,26 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     model, pipe = build(dev, seed=1234 + 100 * rank)
+    keep = lambda n, p: p.requires_grad or "discriminator" in n
+
+    def checksum():
+        v = torch.stack([p.detach().double().sum() for n, p in model.named_parameters() if keep(n, p)])
+        lo, hi = v.clone(), v.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        return float((hi - lo).abs().max())
+
+    # configure_optimizers() ended with TrainingPipeline.sync_replicas(): the per-rank seeds are gone
+    assert checksum() == 0.0, "start-up broadcast left the replicas different"
+    if rank == 0:
+        torch.save({n: p.detach().cpu() for n, p in model.named_parameters() if keep(n, p)},
+                   os.path.join(out_dir, "init.pt"))
     batch, draws = data(2 * world, dev)
     pipe.training_step(slice_(batch, 2 * rank, 2 * rank + 2), 0, draws=slice_(draws, 2 * rank, 2 * rank + 2))
     torch.cuda.synchronize()
+    assert checksum() == 0.0, "replicas diverged after one all-reduced step"
     if rank == 0:
-        torch.save({n: p.detach().cpu() for n, p in model.named_parameters() if p.requires_grad or "discriminator" in n},
+        torch.save({n: p.detach().cpu() for n, p in model.named_parameters() if keep(n, p)},
                    os.path.join(out_dir, "dp.pt"))
     dist.barrier()
     dist.destroy_process_group()

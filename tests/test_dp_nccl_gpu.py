@@ -25,7 +25,12 @@ def test_two_ranks_nccl_equal_one_rank_double_batch(tmp_path):
                     str(tmp_path)], check=True, timeout=900)
     dp = torch.load(os.path.join(tmp_path, "dp.pt"))
     dev = torch.device("cuda", 0)
-    model, pipe = W.build(dev, seed=1234)                 # rank 0's seed: what the broadcast made every replica
+    model, pipe = W.build(dev, seed=1234)
+    init = torch.load(os.path.join(tmp_path, "init.pt"))  # rank 0's weights: what the broadcast made every replica
+    with torch.no_grad():
+        for n, p in model.named_parameters():
+            if n in init:
+                p.copy_(init[n].to(dev))
     before = {n: p.detach().cpu().clone() for n, p in model.named_parameters()}
     batch, draws = W.data(4, dev)
     pipe.training_step(batch, 0, draws=draws)

@@ -217,3 +217,53 @@ def test_conv3x3_work_split(raw, mode):
         out = raw.gemm(x_nhwc, wp, bias=bias, conv=dict(NB_in=NB, H=H, W=W, C=Cin, taps=raw.TAPS_3X3), M=NB * H * W,
                        force_bn=bn | SPLIT_MODES[mode])
         assert _rel(out, ref) < 6e-3, (bn, _rel(out, ref))
+
+
+@pytest.mark.parametrize("mode", ["auto", "streamk", "whole_tiles"])
+@pytest.mark.parametrize("NB,HW,N,K,bn", [(4, 1024, 1280, 1280, 0), (3, 4096, 320, 640, 512 + 160),
+                                          (8, 64, 1280, 320, 0), (2, 2048, 96, 200, 512 + 128),
+                                          (5, 4096, 640, 1920, 512 + 256)])
+def test_gemm_colstats(raw, NB, HW, N, K, bn, mode):
+    """FdGemmArgs.colstats_out: per-image column (sum, sum of squares) of the STORED bf16 output, accumulated by the
+    epilogue (GroupNorm statistics from the producer) — with bias + residual, through every work split."""
+    torch.manual_seed(NB + HW + N)
+    M = NB * HW
+    a = torch.randn(M, K, device="cuda").bfloat16()
+    b = (torch.randn(N, K, device="cuda") / K ** 0.5).bfloat16()
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda").bfloat16()
+    ref = raw.gemm(a, b, bias=bias, residual=res, force_bn=bn | SPLIT_MODES[mode])
+    cs = torch.zeros(NB, N, 2, device="cuda")
+    out = raw.gemm(a, b, bias=bias, residual=res, force_bn=bn | SPLIT_MODES[mode], colstats=cs)
+    assert torch.equal(out, ref)                         # the statistics do not perturb the output
+    o = out.float().view(NB, HW, N)
+    want = torch.stack([o.sum(1), (o * o).sum(1)], dim=-1)
+    scale = (o * o).sum(1).max().item()
+    assert (cs - want).abs().max().item() < 2e-5 * scale + 1e-2, (cs - want).abs().max().item()
+    # accumulate semantics: a second call adds on top
+    raw.gemm(a, b, bias=bias, residual=res, force_bn=bn | SPLIT_MODES[mode], colstats=cs)
+    assert (cs - 2 * want).abs().max().item() < 4e-5 * scale + 2e-2
+
+
+def test_conv3x3_colstats(raw):
+    torch.manual_seed(9)
+    NB, H, W, Cin, Cout = 3, 32, 32, 128, 320
+    x = torch.randn(NB, H, W, Cin, device="cuda").bfloat16()
+    cpad = (Cin + 63) // 64 * 64
+    wp = (torch.randn(Cout, 9 * cpad, device="cuda") / (9 * Cin) ** 0.5).bfloat16()
+    bias = torch.randn(Cout, device="cuda")
+    conv = dict(NB_in=NB, H=H, W=W, C=Cin, taps=raw.TAPS_3X3)
+    ref = raw.gemm(x, wp, bias=bias, conv=conv, M=NB * H * W)
+    cs = torch.zeros(NB, Cout, 2, device="cuda")
+    out = raw.gemm(x, wp, bias=bias, conv=conv, M=NB * H * W, colstats=cs)
+    assert torch.equal(out, ref)
+    o = out.float().view(NB, H * W, Cout)
+    want = torch.stack([o.sum(1), (o * o).sum(1)], dim=-1)
+    assert (cs - want).abs().max().item() < 2e-5 * (o * o).sum(1).max().item() + 1e-2
+
+
+def test_gemm_colstats_rejects_unsupported(raw):
+    a = torch.randn(256, 64, device="cuda").bfloat16()
+    b = torch.randn(72, 64, device="cuda").bfloat16()          # N % 32 != 0
+    with pytest.raises(RuntimeError):
+        raw.gemm(a, b, colstats=torch.zeros(2, 72, 2, device="cuda"))

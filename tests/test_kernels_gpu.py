@@ -65,6 +65,12 @@ def test_groupnorm(raw, NB, HW, C, silu):
     y2, stats2 = raw.groupnorm_fwd(x, gamma, beta, NB, HW, C, G, 1e-5, silu, want_stats=True)
     assert _rel(y2, ref.transpose(1, 2)) < 6e-3
     assert torch.allclose(stats2, stats, rtol=1e-4, atol=1e-5)
+    # one launch from per-image column sums (what the producing GEMM / conv epilogue leaves: FdGemmArgs.colstats_out)
+    xf32 = x.float()
+    cols = torch.stack([xf32.sum(1), (xf32 * xf32).sum(1)], dim=-1).contiguous()
+    y3 = raw.groupnorm_apply_cols(x, cols, gamma, beta, NB, HW, C, G, 1e-5, silu)
+    assert _rel(y3, ref.transpose(1, 2)) < 6e-3
+    assert _rel(y3, y2) < 2e-3
     dy = torch.randn(NB, HW, C, device="cuda").bfloat16()
     ref.backward(dy.float().transpose(1, 2))
     dx = raw.groupnorm_bwd(x, stats, gamma, beta, dy, NB, HW, C, G, silu)

@@ -166,3 +166,29 @@ def test_teacher_kv_cache_is_output_preserving():
         assert len(g.graphs) == 2
     with pytest.raises(ValueError):
         prod(x, t, cond, kv_cache="bogus")
+
+
+def test_groupnorm_statistics_from_producer_epilogue(monkeypatch):
+    """No-grad evaluations take the GroupNorm statistics from the epilogue of the conv / proj_out GEMM that produced
+    the tensor (FdGemmArgs.colstats_out -> fd_groupnorm_apply_cols): same output as the reduce + apply kernels."""
+    from flash.b200 import ops, raw
+    prod, ora = _pair(SMALL)
+    prod.freeze()
+    x, t, cond = _inputs(2, 32, 32, 96, 48)
+    calls = {"cols": 0, "reduce": 0}
+    apply_cols, fwd = raw.groupnorm_apply_cols, raw.groupnorm_fwd
+    monkeypatch.setattr(raw, "groupnorm_apply_cols", lambda *a, **k: (calls.__setitem__("cols", calls["cols"] + 1), apply_cols(*a, **k))[1])
+    monkeypatch.setattr(raw, "groupnorm_fwd", lambda *a, **k: (calls.__setitem__("reduce", calls["reduce"] + 1), fwd(*a, **k))[1])
+    with torch.no_grad():
+        fused = prod(x, t, cond)
+        n_cols, n_reduce = calls["cols"], calls["reduce"]
+        assert n_cols > 0 and n_cols >= 2 * n_reduce, calls         # the small maps (HW % 32 != 0) keep the reduction
+        monkeypatch.setattr(ops, "_NO_COLSTATS", True)
+        plain = prod(x, t, cond)
+        assert calls["cols"] == n_cols                              # switched off: no further fused calls
+        # same bf16 activations, same (sum, sum of squares) up to fp32 summation order: the two paths differ like two
+        # runs of either one do (GroupNorm atomics; same tolerance as test_cuda_graph_replay_matches_eager) and sit
+        # at the same distance from the fp32 oracle
+        ref = ora(x, t, cond)
+        assert _rel(fused, plain) < 2e-2, _rel(fused, plain)
+        assert _rel(fused, ref) < 2e-2 and _rel(fused, ref) < 1.25 * _rel(plain, ref) + 2e-3, (_rel(fused, ref), _rel(plain, ref))
