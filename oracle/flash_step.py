@@ -3,7 +3,11 @@
 Follows reference src/flash/models/flash/flash_diffusion_model.py line by line:
   :236-257 noising, :260-280 student prediction + x0, :284-324 teacher CFG rollout (two separate B-sized teacher
   calls, DPM-Solver++), :328 c_skip/c_out mix, :368-399 distill loss, :401-499 DMD loss, :501-667 GAN loss.
-Every random draw is an explicit input (SURVEY.md §8c decision 5).  PARITY UNPINNED upstream (see oracle/unet.py).
+Every random draw is an explicit input (SURVEY.md §8c decision 5).
+PINNED: tests/test_reference_golden.py replays tests/golden/reference_step.pt — six runs of the reference's own
+`FlashDiffusion.forward` (imported from /root/reference/src by tests/golden/make_reference_step_golden.py, draws recorded)
+— through this function: outputs, both losses and the LoRA / discriminator gradients agree to fp32 rounding.  (The
+denoiser and scheduler arithmetic inside stays unpinned upstream, see oracle/unet.py.)
 """
 import torch
 import torch.nn.functional as F
@@ -80,6 +84,10 @@ def flash_forward(student, teacher, discriminator, z, cond, uncond, draws, *, K=
     f_fake, f_real = feats.chunk(2)
     valid, zeros = torch.ones(B, 1, device=z.device), torch.zeros(B, 1, device=z.device)
     loss_G, loss_D = 0, 0
+    if gan_loss_type == "wgan":        # reference :573-576: the critic's weights are clipped in place, on BOTH turns
+        with torch.no_grad():
+            for p in discriminator.parameters():
+                p.clamp_(-0.01, 0.01)
     if step % 2 == 0:
         d = discriminator(f_fake)
         loss_G = {"lsgan": lambda: F.mse_loss(torch.sigmoid(d), valid), "hinge": lambda: -d.mean(),
