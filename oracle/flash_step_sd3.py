@@ -6,8 +6,13 @@ student x0 read-out, :372-383 distill loss, :413-494 DMD loss, :496-658 GAN loss
 non-saturating / vanilla), :1043-1060 sigma look-up.  Every random draw is an explicit input.
 
 The flow-matching grid is restated from upstream diffusers' published `FlowMatchEulerDiscreteScheduler` (v0.29); the
-"trailing" spacing of the authors' fork is read as in flash/schedulers.py (assumption).  PARITY UNPINNED
-upstream (see oracle/unet.py): diffusers is not installable here, so there are no reference-generated vectors.
+"trailing" spacing of the authors' fork is read as in flash/schedulers.py (assumption).
+PINNED (step logic): tests/test_reference_sd3_golden.py replays tests/golden/reference_sd3_step.pt — five runs of the
+reference's own `FlashDiffusionSD3.forward`, imported from /root/reference/src by
+tests/golden/make_reference_sd3_golden.py with its draws recorded — through this function: outputs, losses and
+gradients agree to fp32 rounding.  Unpinned upstream: the scheduler grid itself and the MMDiT (diffusers is not
+installable here), and what the fork's `return_post_mid_blocks=True` backbone call returns (:563; read as the full
+backbone output).
 """
 import numpy as np
 import torch
@@ -39,6 +44,10 @@ def inference_grid(K, n=1000, shift=3.0, spacing="trailing"):
 def gan_objective(D, f_fake, f_real, B, step, kind):
     valid = torch.ones(B, 1, device=f_fake.device)
     zeros = torch.zeros(B, 1, device=f_fake.device)
+    if kind == "wgan":                 # reference flash_sd3/flash_diffusion_model.py:568-571: critic weights clipped in place
+        with torch.no_grad():
+            for p in D.parameters():
+                p.clamp_(-0.01, 0.01)
     if step % 2 == 0:
         d = D(f_fake)
         if kind in ("wgan", "hinge"):

@@ -65,6 +65,46 @@ def install_shims():
     mod("diffusers.models.transformers", SD3Transformer2DModel=_Absent, Transformer2DModel=_Absent)
     mod("diffusers.models.embeddings", Timesteps=_Absent, TimestepEmbedding=_Absent)
     mod("lpips", LPIPS=_Absent)
+
+    class LightningModule(torch.nn.Module):
+        """The five LightningModule services the reference's TrainingPipeline.training_step uses (trainer.py:169-218),
+        with Lightning's documented semantics: toggle_optimizer freezes every parameter that belongs to ANOTHER
+        optimizer only, untoggle_optimizer restores the flags, manual_backward is loss.backward()."""
+        automatic_optimization = True
+        global_rank = 0
+
+        def save_hyperparameters(self, *a, **k):
+            pass
+
+        @property
+        def device(self):
+            return next(self.parameters()).device
+
+        def optimizers(self):
+            return self.optims
+
+        def toggle_optimizer(self, optimizer):
+            mine = {id(p) for g in optimizer.param_groups for p in g["params"]}
+            self._toggled = {}
+            for opt in self.optims:
+                for g in opt.param_groups:
+                    for p in g["params"]:
+                        if id(p) not in mine and id(p) not in self._toggled:
+                            self._toggled[id(p)] = (p, p.requires_grad)
+                            p.requires_grad = False
+
+        def untoggle_optimizer(self, optimizer):
+            for p, flag in self._toggled.values():
+                p.requires_grad = flag
+            self._toggled = {}
+
+        def manual_backward(self, loss):
+            loss.backward()
+
+    pl = mod("pytorch_lightning", LightningModule=LightningModule, Trainer=_Absent)
+    pl.__path__ = []
+    mod("pytorch_lightning.callbacks", Callback=object)
+    mod("pytorch_lightning.utilities", rank_zero_only=lambda f: f)
     return sched
 
 
@@ -118,6 +158,22 @@ class Tape:
                     dmd_timestep=v[4], dmd_guidance=float(v[5] * (g_max - g_min) + g_min), gan_noise=v[6],
                     guidance_uniform=float(v[2]), dmd_guidance_uniform=float(v[5]),
                     gan_timesteps=torch.tensor([10, 250, 500, 750])[v[7]])
+
+
+class RandnTape:
+    """records torch.randn (the LCM scheduler's inter-step noise and log_samples' initial latents)"""
+
+    def __init__(self):
+        self.events, self.orig = [], torch.randn
+
+    def __enter__(self):
+        def randn(*a, **k):
+            r = self.orig(*a, **k); self.events.append(r.clone()); return r
+        torch.randn = randn
+        return self
+
+    def __exit__(self, *exc):
+        torch.randn = self.orig
 
 
 def build_models(seed):
@@ -232,6 +288,103 @@ def main():
         out["cases"][case["name"]] = rec
         print(case["name"], "start_idx", draws["start_idx"], "t0", rec["start_timestep"], "loss_G", float(loss_G),
               "loss_D", float(loss_D), "grads", len(rec["grads"]))
+
+    # ---- the reference's TrainingPipeline.configure_optimizers / training_step (src/flash/trainer/trainer.py:76-218):
+    #      two optimizers, per optimizer a full forward with step=i and fresh draws, zero_grad / backward / step
+    from flash.trainer.trainer import TrainingPipeline
+    from flash.trainer.training_config import TrainingConfig
+    student.load_state_dict(student_state); disc.load_state_dict(disc_state)
+    for p in student.parameters():
+        p.requires_grad_(True)                  # configure_optimizers must do the freezing by regex itself
+    for n, p in student.named_parameters():
+        if "lora" not in n:
+            p.requires_grad_(False)             # (what add_adapter leaves: only LoRA weights trainable)
+    cfg = FlashDiffusionConfig(
+        K=[K], num_iterations_per_K=[10 ** 9], guidance_scale_min=3.0, guidance_scale_max=13.0,
+        distill_loss_type="l2", ucg_keys=["text_emb", "pooled_emb"], timestep_distribution="mixture",
+        mixture_num_components=4, mixture_var=0.5, use_dmd_loss=True, dmd_loss_scale=0.7, distill_loss_scale=1.0,
+        adversarial_loss_scale=0.3, gan_loss_type="lsgan", mode_probs=[[0.25, 0.25, 0.25, 0.25]], input_key="image")
+    ident = dict(nn_modules=["torch.nn.Identity"], nn_modules_kwargs=[{}], ucg_rate=0.0)
+    conditioner = ConditionerWrapper([TorchNNEmbedder(TorchNNEmbedderConfig(input_key="text_emb", **ident)),
+                                      TorchNNEmbedder(TorchNNEmbedderConfig(input_key="pooled_emb", **ident))])
+    mk = lambda cls: cls.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", subfolder="scheduler",
+                                         timestep_spacing="trailing")
+    model = FlashDiffusion(cfg, student_denoiser=student, teacher_denoiser=teacher,
+                           teacher_noise_scheduler=mk(sched_mod.DPMSolverMultistepScheduler),
+                           sampling_noise_scheduler=mk(sched_mod.LCMScheduler), vae=None, conditioner=conditioner,
+                           discriminator=disc)
+    model.switch_teacher = False
+    tcfg = dict(optimizers_name=["SGD", "SGD"], learning_rates=[2e-3, 5e-3], optimizers_kwargs=[{}, {"momentum": 0.5}],
+                trainable_params=[["student_denoiser"], ["discriminator."]], lr_schedulers_name=[None, None],
+                lr_schedulers_kwargs=[{}, {}], lr_schedulers_interval=["step", "step"], lr_schedulers_frequency=[1, 1])
+    pipe = TrainingPipeline(model, TrainingConfig(**tcfg))
+    pipe.configure_optimizers()
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    trainable = sorted(n for n, p in model.named_parameters() if p.requires_grad)
+    torch.manual_seed(321)
+    steps = []
+    for it, forced in enumerate([(2, 1), (3, 0)]):          # two training steps: momentum and the turn order matter
+        tapes = []
+
+        class Both:                                          # one tape per model.forward call (two per training_step)
+            def __enter__(self_):
+                return self_
+        orig_forward = model.forward
+
+        def taped_forward(*a, _orig=orig_forward, **k):
+            with Tape(forced[len(tapes)]) as tp:
+                r = _orig(*a, **k)
+            tapes.append(tp)
+            return r
+        model.forward = taped_forward
+        outs = pipe.training_step(dict(batch), it)
+        model.forward = orig_forward
+        steps.append(dict(draws=[tp.draws(3.0, 13.0) for tp in tapes],
+                          loss_optimizer_0=torch.as_tensor(float(outs["loss_optimizer_0"])),
+                          loss_optimizer_1=torch.as_tensor(float(outs["loss_optimizer_1"])),
+                          start_timestep=int(outs["start_timestep"])))
+        print("training_step", it, {k: float(v) for k, v in outs.items() if k.startswith("loss")})
+    after = {n: p.detach().clone() for n, p in model.named_parameters()}
+    moved = [n for n in before if not torch.equal(before[n], after[n])]
+    assert set(moved) <= set(trainable), "a frozen parameter moved"
+    out["trainer"] = dict(config=tcfg, steps=steps, trainable=trainable, moved=sorted(moved),
+                          delta_norms={n: (after[n] - before[n]).norm().clone() for n in moved},
+                          deltas={n: (after[n] - before[n]).clone() for i, n in enumerate(sorted(moved)) if i % 4 == 0})
+    print("trainer: trainable", len(trainable), "moved", len(moved))
+
+    # ---- the reference's sampler (:754-915) and sample logging (:917-1019)
+    student.load_state_dict(student_state)
+    cfg = FlashDiffusionConfig(K=[K], num_iterations_per_K=[10 ** 9], ucg_keys=["text_emb", "pooled_emb"], input_key="image")
+    ident = dict(nn_modules=["torch.nn.Identity"], nn_modules_kwargs=[{}], ucg_rate=0.0)
+    conditioner = ConditionerWrapper([TorchNNEmbedder(TorchNNEmbedderConfig(input_key="text_emb", **ident)),
+                                      TorchNNEmbedder(TorchNNEmbedderConfig(input_key="pooled_emb", **ident))])
+    mk = lambda cls: cls.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", subfolder="scheduler",
+                                         timestep_spacing="trailing")
+    model = FlashDiffusion(cfg, student_denoiser=student, teacher_denoiser=teacher,
+                           teacher_noise_scheduler=mk(sched_mod.DPMSolverMultistepScheduler),
+                           teacher_sampling_noise_scheduler=mk(sched_mod.DPMSolverMultistepScheduler),
+                           sampling_noise_scheduler=mk(sched_mod.LCMScheduler), vae=None, conditioner=conditioner,
+                           discriminator=None)
+    cin = {k: v for k, v in batch.items() if k != "image"}
+    z = torch.randn(B, 4, HW, HW, generator=g)
+    out["sample"] = {}
+    for name, kw in [("lcm4_cfg1", dict(num_steps=4, guidance_scale=1.0)),
+                     ("lcm2_cfg1.7_teacher", dict(num_steps=2, guidance_scale=1.7, teacher_guidance_scale=5.0,
+                                                  log_teacher_samples=True)),
+                     ("lcm1_max1", dict(num_steps=1, guidance_scale=1.0, max_samples=1))]:
+        torch.manual_seed(55)
+        with RandnTape() as tape:
+            smp, smp_ref = model.sample(z.clone(), conditioner_inputs=dict(cin), **kw)
+        out["sample"][name] = dict(kwargs=kw, z=z.clone(), randn=tape.events, sample=smp.clone(),
+                                   sample_ref=None if smp_ref is None else smp_ref.clone(),
+                                   lcm_timesteps=model.sampling_noise_scheduler.timesteps.clone())
+        print("sample", name, "noise draws", len(tape.events), "timesteps", model.sampling_noise_scheduler.timesteps.tolist())
+    torch.manual_seed(56)
+    with RandnTape() as tape:
+        logs = model.log_samples(dict(cin), input_shape=(4, HW, HW), guidance_scale=1.0, teacher_guidance_scale=3.0,
+                                 max_samples=8, num_steps=[1, 2], device="cpu", log_teacher_samples=True)
+    out["log_samples"] = dict(randn=tape.events, logs={k: v.clone() for k, v in logs.items()})
+    print("log_samples keys", sorted(logs))
 
     path = os.path.join(HERE, "reference_step.pt")
     torch.save(out, path)

@@ -161,3 +161,124 @@ def test_cuda_step_matches_reference_run(name):
     else:
         ld, ref_d = float(out["loss"][1]), float(rec["loss_D"])
         assert abs(ld - ref_d) <= 5e-2 * abs(ref_d) + 1e-3, (ld, ref_d)
+
+
+class _ReplayRandn:
+    """torch.randn replaced by the tensors the reference run drew, in order (moved to the requested device)."""
+
+    def __init__(self, tensors):
+        self.queue, self.orig = list(tensors), torch.randn
+
+    def __enter__(self):
+        def randn(*shape, **k):
+            t = self.queue.pop(0)
+            want = tuple(shape[0]) if len(shape) == 1 and not isinstance(shape[0], int) else tuple(shape)
+            assert tuple(t.shape) == want, (t.shape, want)
+            return t.to(device=k.get("device") or "cpu", dtype=k.get("dtype") or t.dtype)
+        torch.randn = randn
+        return self
+
+    def __exit__(self, *exc):
+        torch.randn = self.orig
+        assert not exc[0] is None or not self.queue, f"{len(self.queue)} recorded draws were not consumed"
+
+
+def _sampler_model(student, teacher, device="cpu"):
+    from flash.models.embedders import ConditionerWrapper, TorchNNEmbedder, TorchNNEmbedderConfig
+    from flash.models.flash import FlashDiffusion, FlashDiffusionConfig
+    from flash.schedulers import DPMSolverMultistepScheduler, LCMScheduler
+    cfg = FlashDiffusionConfig(K=[GOLD["K"]], num_iterations_per_K=[10 ** 9], ucg_keys=["text_emb", "pooled_emb"],
+                               input_key="image")
+    ident = dict(nn_modules=["torch.nn.Identity"], nn_modules_kwargs=[{}], ucg_rate=0.0)
+    conditioner = ConditionerWrapper([TorchNNEmbedder(TorchNNEmbedderConfig(input_key="text_emb", **ident)),
+                                      TorchNNEmbedder(TorchNNEmbedderConfig(input_key="pooled_emb", **ident))])
+    mk = lambda cls: cls.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", subfolder="scheduler",
+                                         timestep_spacing="trailing")
+    return FlashDiffusion(cfg, student_denoiser=student, teacher_denoiser=teacher,
+                          teacher_noise_scheduler=mk(DPMSolverMultistepScheduler),
+                          teacher_sampling_noise_scheduler=mk(DPMSolverMultistepScheduler),
+                          sampling_noise_scheduler=mk(LCMScheduler), vae=None, conditioner=conditioner,
+                          discriminator=None).to(device)
+
+
+@pytest.mark.parametrize("name", list(GOLD["sample"]))
+def test_product_sampler_matches_reference_run(name):
+    """`sample()` (reference :754-915): few-step LCM sampling with CFG, `max_samples`, the teacher reference samples."""
+    rec = GOLD["sample"][name]
+    student, teacher, _ = _models()
+    model = _sampler_model(student, teacher)
+    cin = {k: v for k, v in GOLD["batch"].items() if k != "image"}
+    with _ReplayRandn(rec["randn"]):
+        smp, smp_ref = model.sample(rec["z"].clone(), conditioner_inputs=dict(cin), **rec["kwargs"])
+    assert model.sampling_noise_scheduler.timesteps.tolist() == rec["lcm_timesteps"].tolist()
+    assert smp.shape == rec["sample"].shape and _rel(smp, rec["sample"]) < 1e-4, _rel(smp, rec["sample"])
+    if rec["sample_ref"] is None:
+        assert smp_ref is None
+    else:
+        assert _rel(smp_ref, rec["sample_ref"]) < 1e-4
+
+
+def test_product_log_samples_matches_reference_run():
+    """`log_samples()` (reference :917-1019): same keys, same tensors, same order of latent draws."""
+    rec = GOLD["log_samples"]
+    student, teacher, _ = _models()
+    model = _sampler_model(student, teacher)
+    cin = {k: v for k, v in GOLD["batch"].items() if k != "image"}
+    with _ReplayRandn(rec["randn"]):
+        logs = model.log_samples(dict(cin), input_shape=(4, 16, 16), guidance_scale=1.0, teacher_guidance_scale=3.0,
+                                 max_samples=8, num_steps=[1, 2], device="cpu", log_teacher_samples=True)
+    assert set(logs) == set(rec["logs"])
+    for k, v in rec["logs"].items():
+        assert logs[k].shape == v.shape and _rel(logs[k], v) < 1e-4, (k, _rel(logs[k], v))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(GOLD["sample"]))
+def test_cuda_sampler_matches_reference_run(name):
+    from flash.models.lora import LoraConfig
+    from flash.models.unets import DiffusersUNet2DCondWrapper
+    rec = GOLD["sample"][name]
+    o_student, o_teacher, _ = _models()
+    dev = torch.device("cuda", 0)
+    teacher = DiffusersUNet2DCondWrapper(**GOLD["unet_kwargs"])
+    teacher.load_state_dict(o_teacher.state_dict())
+    student = DiffusersUNet2DCondWrapper(**GOLD["unet_kwargs"])
+    student.load_state_dict(o_teacher.state_dict())
+    student.add_adapter(LoraConfig(**GOLD["lora"]))
+    student.load_state_dict(o_student.state_dict())
+    teacher.freeze(); student.freeze()
+    model = _sampler_model(student.to(dev), teacher.to(dev), device=dev)
+    cin = {k: v.to(dev) for k, v in GOLD["batch"].items() if k != "image"}
+    with _ReplayRandn(rec["randn"]):
+        smp, smp_ref = model.sample(rec["z"].to(dev), conditioner_inputs=cin, **rec["kwargs"])
+    assert _rel(smp.cpu(), rec["sample"]) < 4e-2, _rel(smp.cpu(), rec["sample"])
+    if rec["sample_ref"] is not None:
+        assert _rel(smp_ref.cpu(), rec["sample_ref"]) < 4e-2
+
+
+def test_product_training_pipeline_matches_reference_run():
+    """`TrainingPipeline.configure_optimizers` + two `training_step`s (reference src/flash/trainer/trainer.py:76-218:
+    regex parameter groups, per optimizer a full forward with step=i and fresh draws, zero_grad / backward / step, SGD
+    with momentum on the discriminator): same frozen set, same parameter updates."""
+    from flash.trainer import TrainingConfig, TrainingPipeline
+    rec = GOLD["trainer"]
+    student, teacher, disc = _models()
+    case = dict(distill="l2", dmd=True, gan="lsgan", teacher_real=False)
+    model = _product_model(case, student, teacher, disc)
+    pipe = TrainingPipeline(model, TrainingConfig(**rec["config"]))
+    pipe.configure_optimizers()
+    assert sorted(n for n, p in model.named_parameters() if p.requires_grad) == rec["trainable"]
+    before = {n: p.detach().clone() for n, p in model.named_parameters()}
+    for it, st in enumerate(rec["steps"]):
+        out = pipe.training_step({k: v.clone() for k, v in GOLD["batch"].items()}, it, draws=[dict(d) for d in st["draws"]])
+        assert out["start_timestep"] == st["start_timestep"]
+        for k in ("loss_optimizer_0", "loss_optimizer_1"):
+            assert torch.allclose(torch.as_tensor(out[k]).float(), st[k], rtol=1e-3, atol=1e-6), (it, k, out[k], st[k])
+    after = {n: p.detach() for n, p in model.named_parameters()}
+    moved = sorted(n for n in before if not torch.equal(before[n], after[n]))
+    assert moved == rec["moved"]
+    for n, d in rec["deltas"].items():
+        assert _rel(after[n] - before[n], d) < 2e-3, (n, _rel(after[n] - before[n], d))
+    for n, dn in rec["delta_norms"].items():
+        got = float((after[n] - before[n]).norm())
+        assert abs(got - float(dn)) <= 2e-3 * float(dn) + 1e-9, n

@@ -1,0 +1,87 @@
+"""Parity of the rectified-flow (SD3) objective against vectors the REFERENCE ITSELF produced
+(tests/golden/reference_sd3_step.pt, written by tests/golden/make_reference_sd3_golden.py from the unmodified
+src/flash/models/flash_sd3/flash_diffusion_model.py:187-662 with every random draw recorded):
+oracle/flash_step_sd3.py and the product's FlashDiffusionSD3 host logic replay the draws on CPU."""
+import os
+import sys
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+GOLD = torch.load(os.path.join(HERE, "golden", "reference_sd3_step.pt"), weights_only=False)
+CASES = list(GOLD["cases"])
+SCALES = (1.0, 0.7, 0.3)
+
+
+def _models():
+    import make_reference_sd3_golden as G3
+    return G3.build_models(GOLD["model_seed"])
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+def _check_grads(rec, case, student, disc, loss_G, loss_D):
+    if case["step"] % 2 == 0:
+        loss_G.backward()
+        got = {n: p.grad for n, p in student.named_parameters() if p.grad is not None}
+        assert set(got) == set(rec["grad_norms"])
+        for n, g in rec["grads"].items():
+            assert _rel(got[n], g) < 1e-3, (n, _rel(got[n], g))
+        for n, gn in rec["grad_norms"].items():
+            assert abs(float(got[n].norm()) - float(gn)) <= 1e-3 * float(gn) + 1e-7, n
+    else:
+        assert torch.allclose(torch.as_tensor(loss_D).detach(), rec["loss_D"], rtol=2e-4, atol=1e-6)
+        loss_D.backward()
+        for n, p in disc.named_parameters():
+            assert _rel(p.grad, rec["grads"]["disc." + n]) < 1e-3, n
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_sd3_step_matches_reference_run(name):
+    from oracle import flash_step_sd3 as O3
+    rec = GOLD["cases"][name]
+    case, b = rec["case"], GOLD["batch"]
+    student, teacher, disc = _models()
+    cond = {"vector": b["pooled_prompt_embeds"], "crossattn": b["prompt_embeds"]}
+    unc = {"vector": b["negative_pooled_prompt_embeds"], "crossattn": b["negative_prompt_embeds"]}
+    call = lambda net: (lambda x, t, c: net(x, t, {"cond": c}))
+    out = O3.flash_forward_sd3(call(student), call(teacher), disc, b["image"], cond, unc, rec["draws"], K=GOLD["K"],
+                               step=case["step"], gan_loss_type=case["gan"], scales=SCALES,
+                               use_teacher_as_real=case["teacher_real"])
+    assert _rel(out["student_output"], rec["student_output"]) < 1e-5
+    assert _rel(out["teacher_output"], rec["teacher_output"]) < 1e-4
+    assert torch.allclose(out["loss_G"].detach(), rec["loss_G"], rtol=2e-4, atol=1e-6), (out["loss_G"], rec["loss_G"])
+    _check_grads(rec, case, student, disc, out["loss_G"], out["loss_D"])
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_product_sd3_host_logic_matches_reference_run(name):
+    from flash.models.flash_sd3 import FlashDiffusionSD3, FlashDiffusionSD3Config
+    from flash.schedulers import FlashFlowMatchEulerDiscreteScheduler, FlowMatchEulerDiscreteScheduler
+    rec = GOLD["cases"][name]
+    case = rec["case"]
+    student, teacher, disc = _models()
+    cfg = FlashDiffusionSD3Config(
+        K=[GOLD["K"]], num_iterations_per_K=[10 ** 9], guidance_scale_min=7.0, guidance_scale_max=13.0,
+        distill_loss_type="l2", timestep_distribution="mixture", mixture_num_components=4, mixture_var=0.5,
+        use_dmd_loss=True, dmd_loss_scale=SCALES[1], distill_loss_scale=SCALES[0], adversarial_loss_scale=SCALES[2],
+        gan_loss_type=case["gan"], mode_probs=[[0.25, 0.25, 0.25, 0.25]], use_teacher_as_real=case["teacher_real"],
+        input_key="image")
+    mk = lambda cls, **kw: cls.from_pretrained("stabilityai/stable-diffusion-3-medium", subfolder="scheduler", **kw)
+    model = FlashDiffusionSD3(cfg, student_denoiser=student, teacher_denoiser=teacher,
+                              teacher_noise_scheduler=mk(FlowMatchEulerDiscreteScheduler, timestep_spacing="trailing"),
+                              sampling_noise_scheduler=mk(FlashFlowMatchEulerDiscreteScheduler,
+                                                          timestep_spacing="trailing"),
+                              discriminator=disc)
+    batch = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in GOLD["batch"].items()}
+    out = model(batch, step=case["step"], draws=dict(rec["draws"]))
+    assert float(out["start_timestep"]) == rec["start_timestep"]
+    assert torch.allclose(out["noisy_sample"], rec["noisy_sample"], rtol=1e-5, atol=1e-6)
+    assert _rel(out["student_output"], rec["student_output"]) < 1e-5
+    assert _rel(out["teacher_output"], rec["teacher_output"]) < 1e-4
+    assert torch.allclose(torch.as_tensor(out["loss"][0]).detach(), rec["loss_G"], rtol=2e-4, atol=1e-6)
+    _check_grads(rec, case, student, disc, out["loss"][0], out["loss"][1])
