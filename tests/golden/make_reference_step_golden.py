@@ -113,7 +113,7 @@ class Tape:
     (the start index of `_get_timesteps`) only."""
 
     def __init__(self, force_start_idx=None):
-        self.events, self.force = [], force_start_idx
+        self.events, self.force, self.probs = [], force_start_idx, []
         self.orig = dict(randn_like=torch.randn_like, rand=torch.rand, randint=torch.randint,
                          multinomial=torch.multinomial, t_multinomial=torch.Tensor.multinomial)
 
@@ -131,6 +131,7 @@ class Tape:
 
         def multinomial(p, n, *a, **k):
             r = o["multinomial"](p, n, *a, **k)
+            tape.probs.append(p.clone())
             if tape.force is not None and n == 1 and p.dim() == 1:
                 r = torch.tensor([tape.force])
             ev.append(("multinomial", r.clone())); return r
@@ -158,6 +159,20 @@ class Tape:
                     dmd_timestep=v[4], dmd_guidance=float(v[5] * (g_max - g_min) + g_min), gan_noise=v[6],
                     guidance_uniform=float(v[2]), dmd_guidance_uniform=float(v[5]),
                     gan_timesteps=torch.tensor([10, 250, 500, 750])[v[7]])
+
+
+class StubLPIPS(torch.nn.Module):
+    """stands where lpips.LPIPS(net="vgg") stands in `_distill_loss` (:383-397): any perceptual distance [B,1,1,1]"""
+
+    def forward(self, a, b):
+        return ((a - b) ** 2).mean((1, 2, 3), keepdim=True) + (a - b).abs().amax((1, 2, 3), keepdim=True)
+
+
+class StubVAE:
+    """stands where AutoencoderKLDiffusers stands in `_distill_loss`: latents [B,4,h,w] -> images [B,3,2h,2w]"""
+
+    def decode(self, z):
+        return torch.nn.functional.interpolate(z[:, :3] * 1.5 + 0.25 * z[:, 3:4], scale_factor=2, mode="nearest")
 
 
 class RandnTape:
@@ -288,6 +303,36 @@ def main():
         out["cases"][case["name"]] = rec
         print(case["name"], "start_idx", draws["start_idx"], "t0", rec["start_timestep"], "loss_G", float(loss_G),
               "loss_D", float(loss_D), "grads", len(rec["grads"]))
+
+    # ---- `_get_timesteps` (:139-177): the start-index pmf of every distribution type, K = 32 and 4
+    out["pmf"] = []
+    for dist, kw in [("uniform", {}), ("gaussian", {}),
+                     ("mixture", dict(mixture_num_components=4, mixture_var=0.5, mode_probs=[[0.25, 0.25, 0.25, 0.25]])),
+                     ("mixture", dict(mixture_num_components=4, mixture_var=2.0, mode_probs=[[0.4, 0.2, 0.2, 0.2]])),
+                     ("mixture", dict(mixture_num_components=2, mixture_var=0.5, mode_probs=[[0.0, 1.0]]))]:
+        for K_ in (32, 4):
+            cfg = FlashDiffusionConfig(K=[K_], num_iterations_per_K=[10 ** 9], timestep_distribution=dist,
+                                       ucg_keys=["text_emb"], input_key="image", **kw)
+            tsched = sched_mod.DPMSolverMultistepScheduler.from_pretrained(
+                "stabilityai/stable-diffusion-xl-base-1.0", subfolder="scheduler", timestep_spacing="trailing")
+            m = FlashDiffusion(cfg, student_denoiser=student, teacher_denoiser=teacher, teacher_noise_scheduler=tsched,
+                               sampling_noise_scheduler=None, vae=None, conditioner=None, discriminator=None)
+            torch.manual_seed(5)
+            with Tape() as tape:
+                idx, t0 = m._get_timesteps(num_samples=3, K=K_, K_step=0, device="cpu")
+            out["pmf"].append(dict(dist=dist, K=K_, kw=kw, prob=tape.probs[0].clone(), start_idx=int(idx),
+                                   start_timestep=t0.clone(), timesteps=tsched.timesteps.clone()))
+    print("pmf cases", len(out["pmf"]))
+
+    # ---- `_distill_loss` lpips branch (:383-397): center crop 64x64, decode both, clamp, perceptual distance, mean
+    cfg = FlashDiffusionConfig(K=[K], num_iterations_per_K=[10 ** 9], ucg_keys=["text_emb"], input_key="image")
+    m = FlashDiffusion(cfg, student_denoiser=student, teacher_denoiser=teacher, teacher_noise_scheduler=None,
+                       sampling_noise_scheduler=None, vae=StubVAE(), conditioner=None, discriminator=None)
+    m.distill_loss_type, m.lpips = "lpips", StubLPIPS()
+    gl = torch.Generator().manual_seed(3)
+    s_out, t_out = torch.randn(2, 4, 72, 80, generator=gl), torch.randn(2, 4, 72, 80, generator=gl)
+    out["lpips_glue"] = dict(seed=3, shape=(2, 4, 72, 80), loss=m._distill_loss(s_out.clone(), t_out.clone()).clone())
+    print("lpips glue", float(out["lpips_glue"]["loss"]))
 
     # ---- the reference's TrainingPipeline.configure_optimizers / training_step (src/flash/trainer/trainer.py:76-218):
     #      two optimizers, per optimizer a full forward with step=i and fresh draws, zero_grad / backward / step

@@ -282,3 +282,40 @@ def test_product_training_pipeline_matches_reference_run():
     for n, dn in rec["delta_norms"].items():
         got = float((after[n] - before[n]).norm())
         assert abs(got - float(dn)) <= 2e-3 * float(dn) + 1e-9, n
+
+
+def test_product_start_index_pmf_matches_reference_run():
+    """`_get_timesteps` (reference :139-177): the start-index distribution (uniform / gaussian / mixture with mode
+    probabilities) the reference handed to torch.multinomial, and the timestep it looked up."""
+    from flash.models.flash import FlashDiffusion, FlashDiffusionConfig
+    from flash.schedulers import DPMSolverMultistepScheduler
+    student, teacher, _ = _models()
+    for rec in GOLD["pmf"]:
+        cfg = FlashDiffusionConfig(K=[rec["K"]], num_iterations_per_K=[10 ** 9], timestep_distribution=rec["dist"],
+                                   ucg_keys=["text_emb"], input_key="image", **rec["kw"])
+        sched = DPMSolverMultistepScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0",
+                                                            subfolder="scheduler", timestep_spacing="trailing")
+        m = FlashDiffusion(cfg, student_denoiser=student, teacher_denoiser=teacher, teacher_noise_scheduler=sched,
+                           sampling_noise_scheduler=None, vae=None, conditioner=None, discriminator=None)
+        pmf = m._start_index_pmf(rec["K"], 0)
+        assert torch.allclose(pmf, rec["prob"], rtol=1e-6, atol=1e-9), (rec["dist"], rec["K"], rec["kw"])
+        idx, t0 = m._get_timesteps(num_samples=3, K=rec["K"], K_step=0, start_idx=rec["start_idx"])
+        assert torch.equal(t0, rec["start_timestep"]) and sched.timesteps.tolist() == rec["timesteps"].tolist()
+
+
+def test_product_lpips_distill_glue_matches_reference_run():
+    """`_distill_loss(..., "lpips")` (reference :383-397): centre crop of 64x64 latents, decode, clamp, distance, mean —
+    the same stand-in VAE / perceptual distance on both sides, so only the reference's glue is compared."""
+    import make_reference_step_golden as G
+    from flash.models.flash import FlashDiffusion, FlashDiffusionConfig
+    rec = GOLD["lpips_glue"]
+    student, teacher, _ = _models()
+    cfg = FlashDiffusionConfig(K=[GOLD["K"]], num_iterations_per_K=[10 ** 9], ucg_keys=["text_emb"], input_key="image")
+    m = FlashDiffusion(cfg, student_denoiser=student, teacher_denoiser=teacher, teacher_noise_scheduler=None,
+                       sampling_noise_scheduler=None, vae=None, conditioner=None, discriminator=None)
+    m.__dict__["vae"] = G.StubVAE()
+    m.distill_loss_type = "lpips"
+    m.__dict__["lpips"] = G.StubLPIPS()
+    g = torch.Generator().manual_seed(rec["seed"])
+    s_out, t_out = torch.randn(*rec["shape"], generator=g), torch.randn(*rec["shape"], generator=g)
+    assert torch.allclose(m._distill_loss(s_out, t_out), rec["loss"], rtol=1e-5)
