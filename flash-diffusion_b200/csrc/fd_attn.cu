@@ -46,6 +46,7 @@ struct AttnKParams {
     float* lse;  // [B,H,Nq] or null
     int H;
     int bar_all;  // attn_fwd1: 1 = one 256-thread barrier for the row-maximum exchange (r02 A/B, FD_ATTN_BAR256)
+    int early;    // attn_fwd1: 1 = first TMA loads issued before the TMEM allocation / block sync (FD_ATTN_EARLY=0: off)
 };
 
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
@@ -467,12 +468,11 @@ attn_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int q_blk = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
     const int n_kv_tiles = (p.Nkv + ATT_BN - 1) / ATT_BN;
 
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmQ);
-        tma_prefetch_desc(&tmK);
-        tma_prefetch_desc(&tmV);
-    }
-    if (warp == 1 && lane == 0) {
+    // PROLOGUE.  The thread that initialises the barriers also issues the first TMA loads (Q and the first key / value
+    // tiles) BEFORE the TMEM allocation and the block-wide synchronisation: a CTA has only 8 key tiles at 1024 keys, so
+    // the ~1 us of TMA latency in front of its first S = Q K^T is worth hiding (p.early = 0 keeps the r02a order).
+    const int n_pre = p.early ? min(ATT1_STAGES, n_kv_tiles) : 0;
+    if (warp == (p.early ? 0 : 1) && lane == 0) {
         mbar_init(q_full, 1);
         for (int s = 0; s < ATT1_STAGES; ++s) {
             mbar_init(&kv_full[s], 1);
@@ -483,8 +483,24 @@ attn_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         mbar_init(p_ready, 256);
         mbar_init(pv_done, 1);
         fence_barrier_init();
+        fence_proxy_async();            // the initialised barriers are about to be used by the async proxy (TMA)
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+        if (p.early) {
+            mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
+            tma_load_3d(&tmQ, q_full, sQ, head * ATT_D, q_blk * 128, batch);
+            for (int j = 0; j < n_pre; ++j) {
+                mbar_arrive_expect_tx(&kv_full[j], 2 * ATT_TILE_BYTES);
+                tma_load_3d(&tmK, &kv_full[j], sK + j * ATT_TILE_BYTES, head * ATT_D, j * ATT_BN, batch);
+                tma_load_3d(&tmV, &kv_full[j], sV + j * ATT_TILE_BYTES, head * ATT_D, j * ATT_BN, batch);
+            }
+        }
     }
     if (warp == 0) {
+        __syncwarp();
         tmem_alloc(tmem_holder, 256);
         tmem_relinquish();
     }
@@ -495,11 +511,13 @@ attn_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
-            tma_load_3d(&tmQ, q_full, sQ, head * ATT_D, q_blk * 128, batch);
-            int st = 0;
-            uint32_t ph = 0;
-            for (int j = 0; j < n_kv_tiles; ++j) {
+            if (!p.early) {
+                mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
+                tma_load_3d(&tmQ, q_full, sQ, head * ATT_D, q_blk * 128, batch);
+            }
+            int st = n_pre % ATT1_STAGES;
+            uint32_t ph = (n_pre / ATT1_STAGES) & 1u;
+            for (int j = n_pre; j < n_kv_tiles; ++j) {
                 mbar_wait(&kv_empty[st], ph ^ 1u);
                 mbar_arrive_expect_tx(&kv_full[st], 2 * ATT_TILE_BYTES);
                 tma_load_3d(&tmK, &kv_full[st], sK + st * ATT_TILE_BYTES, head * ATT_D, j * ATT_BN, batch);
@@ -710,6 +728,8 @@ extern "C" int fd_attn_fwd(const FdAttnArgs* a, void* stream_) {
     p.H = a->H;
     static const int bar_all = getenv("FD_ATTN_BAR256") != nullptr;
     p.bar_all = bar_all;
+    static const int early = getenv("FD_ATTN_EARLY") ? atoi(getenv("FD_ATTN_EARLY")) : 1;
+    p.early = early;
     static bool attr_set = false;
     if (!attr_set) {
         FD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
