@@ -46,6 +46,8 @@ struct AttnKParams {
     float* lse;  // [B,H,Nq] or null
     int H;
     int bar_all;  // attn_fwd1: 1 = one 256-thread barrier for the row-maximum exchange (r02 A/B, FD_ATTN_BAR256)
+    int diag;     // attn_fwd1: FD_ATTN_DIAG bits — timing diagnostics that BREAK the result (1: no row-max exchange, 2: no MUFU)
+    int spin;     // attn_fwd1: 1 = the S / P ping-pong waits poll with test_wait instead of suspending in try_wait (FD_ATTN_SPIN)
     int early;    // attn_fwd1: 1 = first TMA loads issued before the TMEM allocation / block sync (FD_ATTN_EARLY=0: off)
 };
 
@@ -341,6 +343,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                     float2 e;
                     if (POLY && FD_ATTN_POLY_MOD > 0 && ((i >> 1) % (FD_ATTN_POLY_MOD > 0 ? FD_ATTN_POLY_MOD : 1)) == 1)
                         e = exp2_poly2(x);
+                    else if (p.diag & 2)    // diag bit 1 (TIMING DIAGNOSTIC ONLY): no MUFU, one FMA per element
+                        e = ffma2(x, make_float2(0.001f, 0.001f), make_float2(1.f, 1.f));
                     else
                         e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
                     ps2 = fadd2(ps2, e);
@@ -438,9 +442,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // the last partial wave is also half as long.  K/V tiles are staged per CTA (2-stage ring): twice the L2 -> smem
 // operand traffic of the shared ring, 64 B/clk/SM, still inside the budget.
 // TMEM: S [0,128)  O [128,192)  P [192,256) (bf16 pairs; A operand of O += P V read from TMEM).
-constexpr int ATT1_STAGES = 2;
+constexpr int ATT1_KST = 3;                   // K ring: a stage is released as soon as S = Q K^T has read it
+constexpr int ATT1_VST = 2;                   // V ring: released after O += P V
 constexpr int ATT1_THREADS = 64 + 256;        // TMA warp, MMA warp, 2 column halves x 4 softmax warps
-constexpr int ATT1_SMEM = ATT_TILE_BYTES + 2 * ATT1_STAGES * ATT_TILE_BYTES + 256 + 2048 + 1024;
+constexpr int ATT1_SMEM = ATT_TILE_BYTES + (ATT1_KST + ATT1_VST) * ATT_TILE_BYTES + 256 + 2048 + 1024;
 
 template <int POLY>     // 0: every exponential on the MUFU; m > 0: every m-th pair of scores on the FMA pipe (cubic)
 __global__ void __launch_bounds__(ATT1_THREADS, 2)
@@ -451,12 +456,14 @@ attn_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + ATT_TILE_BYTES;
-    uint8_t* sV = sK + ATT1_STAGES * ATT_TILE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT1_STAGES * ATT_TILE_BYTES);
+    uint8_t* sV = sK + ATT1_KST * ATT_TILE_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT1_VST * ATT_TILE_BYTES);
     uint64_t* q_full = bars;
-    uint64_t* kv_full = bars + 1;                  // [ATT1_STAGES]
-    uint64_t* kv_empty = kv_full + ATT1_STAGES;    // [ATT1_STAGES]
-    uint64_t* s_full = kv_empty + ATT1_STAGES;     // S(j) written by the tensor core
+    uint64_t* k_full = bars + 1;                   // [ATT1_KST]
+    uint64_t* k_empty = k_full + ATT1_KST;         // [ATT1_KST]
+    uint64_t* v_full = k_empty + ATT1_KST;         // [ATT1_VST]
+    uint64_t* v_empty = v_full + ATT1_VST;         // [ATT1_VST]
+    uint64_t* s_full = v_empty + ATT1_VST;         // S(j) written by the tensor core
     uint64_t* s_free = s_full + 1;                 // S(j) copied to registers: S(j+1) may be issued
     uint64_t* p_ready = s_free + 1;                // P(j) in TMEM
     uint64_t* pv_done = p_ready + 1;               // O += P(j) V(j) complete
@@ -468,15 +475,28 @@ attn_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const int q_blk = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
     const int n_kv_tiles = (p.Nkv + ATT_BN - 1) / ATT_BN;
 
-    // PROLOGUE.  The thread that initialises the barriers also issues the first TMA loads (Q and the first key / value
-    // tiles) BEFORE the TMEM allocation and the block-wide synchronisation: a CTA has only 8 key tiles at 1024 keys, so
-    // the ~1 us of TMA latency in front of its first S = Q K^T is worth hiding (p.early = 0 keeps the r02a order).
-    const int n_pre = p.early ? min(ATT1_STAGES, n_kv_tiles) : 0;
+    // PROLOGUE.  The thread that initialises the barriers also issues the first TMA loads (Q, the first three key tiles
+    // and the first two value tiles) BEFORE the TMEM allocation and the block-wide synchronisation: a CTA has only 8
+    // key tiles at 1024 keys, so the ~1 us of TMA latency in front of its first S = Q K^T is worth hiding
+    // (p.early = 0 keeps the r02a order).
+    //
+    // K / V PIPELINE.  Keys and values travel in SEPARATE rings: K(j) is dead once S(j) = Q K(j)^T has been computed
+    // (one softmax EARLIER than V(j)), so its stage goes back to the TMA thread right then and K(j+3) is requested
+    // more than two tile times before it is needed.  With the shared 2-stage ring of r02a the load of tile j+2 could
+    // only start after O += P(j) V(j) — about when S(j+2) was already due — and the ~1 us TMA latency sat on every
+    // tile: switching the MUFU work or the row-max exchange OFF changed the kernel time by 2 % each
+    // (profiles/r02_attention.txt), the loop was waiting for keys.
+    const int nk_pre = p.early ? min(ATT1_KST, n_kv_tiles) : 0;
+    const int nv_pre = p.early ? min(ATT1_VST, n_kv_tiles) : 0;
     if (warp == (p.early ? 0 : 1) && lane == 0) {
         mbar_init(q_full, 1);
-        for (int s = 0; s < ATT1_STAGES; ++s) {
-            mbar_init(&kv_full[s], 1);
-            mbar_init(&kv_empty[s], 1);
+        for (int s = 0; s < ATT1_KST; ++s) {
+            mbar_init(&k_full[s], 1);
+            mbar_init(&k_empty[s], 1);
+        }
+        for (int s = 0; s < ATT1_VST; ++s) {
+            mbar_init(&v_full[s], 1);
+            mbar_init(&v_empty[s], 1);
         }
         mbar_init(s_full, 1);
         mbar_init(s_free, 256);
@@ -485,6 +505,16 @@ attn_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         fence_barrier_init();
         fence_proxy_async();            // the initialised barriers are about to be used by the async proxy (TMA)
     }
+    auto load_k = [&](int j) {
+        const int st = j % ATT1_KST;
+        mbar_arrive_expect_tx(&k_full[st], ATT_TILE_BYTES);
+        tma_load_3d(&tmK, &k_full[st], sK + st * ATT_TILE_BYTES, head * ATT_D, j * ATT_BN, batch);
+    };
+    auto load_v = [&](int j) {
+        const int st = j % ATT1_VST;
+        mbar_arrive_expect_tx(&v_full[st], ATT_TILE_BYTES);
+        tma_load_3d(&tmV, &v_full[st], sV + st * ATT_TILE_BYTES, head * ATT_D, j * ATT_BN, batch);
+    };
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ);
         tma_prefetch_desc(&tmK);
@@ -492,11 +522,10 @@ attn_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         if (p.early) {
             mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
             tma_load_3d(&tmQ, q_full, sQ, head * ATT_D, q_blk * 128, batch);
-            for (int j = 0; j < n_pre; ++j) {
-                mbar_arrive_expect_tx(&kv_full[j], 2 * ATT_TILE_BYTES);
-                tma_load_3d(&tmK, &kv_full[j], sK + j * ATT_TILE_BYTES, head * ATT_D, j * ATT_BN, batch);
-                tma_load_3d(&tmV, &kv_full[j], sV + j * ATT_TILE_BYTES, head * ATT_D, j * ATT_BN, batch);
-            }
+            load_k(0);
+            if (nv_pre > 0) load_v(0);
+            for (int j = 1; j < nk_pre; ++j) load_k(j);
+            for (int j = 1; j < nv_pre; ++j) load_v(j);
         }
     }
     if (warp == 0) {
@@ -508,6 +537,13 @@ attn_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_holder;
+    // waits on the S / P ping-pong between the MMA thread and the softmax warps: polled (p.spin) or suspended try_wait
+    auto wait_pp = [&](uint64_t* bar, uint32_t parity) {
+        if (p.spin)
+            mbar_wait_poll(bar, parity);
+        else
+            mbar_wait(bar, parity);
+    };
 
     if (warp == 0) {
         if (lane == 0) {
@@ -515,16 +551,18 @@ attn_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                 mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
                 tma_load_3d(&tmQ, q_full, sQ, head * ATT_D, q_blk * 128, batch);
             }
-            int st = n_pre % ATT1_STAGES;
-            uint32_t ph = (n_pre / ATT1_STAGES) & 1u;
-            for (int j = n_pre; j < n_kv_tiles; ++j) {
-                mbar_wait(&kv_empty[st], ph ^ 1u);
-                mbar_arrive_expect_tx(&kv_full[st], 2 * ATT_TILE_BYTES);
-                tma_load_3d(&tmK, &kv_full[st], sK + st * ATT_TILE_BYTES, head * ATT_D, j * ATT_BN, batch);
-                tma_load_3d(&tmV, &kv_full[st], sV + st * ATT_TILE_BYTES, head * ATT_D, j * ATT_BN, batch);
-                if (++st == ATT1_STAGES) {
-                    st = 0;
-                    ph ^= 1u;
+            // keys run ahead of values: K(jk) is requested as soon as S(jk - 3) is done, V(jv) as soon as P V(jv - 2) is
+            int jk = nk_pre, jv = nv_pre;
+            while (jk < n_kv_tiles || jv < n_kv_tiles) {
+                if (jk < n_kv_tiles) {
+                    mbar_wait(&k_empty[jk % ATT1_KST], ((jk / ATT1_KST) & 1) ^ 1u);
+                    load_k(jk);
+                    ++jk;
+                }
+                if (jv < n_kv_tiles && (jv + 1 < jk || jk >= n_kv_tiles)) {
+                    mbar_wait(&v_empty[jv % ATT1_VST], ((jv / ATT1_VST) & 1) ^ 1u);
+                    load_v(jv);
+                    ++jv;
                 }
             }
         }
@@ -533,36 +571,38 @@ attn_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             constexpr uint32_t idesc_qk = make_idesc_bf16(128, ATT_BN, 0, 0);
             constexpr uint32_t idesc_pv = make_idesc_bf16(128, ATT_D, 0, 1);  // B (=V) MN-major
             const uint32_t q_addr = smem_u32(sQ);
-            auto issue_s = [&](int st) {
+            auto issue_s = [&](int j) {
+                const int st = j % ATT1_KST;
                 const uint32_t k_addr = smem_u32(sK + st * ATT_TILE_BYTES);
 #pragma unroll
                 for (int k = 0; k < ATT_D / 16; ++k)
                     tc_mma_bf16(tmem_base, make_desc_k_sw128(q_addr + k * 32), make_desc_k_sw128(k_addr + k * 32),
                                 idesc_qk, k != 0 ? 1u : 0u);
                 tc_commit(s_full);
+                tc_commit(&k_empty[st]);            // the key tile is dead once S(j) is complete
             };
             mbar_wait(q_full, 0);
-            mbar_wait(&kv_full[0], 0);
+            mbar_wait(&k_full[0], 0);
             tc_fence_after();
             issue_s(0);
             for (int j = 0; j < n_kv_tiles; ++j) {
                 if (j + 1 < n_kv_tiles) {
                     // S(j+1) as soon as S(j) sits in the softmax warps' registers and K(j+1) has landed
-                    mbar_wait(s_free, j & 1);
-                    const int stn = (j + 1) % ATT1_STAGES;
-                    mbar_wait(&kv_full[stn], ((j + 1) / ATT1_STAGES) & 1);
+                    wait_pp(s_free, j & 1);
+                    mbar_wait(&k_full[(j + 1) % ATT1_KST], ((j + 1) / ATT1_KST) & 1);
                     tc_fence_after();
-                    issue_s(stn);
+                    issue_s(j + 1);
                 }
-                mbar_wait(p_ready, j & 1);
+                wait_pp(p_ready, j & 1);
+                mbar_wait(&v_full[j % ATT1_VST], (j / ATT1_VST) & 1);
                 tc_fence_after();
-                const uint32_t v_addr = smem_u32(sV + (j % ATT1_STAGES) * ATT_TILE_BYTES);
+                const uint32_t v_addr = smem_u32(sV + (j % ATT1_VST) * ATT_TILE_BYTES);
 #pragma unroll
                 for (int k = 0; k < ATT_BN / 16; ++k)
                     tc_mma_bf16_ts(tmem_base + 128, tmem_base + 192 + k * 8,
                                    make_desc_mn_sw128(v_addr + k * 2048, 0, 1024), idesc_pv, (j | k) != 0 ? 1u : 0u);
                 tc_commit(pv_done);
-                tc_commit(&kv_empty[j % ATT1_STAGES]);
+                tc_commit(&v_empty[j % ATT1_VST]);
             }
         }
     } else {
@@ -576,7 +616,7 @@ attn_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint32_t tmem_O = tmem_base + 128 + h * 32;
         float m_used = -INFINITY, l_run = 0.f;
         for (int j = 0; j < n_kv_tiles; ++j) {
-            mbar_wait(s_full, j & 1);
+            wait_pp(s_full, j & 1);
             tc_fence_after();
             const int kv_valid = min(ATT_BN, p.Nkv - j * ATT_BN) - h * 64;
             uint32_t sr[2][32];
@@ -600,6 +640,7 @@ attn_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     mxs[c] = max3(mxs[c], __uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1]));
             float mx = fmaxf(mxs[0], mxs[1]);
             float* slot = mx_buf + (j & 1) * 256;
+            if (!(p.diag & 1)) {        // diag bit 0 (TIMING DIAGNOSTIC ONLY, wrong results): no half-row exchange
             slot[h * 128 + row] = mx;
             // only the two warps of one lane quarter exchange: a 64-thread barrier per quarter, so a quarter never
             // waits for the slowest of the eight warps
@@ -608,6 +649,7 @@ attn_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             else
                 asm volatile("bar.sync %0, 64;" ::"r"(2 + quarter) : "memory");
             mx = fmaxf(mx, slot[(h ^ 1) * 128 + row]);
+            }
             const float m_new = mx * p.scale_log2;
             const bool grow = m_new > m_used + ATT_RESCALE_THRESHOLD;
             const float alpha = (grow && j > 0) ? fast_exp2(m_used - m_new) : 1.0f;
@@ -625,6 +667,8 @@ attn_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     float2 e;
                     if (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == (POLY > 1 ? 1 : 0))
                         e = exp2_poly2(x);
+                    else if (p.diag & 2)    // diag bit 1 (TIMING DIAGNOSTIC ONLY): no MUFU, one FMA per element
+                        e = ffma2(x, make_float2(0.001f, 0.001f), make_float2(1.f, 1.f));
                     else
                         e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
                     ps2 = fadd2(ps2, e);
@@ -633,7 +677,7 @@ attn_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
             }
             l_run += ps2.x + ps2.y;
             if (j > 0) {
-                mbar_wait(pv_done, (j - 1) & 1);
+                wait_pp(pv_done, (j - 1) & 1);
                 tc_fence_after();
                 if (__any_sync(0xffffffffu, alpha != 1.0f)) {
                     uint32_t r[32];
@@ -730,6 +774,10 @@ extern "C" int fd_attn_fwd(const FdAttnArgs* a, void* stream_) {
     p.bar_all = bar_all;
     static const int early = getenv("FD_ATTN_EARLY") ? atoi(getenv("FD_ATTN_EARLY")) : 1;
     p.early = early;
+    static const int spin = getenv("FD_ATTN_SPIN") ? atoi(getenv("FD_ATTN_SPIN")) : 0;
+    p.spin = spin;
+    static const int diag = getenv("FD_ATTN_DIAG") ? atoi(getenv("FD_ATTN_DIAG")) : 0;
+    p.diag = diag;
     static bool attr_set = false;
     if (!attr_set) {
         FD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));

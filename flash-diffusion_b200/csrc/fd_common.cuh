@@ -86,6 +86,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// busy polling (test_wait never suspends the thread): for waits that sit on a short producer -> consumer ping-pong,
+// where the wake-up latency of a suspended try_wait is paid on every hop
+__device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
+    uint32_t spins = 0;
+    while (!mbar_test_wait(bar, parity)) {
+        if (++spins > FD_SPIN_LIMIT) {
+            printf("fd: mbarrier (poll) timeout block %d thread %d\n", (int)blockIdx.x, (int)threadIdx.x);
+            __trap();
+        }
+    }
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
