@@ -46,7 +46,7 @@ struct AttnKParams {
     float* lse;  // [B,H,Nq] or null
     int H;
     int bar_all;  // attn_fwd1: 1 = one 256-thread barrier for the row-maximum exchange (r02 A/B, FD_ATTN_BAR256)
-    int diag;     // attn_fwd1: FD_ATTN_DIAG bits — timing diagnostics that BREAK the result (1: no row-max exchange, 2: no MUFU)
+    int diag;     // attn_fwd1: FD_ATTN_DIAG bits — timing diagnostic that BREAKS the result (bit 0: no row-maximum exchange)
     int spin;     // attn_fwd1: 1 = the S / P ping-pong waits poll with test_wait instead of suspending in try_wait (FD_ATTN_SPIN)
     int early;    // attn_fwd1: 1 = first TMA loads issued before the TMEM allocation / block sync (FD_ATTN_EARLY=0: off)
 };
@@ -447,7 +447,9 @@ constexpr int ATT1_VST = 2;                   // V ring: released after O += P V
 constexpr int ATT1_THREADS = 64 + 256;        // TMA warp, MMA warp, 2 column halves x 4 softmax warps
 constexpr int ATT1_SMEM = ATT_TILE_BYTES + (ATT1_KST + ATT1_VST) * ATT_TILE_BYTES + 256 + 2048 + 1024;
 
-template <int POLY>     // 0: every exponential on the MUFU; m > 0: every m-th pair of scores on the FMA pipe (cubic)
+// POLY 0: every exponential on the MUFU; m > 0: every m-th pair of scores on the FMA pipe (cubic); -1: NO exponential
+// (FD_ATTN_POLY=-1: timing diagnostic with a wrong result — the floor of everything that is not an exponential).
+template <int POLY>
 __global__ void __launch_bounds__(ATT1_THREADS, 2)
 attn_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttnKParams p) {
@@ -667,7 +669,7 @@ attn_fwd1_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
                     float2 e;
                     if (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == (POLY > 1 ? 1 : 0))
                         e = exp2_poly2(x);
-                    else if (p.diag & 2)    // diag bit 1 (TIMING DIAGNOSTIC ONLY): no MUFU, one FMA per element
+                    else if (POLY < 0)      // TIMING DIAGNOSTIC ONLY: no MUFU, one FMA per element
                         e = ffma2(x, make_float2(0.001f, 0.001f), make_float2(1.f, 1.f));
                     else
                         e = make_float2(fast_exp2(x.x), fast_exp2(x.y));
@@ -783,6 +785,7 @@ extern "C" int fd_attn_fwd(const FdAttnArgs* a, void* stream_) {
         FD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         FD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         FD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd1_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT1_SMEM));
+        FD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd1_kernel<-1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT1_SMEM));
         FD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd1_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT1_SMEM));
         FD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd1_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT1_SMEM));
         FD_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd1_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT1_SMEM));
@@ -798,7 +801,9 @@ extern "C" int fd_attn_fwd(const FdAttnArgs* a, void* stream_) {
         // 710 TFLOP/s at 1024 / 4096 keys vs 507 / 690 at 25 %, and the 50 % variant falls off the register cliff),
         // so the default is 0 and the training and inference forwards are the same kernel.
         static const int poly = getenv("FD_ATTN_POLY") ? atoi(getenv("FD_ATTN_POLY")) : 0;
-        if (a->lse != nullptr || poly == 0)
+        if (poly < 0)
+            attn_fwd1_kernel<-1><<<grid, ATT1_THREADS, ATT1_SMEM, stream>>>(tq, tk, tv, p);
+        else if (a->lse != nullptr || poly == 0)
             attn_fwd1_kernel<0><<<grid, ATT1_THREADS, ATT1_SMEM, stream>>>(tq, tk, tv, p);
         else if (poly == 2)
             attn_fwd1_kernel<2><<<grid, ATT1_THREADS, ATT1_SMEM, stream>>>(tq, tk, tv, p);
