@@ -13,6 +13,8 @@ flash_diffusion_model.py:383-397); the encoder runs frozen, without a graph.  No
 There is no network: `from_pretrained` builds the architecture of the checkpoints the example scripts name with random
 weights (load real ones with `load_state_dict`, diffusers keys).  Math restated in oracle/vae.py.
 """
+import math
+
 import torch
 import torch.nn as nn
 
@@ -294,40 +296,38 @@ class AutoencoderKLDiffusers(BaseModel):
             return self.vae_model.decode(z)
         return self._decode_tiled(z)
 
+    @staticmethod
+    def _tile_window(n, centre, device):
+        """Gaussian tile weight of the reference's `Tiler._gaussian_weights` (src/flash/models/utils.py:156-204):
+        exp(-(t - centre)^2 / n^2 / (2 var)) / sqrt(2 pi var), var = 0.01 — evaluated in float64 as numpy does."""
+        t = torch.arange(n, dtype=torch.float64, device=device)
+        var = 0.01
+        return torch.exp(-(t - centre) ** 2 / (n * n) / (2 * var)) / math.sqrt(2 * math.pi * var)
+
     @torch.no_grad()
     def _decode_tiled(self, z):
+        """reference :80-124 — `Tiler.get_tiles` (stride = tile - overlap, the overlap only along an axis that is
+        actually tiled, trailing tiles may be partial), every tile zero-padded to the tile size, decoded, cropped,
+        then `Tiler.merge_tiles("gaussian")`: sum(tile * w) / sum(w) with the gaussian window of the CROPPED tile (its
+        column window is centred on (n - 1) / 2, its row window on n / 2, as upstream).  On the device, whole batch at
+        once (the reference loops over samples and merges on the CPU)."""
         th, tw = self.tiling_size
         oh = self.tiling_overlap[0] if z.shape[2] > th else 0
         ow = self.tiling_overlap[1] if z.shape[3] > tw else 0
         f = self.downsampling_factor
         B, _, H, W = z.shape
-        out = torch.zeros((B, self.vae_model.config.out_channels, H * f, W * f), device=z.device, dtype=torch.float32)
-        wsum = torch.zeros((1, 1, H * f, W * f), device=z.device, dtype=torch.float32)
-
-        def ramp(n, lo, hi, ov):
-            w = torch.ones(n, device=z.device)
-            if ov > 0:
-                r = (torch.arange(ov * f, device=z.device, dtype=torch.float32) + 0.5) / (ov * f)
-                if lo:
-                    w[:ov * f] = r
-                if hi:
-                    w[n - ov * f:] = torch.minimum(w[n - ov * f:], r.flip(0))
-            return w
-
-        for i in range(0, H, max(th - oh, 1)):
-            for j in range(0, W, max(tw - ow, 1)):
+        out = torch.zeros((B, self.vae_model.config.out_channels, H * f, W * f), device=z.device, dtype=torch.float64)
+        wsum = torch.zeros((1, 1, H * f, W * f), device=z.device, dtype=torch.float64)
+        for i in range(0, H, th - oh):
+            for j in range(0, W, tw - ow):
                 tile = z[:, :, i:i + th, j:j + tw]
                 hh, ww = tile.shape[2], tile.shape[3]
                 pad = torch.zeros((B, z.shape[1], th, tw), device=z.device, dtype=z.dtype)
                 pad[:, :, :hh, :ww] = tile                    # decode at the fixed tile size (reference :97-104)
                 dec = self.vae_model.decode(pad)[:, :, :hh * f, :ww * f]
-                wy = ramp(hh * f, i > 0, i + th < H, oh)
-                wx = ramp(ww * f, j > 0, j + tw < W, ow)
+                wy = self._tile_window(hh * f, hh * f / 2, z.device)
+                wx = self._tile_window(ww * f, (ww * f - 1) / 2, z.device)
                 w2 = wy[:, None] * wx[None, :]
-                out[:, :, i * f:i * f + hh * f, j * f:j * f + ww * f] += dec * w2
+                out[:, :, i * f:i * f + hh * f, j * f:j * f + ww * f] += dec.double() * w2
                 wsum[:, :, i * f:i * f + hh * f, j * f:j * f + ww * f] += w2
-                if j + tw >= W:
-                    break
-            if i + th >= H:
-                break
-        return out / wsum.clamp_min(1e-8)
+        return (out / wsum).float()
