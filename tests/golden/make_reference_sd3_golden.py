@@ -135,6 +135,34 @@ def main():
         out["cases"][case["name"]] = rec
         print(case["name"], "start_idx", draws["start_idx"], "t0", rec["start_timestep"], "loss_G", float(loss_G),
               "loss_D", float(loss_D))
+    # ---- the reference's SD3 sampler (:683-843): few-step flash sampling (re-noising Euler), CFG, teacher reference samples
+    student.load_state_dict(s_state)
+    cfg = FlashDiffusionSD3Config(K=[K], num_iterations_per_K=[10 ** 9], input_key="image")
+    mk = lambda cls, **kw: cls.from_pretrained("stabilityai/stable-diffusion-3-medium", subfolder="scheduler", **kw)
+    model = FlashDiffusionSD3(cfg, student_denoiser=student, teacher_denoiser=teacher,
+                              teacher_noise_scheduler=mk(sched_mod.FlowMatchEulerDiscreteScheduler,
+                                                         timestep_spacing="trailing"),
+                              sampling_noise_scheduler=mk(sched_mod.FlashFlowMatchEulerDiscreteScheduler,
+                                                          timestep_spacing="trailing"),
+                              teacher_sampling_noise_scheduler=mk(sched_mod.FlowMatchEulerDiscreteScheduler),
+                              vae=None, conditioner=None, discriminator=None, pipeline=Pipeline(batch))
+    z0 = torch.randn(B, 4, HW, HW, generator=g)
+    out["sample"] = {}
+    for name, kw in [("flash4_cfg1", dict(num_steps=4, guidance_scale=1.0)),
+                     ("flash2_cfg2.5_teacher", dict(num_steps=2, guidance_scale=2.5, teacher_guidance_scale=5.0,
+                                                    log_teacher_samples=True)),
+                     ("flash1_max1", dict(num_steps=1, guidance_scale=1.0, max_samples=1))]:
+        torch.manual_seed(77)
+        with G.RandnTape() as tape, G.Tape() as tape2:
+            smp, smp_ref = model.sample(z0.clone(), conditioner_inputs={"text": batch["text"]}, **kw)
+        out["sample"][name] = dict(kwargs=kw, z=z0.clone(), randn=tape.events,
+                                   randn_like=[t for k, t in tape2.events if k == "randn_like"],
+                                   other_draws=[k for k, _ in tape2.events if k != "randn_like"],
+                                   sample=smp.clone(), sample_ref=None if smp_ref is None else smp_ref.clone(),
+                                   timesteps=model.sampling_noise_scheduler.timesteps.clone())
+        print("sd3 sample", name, "randn", len(tape.events), "randn_like", len(out["sample"][name]["randn_like"]),
+              model.sampling_noise_scheduler.timesteps.tolist())
+
     path = os.path.join(HERE, "reference_sd3_step.pt")
     torch.save(out, path)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")

@@ -85,3 +85,49 @@ def test_product_sd3_host_logic_matches_reference_run(name):
     assert _rel(out["teacher_output"], rec["teacher_output"]) < 1e-4
     assert torch.allclose(torch.as_tensor(out["loss"][0]).detach(), rec["loss_G"], rtol=2e-4, atol=1e-6)
     _check_grads(rec, case, student, disc, out["loss"][0], out["loss"][1])
+
+
+class _ReplayRandn:
+    def __init__(self, tensors):
+        self.queue, self.orig = list(tensors), torch.randn
+
+    def __enter__(self):
+        def randn(*shape, **k):
+            t = self.queue.pop(0)
+            want = tuple(shape[0]) if len(shape) == 1 and not isinstance(shape[0], int) else tuple(shape)
+            assert tuple(t.shape) == want, (t.shape, want)
+            return t.to(device=k.get("device") or "cpu", dtype=k.get("dtype") or t.dtype)
+        torch.randn = randn
+        return self
+
+    def __exit__(self, *exc):
+        torch.randn = self.orig
+        assert exc[0] is not None or not self.queue, f"{len(self.queue)} recorded draws were not consumed"
+
+
+@pytest.mark.parametrize("name", list(GOLD["sample"]))
+def test_product_sd3_sampler_matches_reference_run(name):
+    """`FlashDiffusionSD3.sample()` (reference flash_sd3/flash_diffusion_model.py:683-843): flash sampling on the
+    re-noising flow-matching scheduler, CFG, `max_samples`, the teacher's Euler reference samples."""
+    from flash.models.flash_sd3 import FlashDiffusionSD3, FlashDiffusionSD3Config
+    from flash.schedulers import FlashFlowMatchEulerDiscreteScheduler, FlowMatchEulerDiscreteScheduler
+    rec = GOLD["sample"][name]
+    assert rec["other_draws"] == [] and rec["randn_like"] == []
+    student, teacher, _ = _models()
+    cfg = FlashDiffusionSD3Config(K=[GOLD["K"]], num_iterations_per_K=[10 ** 9], input_key="image")
+    mk = lambda cls, **kw: cls.from_pretrained("stabilityai/stable-diffusion-3-medium", subfolder="scheduler", **kw)
+    model = FlashDiffusionSD3(cfg, student_denoiser=student, teacher_denoiser=teacher,
+                              teacher_noise_scheduler=mk(FlowMatchEulerDiscreteScheduler, timestep_spacing="trailing"),
+                              sampling_noise_scheduler=mk(FlashFlowMatchEulerDiscreteScheduler,
+                                                          timestep_spacing="trailing"),
+                              teacher_sampling_noise_scheduler=mk(FlowMatchEulerDiscreteScheduler),
+                              discriminator=None)
+    cin = {k: v for k, v in GOLD["batch"].items() if k != "image"}
+    with _ReplayRandn(rec["randn"]):
+        smp, smp_ref = model.sample(rec["z"].clone(), conditioner_inputs=cin, **rec["kwargs"])
+    assert model.sampling_noise_scheduler.timesteps.tolist() == rec["timesteps"].tolist()
+    assert smp.shape == rec["sample"].shape and _rel(smp, rec["sample"]) < 1e-4, _rel(smp, rec["sample"])
+    if rec["sample_ref"] is None:
+        assert smp_ref is None
+    else:
+        assert _rel(smp_ref, rec["sample_ref"]) < 1e-4
