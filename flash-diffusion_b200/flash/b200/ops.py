@@ -177,7 +177,8 @@ def conv_dgrad(dy, geom, mod, stride):
     return raw.depth_to_space(out, NB, H, W, mod.cin)
 
 
-_NO_COLSTATS = os.environ.get("FD_NO_COLSTATS") is not None
+_NO_COLSTATS = (os.environ.get("FD_NO_COLSTATS") is not None
+                or os.environ.get("FD_NO_TMA_STORE") is not None)     # the statistics live in the TMA-store epilogue
 
 
 def colstats_of(t):
