@@ -78,9 +78,11 @@ class FlashDiffusionSD3(FlashDiffusion):
             self.use_adversarial_loss = True
         self.disc_backbone = self.teacher_denoiser
         if self.distill_loss_type == "lpips":
-            raise NotImplementedError(
-                "distill_loss_type='lpips' needs LPIPS-VGG + VAE decoder weights that are not available offline "
-                "(SURVEY.md §8f-2, NEXT row); use 'l2'")
+            # reference :130-131 `lpips.LPIPS(net="vgg")` — the VGG16 stack on the B200 conv kernels (flash.models.lpips)
+            from ..lpips import LPIPS
+            if self.vae is None:
+                raise ValueError("distill_loss_type='lpips' decodes the latents: a VAE is required (reference :409-410)")
+            self.lpips = LPIPS(net="vgg")
         self.K_steps = np.cumsum(self.num_iterations_per_K)
         self.K_prev = self.K[0]
         self.use_cuda_graphs = True
@@ -206,6 +208,19 @@ class FlashDiffusionSD3(FlashDiffusion):
     def _distill_loss(self, student_output, teacher_output):
         if self.distill_loss_type == "l2":
             return torch.mean(((student_output - teacher_output) ** 2).reshape(student_output.shape[0], -1), 1).mean()
+        if self.distill_loss_type == "l1":
+            return torch.mean(torch.abs(student_output - teacher_output).reshape(student_output.shape[0], -1), 1).mean()
+        if self.distill_loss_type == "lpips":
+            # reference :391-411 — centre crop of at most 64x64 latents (clamped to the latent size, unlike the
+            # epsilon model's), decode both, clamp to [-1, 1], LPIPS-VGG, mean
+            H, W = student_output.shape[2:]
+            ch, cw = max((H - 64) // 2, 0), max((W - 64) // 2, 0)
+            s_crop = student_output[:, :, ch:min(ch + 64, H), cw:min(cw + 64, W)]
+            t_crop = teacher_output[:, :, ch:min(ch + 64, H), cw:min(cw + 64, W)]
+            decoded_student = self.vae.decode(s_crop).clamp(-1, 1)
+            with torch.no_grad():                  # the teacher output carries no graph in the reference either
+                decoded_teacher = self.vae.decode(t_crop).clamp(-1, 1)
+            return self.lpips(decoded_student, decoded_teacher).mean()
         raise NotImplementedError(f"Loss type {self.distill_loss_type} not implemented")
 
     def _dmd_loss(self, student_output, student_conditioning, conditioning, unconditional_conditioning, K, K_step,

@@ -41,8 +41,15 @@ def sincos_2d(embed_dim, grid_size, base_size, interpolation_scale):
     gh, gw = (grid_size, grid_size) if isinstance(grid_size, int) else grid_size
     g_h = np.arange(gh, dtype=np.float32) / (gh / base_size) / interpolation_scale
     g_w = np.arange(gw, dtype=np.float32) / (gw / base_size) / interpolation_scale
-    grid = np.stack(np.meshgrid(g_w, g_h), axis=0).reshape(2, 1, gh, gw)          # w goes first (upstream)
-    return np.concatenate([_sincos_1d(embed_dim // 2, grid[0]), _sincos_1d(embed_dim // 2, grid[1])], axis=1)
+    # upstream builds np.meshgrid(g_w, g_h) and embeds the two coordinate planes (w first); the table is separable —
+    # row i * gw + j = [sincos(g_w[j]) | sincos(g_h[i])] — so two 1-D tables are broadcast into the float32 result
+    # (same float64 arithmetic per entry; the SD3 table is 36864 x 1536)
+    e_w = _sincos_1d(embed_dim // 2, g_w).astype(np.float32)
+    e_h = _sincos_1d(embed_dim // 2, g_h).astype(np.float32)
+    out = np.empty((gh, gw, 2 * e_w.shape[1]), dtype=np.float32)
+    out[:, :, :e_w.shape[1]] = e_w[None, :, :]
+    out[:, :, e_w.shape[1]:] = e_h[:, None, :]
+    return out.reshape(gh * gw, -1)
 
 
 class PatchEmbed(_Container):

@@ -31,6 +31,10 @@ _KNOWN = {
     ("stabilityai/sdxl-vae", ""): dict(scaling_factor=0.13025),
     ("stabilityai/stable-diffusion-xl-base-1.0", "vae"): dict(scaling_factor=0.13025),
     ("PixArt-alpha/PixArt-XL-2-1024-MS", "vae"): dict(scaling_factor=0.13025),
+    # SD3: 16 latent channels, no quant / post-quant 1x1 convs (examples/train_flash_sd3.py:88-96; the reference
+    # wrapper applies `scaling_factor` only and never the checkpoint's shift_factor, vae/autoencoderKL.py:59,78)
+    ("stabilityai/stable-diffusion-3-medium", "vae"): dict(scaling_factor=1.5305, latent_channels=16,
+                                                           use_quant_conv=False, use_post_quant_conv=False),
 }
 
 
@@ -126,13 +130,13 @@ class AutoencoderKL(nn.Module):
 
     def __init__(self, in_channels=3, out_channels=3, latent_channels=4, block_out_channels=(128, 256, 512, 512),
                  layers_per_block=2, norm_num_groups=32, scaling_factor=0.18215, latents_mean=None, latents_std=None,
-                 **unused):
+                 use_quant_conv=True, use_post_quant_conv=True, **unused):
         super().__init__()
         boc = list(block_out_channels)
         self.encoder = VaeEncoder(in_channels, latent_channels, boc, layers_per_block, norm_num_groups)
         self.decoder = VaeDecoder(out_channels, latent_channels, boc, layers_per_block, norm_num_groups)
-        self.quant_conv = nn.Conv2d(2 * latent_channels, 2 * latent_channels, 1)
-        self.post_quant_conv = nn.Conv2d(latent_channels, latent_channels, 1)
+        self.quant_conv = nn.Conv2d(2 * latent_channels, 2 * latent_channels, 1) if use_quant_conv else None
+        self.post_quant_conv = nn.Conv2d(latent_channels, latent_channels, 1) if use_post_quant_conv else None
         from types import SimpleNamespace
         self.config = SimpleNamespace(in_channels=in_channels, out_channels=out_channels, latent_channels=latent_channels,
                                       block_out_channels=tuple(boc), layers_per_block=layers_per_block,
@@ -214,7 +218,8 @@ class AutoencoderKL(nn.Module):
                 geom = (NB, geom[1] // 2, geom[2] // 2)
         h = self._mid(enc.mid_block, h, geom)
         h = ops.group_norm(h, geom, enc.conv_norm_out, silu=True)
-        head = self._pack("e_out", lambda: ConvPack(_FusedConv(enc.conv_out, self.quant_conv)))
+        head = self._pack("e_out", lambda: ConvPack(enc.conv_out if self.quant_conv is None
+                                                    else _FusedConv(enc.conv_out, self.quant_conv)))
         m = ops.to_nchw(ops.conv3x3(h, geom, head, out_fp32=True), geom, 2 * self.config.latent_channels)
         mean, logvar = m.chunk(2, dim=1)
         return mean, logvar.clamp(-30.0, 20.0)
@@ -233,8 +238,9 @@ class AutoencoderKL(nn.Module):
         dec = self.decoder
         NB, C, H, W = z.shape
         # post_quant_conv: a 4x4 channel mix of the fp32 latent at the NCHW boundary (16 FMAs per pixel)
-        wq = self.post_quant_conv.weight.detach().float().reshape(C, C)
-        z = torch.einsum("oi,bihw->bohw", wq, z.float()) + self.post_quant_conv.bias.detach().float().view(1, C, 1, 1)
+        if self.post_quant_conv is not None:
+            wq = self.post_quant_conv.weight.detach().float().reshape(C, C)
+            z = torch.einsum("oi,bihw->bohw", wq, z.float()) + self.post_quant_conv.bias.detach().float().view(1, C, 1, 1)
         conv_in = self._pack("d_in", lambda: ConvPack(dec.conv_in))
         geom = (NB, H, W)
         h = ops.conv3x3(ops.to_nhwc(z, conv_in.cin), geom, conv_in)

@@ -53,6 +53,30 @@ _KNOWN_CONFIGS = {
 }
 
 
+
+def _host_tables(cls):
+    """Scheduler tables are a few thousand floats that live on the host whatever the ambient default device is (the
+    full-size example scripts are plumbing-tested under `torch.device("meta")`): run the table-building methods of
+    `cls` under an explicit CPU device context."""
+    import functools
+    for name in ("__init__", "set_timesteps"):
+        fn = cls.__dict__.get(name)
+        if fn is None:
+            continue
+
+        def make(fn):
+            @functools.wraps(fn)
+            def wrapped(*a, **k):
+                if torch.get_default_device().type == "cpu":
+                    return fn(*a, **k)
+                with torch.device("cpu"):
+                    return fn(*a, **k)
+            return wrapped
+        setattr(cls, name, make(fn))
+    return cls
+
+
+@_host_tables
 class _SchedulerBase:
     order = 1
 
@@ -101,6 +125,7 @@ class _SchedulerBase:
         self.timesteps = torch.from_numpy(ts)
 
 
+@_host_tables
 class DDPMScheduler(_SchedulerBase):
     """Ancestral DDPM sampler (epsilon prediction, fixed_small variance, clip_sample as in diffusers'
     defaults).  The reference's own test builds every scheduler as `DDPMScheduler()`
@@ -142,6 +167,7 @@ class DDPMScheduler(_SchedulerBase):
         return (prev,)
 
 
+@_host_tables
 class DPMSolverMultistepScheduler(_SchedulerBase):
     """DPM-Solver++ (2M, midpoint), epsilon prediction, `final_sigmas_type="zero"`, `lower_order_final`
     (SURVEY.md Appendix B.2).  `set_timesteps` resets the multistep history, so a rollout entered at
@@ -269,6 +295,7 @@ class DPMSolverMultistepScheduler(_SchedulerBase):
         return sample
 
 
+@_host_tables
 class LCMScheduler(_SchedulerBase):
     """Latent-consistency sampler: boundary-condition mix with sigma_data 0.5 and
     timestep_scaling 10, re-noising to the next timestep except on the last step."""
@@ -319,6 +346,7 @@ class LCMScheduler(_SchedulerBase):
         return (prev, denoised)
 
 
+@_host_tables
 class EulerDiscreteScheduler(_SchedulerBase):
     """diffusers `EulerDiscreteScheduler` (epsilon prediction) — the `TEACHER_SAMPLING_SCHEDULER` of the example yamls,
     used only to draw the teacher's reference samples in `log_samples` (reference flash_diffusion_model.py:866-913):
@@ -365,6 +393,7 @@ class EulerDiscreteScheduler(_SchedulerBase):
         return (prev,)
 
 
+@_host_tables
 class EulerAncestralDiscreteScheduler(EulerDiscreteScheduler):
     """ancestral variant: deterministic step to sigma_down, then fresh noise of scale sigma_up."""
 
@@ -380,6 +409,7 @@ class EulerAncestralDiscreteScheduler(EulerDiscreteScheduler):
         return (prev,)
 
 
+@_host_tables
 class FlowMatchEulerDiscreteScheduler:
     """Rectified-flow Euler scheduler used by the SD3 recipe (reference examples/train_flash_sd3.py:123-141,
     consumed at src/flash/models/flash_sd3/flash_diffusion_model.py:253-324 and :1043-1060).
@@ -469,6 +499,7 @@ class FlowMatchEulerDiscreteScheduler:
         return sample
 
 
+@_host_tables
 class FlashFlowMatchEulerDiscreteScheduler(FlowMatchEulerDiscreteScheduler):
     """Few-step student sampler of the SD3 recipe (reference examples/configs/flash_sd3.yaml `SAMPLING_SCHEDULER`,
     consumed at flash_sd3/flash_diffusion_model.py:694-790).  The class exists only in the authors' diffusers fork;

@@ -109,7 +109,9 @@ class Trainer:
             torch.cuda.set_device(device)
         if self.world_size > 1 and not dist.is_initialized():
             dist.init_process_group("nccl" if use_cuda else "gloo", **({"device_id": device} if use_cuda else {}))
-        model.to(device)
+        plumbing_on_meta = self.max_steps == 0 and any(p.is_meta for p in model.parameters())
+        if not plumbing_on_meta:        # FLASH_MAX_STEPS=0 under torch.device("meta"): shapes only, nothing to move
+            model.to(device)
         model.trainer = self
         if hasattr(model, "configure_optimizers") and getattr(model, "optims", None) is None:
             model.configure_optimizers()
@@ -133,7 +135,8 @@ class Trainer:
         summary = {"steps": 0, "device": str(device), "losses": [], "sanity_batch": None}
         if done and loader is not None:
             # plumbing-only run (FLASH_MAX_STEPS=0): pull ONE batch through the data pipeline, run no step
-            first = next(iter(loader))
+            with torch.device("cpu"):        # the data pipeline is host work whatever the ambient default device
+                first = next(iter(loader))
             summary["sanity_batch"] = {k: (list(v.shape) if isinstance(v, torch.Tensor) else f"{type(v).__name__}[{len(v)}]")
                                        for k, v in first.items()}
         for epoch in range(self.max_epochs):

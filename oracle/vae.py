@@ -154,13 +154,15 @@ class Decoder(nn.Module):
 
 class AutoencoderKLOracle(nn.Module):
     def __init__(self, in_channels=3, out_channels=3, latent_channels=4, block_out_channels=(128, 256, 512, 512),
-                 layers_per_block=2, norm_num_groups=32, scaling_factor=0.18215):
+                 layers_per_block=2, norm_num_groups=32, scaling_factor=0.18215, use_quant_conv=True,
+                 use_post_quant_conv=True):
         super().__init__()
         boc = list(block_out_channels)
         self.encoder = Encoder(in_channels, latent_channels, boc, layers_per_block, norm_num_groups)
         self.decoder = Decoder(out_channels, latent_channels, boc, layers_per_block, norm_num_groups)
-        self.quant_conv = nn.Conv2d(2 * latent_channels, 2 * latent_channels, 1)
-        self.post_quant_conv = nn.Conv2d(latent_channels, latent_channels, 1)
+        # the SD3 VAE config switches both 1x1 convs off (identity)
+        self.quant_conv = nn.Conv2d(2 * latent_channels, 2 * latent_channels, 1) if use_quant_conv else nn.Identity()
+        self.post_quant_conv = nn.Conv2d(latent_channels, latent_channels, 1) if use_post_quant_conv else nn.Identity()
         self.scaling_factor = scaling_factor
         self.latent_channels = latent_channels
 

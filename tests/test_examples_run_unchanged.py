@@ -5,6 +5,15 @@ compat shims for the packages that cannot be installed offline (flash-diffusion_
 pytorch_lightning, braceexpand, lpips).  Its yaml (read by the script from ./configs/flash_sd.yaml) is the reference's
 own file with the dataset path pointed at a synthetic webdataset shard and the rollout shortened.
 
+The other three training scripts of the BASELINE configs — examples/train_flash_sdxl.py (config 2), train_flash_pixart.py
+(config 3), train_flash_sd3.py (config 4) — run unmodified the same way (`test_full_size_scripts_run_unchanged`).  They
+build 2-5 billion-parameter teachers / students / text encoders, so on a box without a GPU the script is executed under
+`torch.device("meta")`: every constructor, every `load_state_dict` of the HF-layout checkpoint keys (strict=True in the
+SD3 script), the per-key weight surgery of the SDXL / PixArt scripts, LoRA injection through `peft.get_peft_model`, the
+schedulers' `from_pretrained`, the discriminators, FlashDiffusion(SD3) with the lpips objective, the data module and the
+trainer run for real on shapes, without touching the weights' memory; one batch is then pulled through the data pipeline.
+On a B200 they run 2 real training steps (`tools/example_run_cmd.py <name>`; profiles/r02_example_train_flash_*_gpu.txt).
+
 Without a GPU (this container) the run is plumbing-only — everything the script builds (VAE, CLIP conditioner, teacher /
 LoRA student, discriminator, FlashDiffusion with the lpips loss, data module with its filter / mapper chain, trainer,
 callbacks) plus one batch through the data pipeline (FLASH_MAX_STEPS=0; the denoisers are CUDA-only).  The reference
@@ -42,8 +51,8 @@ def make_shard(path, n=6, px=1024):
                 tf.addfile(info, io.BytesIO(data))
 
 
-def write_config(workdir, shard, steps):
-    with open(REF_YAML) as f:
+def write_config(workdir, shard, steps, ref_yaml=None, name="flash_sd.yaml"):
+    with open(ref_yaml or REF_YAML) as f:
         cfg = yaml.safe_load(f)
     cfg["SHARDS_PATH_OR_URLS"] = [f"pipe:cat {shard}"]
     cfg["K"] = [4, 4, 4, 4]                 # shorter teacher rollout; every other setting (lpips, DMD, lsgan, ...) as shipped
@@ -51,7 +60,7 @@ def write_config(workdir, shard, steps):
     cfg["NUM_STEPS"] = [1]
     cfg["CKPT_EVERY_N_STEPS"] = max(steps, 1)
     os.makedirs(os.path.join(workdir, "configs"), exist_ok=True)
-    with open(os.path.join(workdir, "configs", "flash_sd.yaml"), "w") as f:
+    with open(os.path.join(workdir, "configs", name), "w") as f:
         yaml.safe_dump(cfg, f)
     return cfg
 
@@ -77,6 +86,51 @@ def test_train_flash_sd_runs_unchanged(tmp_path, monkeypatch):
     if steps == 0:
         sb = summary["sanity_batch"]
         assert sb["image"] == [2, 3, 512, 512] and sb["text"].startswith("list")       # mappers: crop, resize, rename
+    else:
+        assert len(summary["losses"]) == steps and all(l["loss_optimizer_0"] > 0 for l in summary["losses"])
+        assert any(f.endswith("_lora.safetensors") for f in os.listdir(tmp_path / "logs" / runs[0] / "checkpoints"))
+
+
+FULL_SIZE = {  # script -> (EXP_NAME suffix of the log dir, keys the mapper chain must deliver, image size)
+    "sdxl": ("FlashSDXL", {"image", "text", "original_size_as_tuple", "crop_coords_top_left", "target_size_as_tuple"}),
+    "pixart": ("FlashPixart", {"image", "text"}),
+    "sd3": ("FlashSD3", {"image", "text"}),
+}
+
+
+@pytest.mark.parametrize("name", sorted(FULL_SIZE))
+def test_full_size_scripts_run_unchanged(name, tmp_path, monkeypatch):
+    """examples/train_flash_{sdxl,pixart,sd3}.py, unmodified (see the module docstring)."""
+    import torch
+    ref_dir = os.environ.get("FLASH_REF_DIR", "/root/reference/examples")
+    script = os.path.join(ref_dir, f"train_flash_{name}.py")
+    ref_yaml = os.path.join(ref_dir, "configs", f"flash_{name}.yaml")
+    if not (os.path.exists(script) and os.path.exists(ref_yaml)):
+        pytest.skip("the reference tree is not on this box")
+    steps = 2 if torch.cuda.is_available() else 0
+    shard = str(tmp_path / "000000.tar")
+    make_shard(shard)
+    cfg = write_config(str(tmp_path), shard, steps, ref_yaml=ref_yaml, name=f"flash_{name}.yaml")
+    assert cfg["DISTILL_LOSS_TYPE"] == "lpips" and cfg["LORA"]
+    monkeypatch.chdir(tmp_path)
+    for k, v in dict(SLURM_NPROCS="1", SLURM_NNODES="1", SLURM_JOB_ID="0", FLASH_MAX_STEPS=str(steps)).items():
+        monkeypatch.setenv(k, v)
+    compat = os.path.join(ROOT, "flash-diffusion_b200", "compat")
+    monkeypatch.setattr(sys, "path", sys.path + [compat])
+    if steps == 0:
+        with torch.device("meta"):
+            ns = runpy.run_path(script, run_name="__main__")
+    else:
+        ns = runpy.run_path(script, run_name="__main__")
+    assert "main" in ns
+    runs = sorted(os.listdir(tmp_path / "logs"))
+    exp, keys = FULL_SIZE[name]
+    assert len(runs) == 1 and exp in runs[0]
+    summary = json.load(open(tmp_path / "logs" / runs[0] / "fit_summary.json"))
+    assert summary["steps"] == steps
+    if steps == 0:
+        sb = summary["sanity_batch"]
+        assert keys <= set(sb) and sb["image"] == [2, 3, 1024, 1024]
     else:
         assert len(summary["losses"]) == steps and all(l["loss_optimizer_0"] > 0 for l in summary["losses"])
         assert any(f.endswith("_lora.safetensors") for f in os.listdir(tmp_path / "logs" / runs[0] / "checkpoints"))

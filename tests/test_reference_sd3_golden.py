@@ -131,3 +131,32 @@ def test_product_sd3_sampler_matches_reference_run(name):
         assert smp_ref is None
     else:
         assert _rel(smp_ref, rec["sample_ref"]) < 1e-4
+
+
+DISTILL = torch.load(os.path.join(HERE, "golden", "reference_sd3_distill.pt"), weights_only=False)
+
+
+@pytest.mark.parametrize("i", range(len(DISTILL["cases"])))
+def test_product_sd3_distill_loss_matches_reference_run(i):
+    """`FlashDiffusionSD3._distill_loss` (reference flash_sd3/flash_diffusion_model.py:373-413): l2, l1 and the lpips
+    branch with its crop CLAMPED to the latent size (the epsilon model's is not) — same stand-in VAE / perceptual
+    distance on both sides (tests/golden/make_reference_sd3_distill_golden.py)."""
+    import make_reference_sd3_distill_golden as GD
+    import make_reference_step_golden as G
+    from flash.models.flash_sd3 import FlashDiffusionSD3, FlashDiffusionSD3Config
+    from flash.schedulers import FlowMatchEulerDiscreteScheduler
+    rec = DISTILL["cases"][i]
+    student, teacher, _ = _models()
+    cfg = FlashDiffusionSD3Config(K=[GOLD["K"]], num_iterations_per_K=[10 ** 9], input_key="image")
+    sched = FlowMatchEulerDiscreteScheduler.from_pretrained("stabilityai/stable-diffusion-3-medium",
+                                                            subfolder="scheduler", timestep_spacing="trailing")
+    m = FlashDiffusionSD3(cfg, student_denoiser=student, teacher_denoiser=teacher, teacher_noise_scheduler=sched,
+                          sampling_noise_scheduler=None, discriminator=None)
+    m.__dict__["vae"], m.__dict__["lpips"] = G.StubVAE(), G.StubLPIPS()
+    m.distill_loss_type = rec["kind"]
+    s_out, t_out = GD.latents(rec["shape"], rec["seed"])
+    s_out.requires_grad_(True)
+    loss = m._distill_loss(s_out, t_out)
+    assert torch.allclose(loss, rec["loss"], rtol=1e-5), (rec["kind"], rec["shape"], float(loss), float(rec["loss"]))
+    loss.backward()
+    assert torch.isfinite(s_out.grad).all() and float(s_out.grad.abs().sum()) > 0

@@ -122,3 +122,39 @@ def test_softmax_rows_kernels():
     pf, df = p.float(), dp.float()
     want = pf * (df - (pf * df).sum(-1, keepdim=True)) * 0.37
     assert _rel(ds, want) < 8e-3
+
+
+SD3_VAE = dict(latent_channels=16, use_quant_conv=False, use_post_quant_conv=False, scaling_factor=1.5305)
+
+
+def test_sd3_vae_16_latent_channels_without_quant_convs():
+    """The SD3 VAE the reference builds at examples/train_flash_sd3.py:88-96: 16 latent channels, `use_quant_conv` /
+    `use_post_quant_conv` False (the encoder head is conv_out alone, decode starts at decoder.conv_in)."""
+    prod, ora = _pair(seed=2, **SD3_VAE)
+    keys = list(prod.state_dict().keys())
+    assert keys == list(ora.state_dict().keys()) and not any("quant_conv" in k for k in keys)
+    x = torch.randn(2, 3, 64, 64, device="cuda")
+    with torch.no_grad():
+        rm, rl = ora.moments(x)
+    m, l = prod.moments(x)
+    assert m.shape == rm.shape == (2, 16, 8, 8)
+    assert _rel(m, rm) < 2e-2 and _rel(l, rl) < 2e-2, (_rel(m, rm), _rel(l, rl))
+    z = torch.randn(2, 16, 8, 8, device="cuda")
+    zp, zo = z.clone().requires_grad_(True), z.clone().requires_grad_(True)
+    out, ref = prod.decode(zp), ora.decoder(ora.post_quant_conv(zo))
+    assert out.shape == ref.shape == (2, 3, 64, 64) and _rel(out, ref) < 2e-2, _rel(out, ref)
+    g = torch.randn_like(ref)
+    (out * g).sum().backward()
+    (ref * g).sum().backward()
+    assert _cos(zp.grad, zo.grad) > 0.999, _cos(zp.grad, zo.grad)
+
+
+def test_sd3_vae_known_checkpoint():
+    from flash.models.vae import AutoencoderKLDiffusers, AutoencoderKLDiffusersConfig
+    vae = AutoencoderKLDiffusers(AutoencoderKLDiffusersConfig(version="stabilityai/stable-diffusion-3-medium",
+                                                              revision="refs/pr/26", subfolder="vae")).cuda()
+    assert vae.latent_channels == 16 and vae.downsampling_factor == 8
+    assert vae.vae_model.quant_conv is None and vae.vae_model.post_quant_conv is None
+    z = vae.encode(torch.randn(1, 3, 64, 64, device="cuda").clamp(-1, 1))
+    assert z.shape == (1, 16, 8, 8) and torch.isfinite(z).all()
+    assert vae.decode(z).shape == (1, 3, 64, 64)

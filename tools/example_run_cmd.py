@@ -1,11 +1,24 @@
-"""Prints the gpurun command that executes the UNMODIFIED reference script examples/train_flash_sd.py for 2 steps on a
-B200 against this repository (tests/test_examples_run_unchanged.py).  /root/reference does not exist on the GPU box and
-its sources must not be copied into the repo, so the script and its yaml travel INSIDE the command (base64) and land in
-/tmp on the box:   gpurun --timeout 1500 -- "$(python tools/example_run_cmd.py)" """
+"""Prints the gpurun command that executes UNMODIFIED reference example scripts for 2 training steps on a B200 against
+this repository (tests/test_examples_run_unchanged.py).  /root/reference does not exist on the GPU box and its sources
+must not be copied into the repo, so the scripts and their yamls travel INSIDE the command (base64) and land in /tmp on
+the box:
+    gpurun --timeout 1500 -- "$(python tools/example_run_cmd.py sd)"            # examples/train_flash_sd.py
+    gpurun --timeout 1500 -- "$(python tools/example_run_cmd.py sdxl sd3)"      # the full-size scripts
+Each script's pytest tail is written to gpurun_out/r02_example_train_flash_<name>_gpu.txt."""
 import base64
+import sys
 
 b = lambda p: base64.b64encode(open(p, "rb").read()).decode()
-print("mkdir -p /tmp/ref && echo %s | base64 -d > /tmp/ref/train_flash_sd.py && echo %s | base64 -d > /tmp/ref/flash_sd.yaml && "
-      "FLASH_REF_SCRIPT=/tmp/ref/train_flash_sd.py FLASH_REF_YAML=/tmp/ref/flash_sd.yaml timeout 1200 python -m pytest "
-      "tests/test_examples_run_unchanged.py -x -q -s 2>&1 | tail -40 | tee gpurun_out/r02_example_train_flash_sd_gpu.txt"
-      % (b("/root/reference/examples/train_flash_sd.py"), b("/root/reference/examples/configs/flash_sd.yaml")))
+names = sys.argv[1:] or ["sd"]
+cmd = ["mkdir -p /tmp/ref/configs gpurun_out"]
+for n in names:
+    cmd.append("echo %s | base64 -d > /tmp/ref/train_flash_%s.py" % (b(f"/root/reference/examples/train_flash_{n}.py"), n))
+    cmd.append("echo %s | base64 -d > /tmp/ref/configs/flash_%s.yaml" % (b(f"/root/reference/examples/configs/flash_{n}.yaml"), n))
+for n in names:
+    if n == "sd":
+        env, sel = "FLASH_REF_SCRIPT=/tmp/ref/train_flash_sd.py FLASH_REF_YAML=/tmp/ref/configs/flash_sd.yaml", "test_train_flash_sd_runs_unchanged"
+    else:
+        env, sel = "FLASH_REF_DIR=/tmp/ref", f"test_full_size_scripts_run_unchanged[{n}]"
+    cmd.append(f"({env} timeout 900 python -m pytest 'tests/test_examples_run_unchanged.py::{sel}' -x -q -s 2>&1 | tail -40 "
+               f"| tee gpurun_out/r02_example_train_flash_{n}_gpu.txt)")
+print(" && ".join(cmd[: 1 + 2 * len(names)]) + " ; " + " ; ".join(cmd[1 + 2 * len(names):]))
