@@ -352,6 +352,11 @@ class LinearPack:
         self.cache = cache_of(self.bases[0])
         self.N = sum(b.weight.shape[0] for b in self.bases)
         self.K = self.bases[0].weight.shape[1]
+        # TMA needs 16-byte row pitches: an input width that is not a multiple of 8 bf16 (a 123-wide text context, a
+        # 12-wide class vector — the reference's own wrapper tests use such sizes) is zero-padded, in the packs'
+        # K columns here and on the activation side in `pad_k`
+        k_eff = self.K if not (head_pad is not None and pad_cols) else head_pad[0] * head_pad[2]
+        self.k_pad = (k_eff + 7) // 8 * 8 if k_eff % 8 else 0
         if head_pad is not None and head_pad[1] != head_pad[2] and geglu:
             raise NotImplementedError("head padding with GEGLU packs")
         self.N_packed = None
@@ -364,7 +369,15 @@ class LinearPack:
                 w = torch.nn.functional.pad(w.reshape(w.shape[0], H, d), (0, dp - d)).reshape(w.shape[0], H * dp)
             else:
                 w = torch.nn.functional.pad(w.reshape(H, d, w.shape[1]), (0, 0, 0, dp - d)).reshape(H * dp, w.shape[1])
+        if self.k_pad:
+            w = torch.nn.functional.pad(w, (0, self.k_pad - w.shape[1]))
         return w
+
+    def pad_k(self, x):
+        """zero columns up to the packs' padded K (autograd-aware: the gradient of the padding is dropped)"""
+        if self.k_pad and x.shape[1] != self.k_pad:
+            x = torch.nn.functional.pad(x, (0, self.k_pad - x.shape[1]))
+        return x
 
     def _bias(self, b):
         bias = b.bias
@@ -451,6 +464,8 @@ class LinearPack:
                         A = torch.nn.functional.pad(A.reshape(r, H, d), (0, dp - d)).reshape(r, H * dp)
                     else:                   # q/k/v: OUTPUT rows (B's rows) are head-padded
                         Bm = torch.nn.functional.pad(Bm.reshape(H, d, r), (0, 0, 0, dp - d)).reshape(H * dp, r)
+                if self.k_pad:
+                    A = torch.nn.functional.pad(A, (0, self.k_pad - A.shape[1]))
                 a_rows.append(A)
                 b_rows.append(Bm)
             a_cat = torch.cat(a_rows, dim=0)                                         # [n*r, K']
@@ -547,6 +562,8 @@ def _lora_weight_grads(pack, lp, x, t, dy, dt):
                     ga = ga.reshape(r, H, dp)[:, :, :d].reshape(r, H * d)
                 else:
                     gb = gb.reshape(H, dp, r)[:, :d].reshape(H * d, r)
+            if pack.k_pad:
+                ga = ga[:, :l.lora_A["default"].weight.shape[1]]
             grads.append(ga)
             grads.append(gb * l.scaling)
         row += rows_here
@@ -577,6 +594,7 @@ def linear(x, pack: LinearPack, residual=None, want_stats=None, act=0, out_fp32=
     taken, else None.  colstats_images = NB > 0 (no-grad, LoRA-free, with an arena): the epilogue leaves the per-image
     column sums of y for a following GroupNorm (`colstats_of(y)`)."""
     lora_params = pack.lora_params() if pack.has_lora else []
+    x = pack.pad_k(x)
     if _grad_on(x, residual, *lora_params):
         y = _LinearFn.apply(x, residual, pack, act, out_fp32, *lora_params)
         return y if want_stats is None else (y, None)

@@ -120,18 +120,33 @@ class GELUProj(_Container):
 
 
 class FeedForward(_Container):
-    def __init__(self, dim, mult=4):
+    def __init__(self, dim, mult=4, geglu=False):
         super().__init__()
-        self.net = nn.ModuleList([GELUProj(dim, dim * mult), nn.Dropout(0.0), nn.Linear(dim * mult, dim)])
+        self.geglu = geglu               # diffusers GEGLU: proj to 2 * inner, value * gelu(gate)
+        self.net = nn.ModuleList([GELUProj(dim, dim * mult * (2 if geglu else 1)), nn.Dropout(0.0),
+                                  nn.Linear(dim * mult, dim)])
 
 
 class AdaBlock(_Container):
-    def __init__(self, dim, heads, dim_head, cross_dim, bias):
+    """diffusers `BasicTransformerBlock` with norm_type="ada_norm_single": norm1 / norm2 carry parameters only when
+    `norm_elementwise_affine` (PixArt: False, so the state dict has none); attn2 is a cross-attention, a second
+    self-attention (`double_self_attention`) or absent (no cross_attention_dim); no norm3."""
+
+    def __init__(self, dim, heads, dim_head, cross_dim, bias, affine=False, eps=1e-6, geglu=False,
+                 double_self_attention=False):
         super().__init__()
         self.scale_shift_table = nn.Parameter(torch.randn(6, dim) / dim ** 0.5)
+        if affine:
+            self.norm1 = nn.LayerNorm(dim, eps=eps, elementwise_affine=True)
         self.attn1 = Attention(dim, None, heads, dim_head, bias)
-        self.attn2 = Attention(dim, cross_dim, heads, dim_head, bias)
-        self.ff = FeedForward(dim)
+        self.attn2 = None
+        if cross_dim is not None or double_self_attention:
+            if affine:
+                self.norm2 = nn.LayerNorm(dim, eps=eps, elementwise_affine=True)
+            self.attn2 = Attention(dim, None if double_self_attention else cross_dim, heads, dim_head, bias)
+        elif affine:
+            self.norm2 = nn.LayerNorm(dim, eps=eps, elementwise_affine=True)       # still modulates the feed-forward
+        self.ff = FeedForward(dim, geglu=geglu)
 
 
 class DiffusersTransformer2DWrapper(nn.Module):
@@ -141,21 +156,29 @@ class DiffusersTransformer2DWrapper(nn.Module):
                  sample_size=128, num_layers=28, attention_head_dim=72, in_channels=4, out_channels=8, patch_size=2,
                  attention_bias=True, num_attention_heads=16, cross_attention_dim=1152,
                  activation_fn="gelu-approximate", norm_type="ada_norm_single", norm_elementwise_affine=False,
-                 norm_eps=1e-6, caption_channels=4096, **unused):
+                 norm_eps=1e-6, caption_channels=4096, double_self_attention=False, **unused):
         super().__init__()
-        if norm_type != "ada_norm_single" or activation_fn != "gelu-approximate" or norm_elementwise_affine \
-                or patch_size != 2:
-            raise NotImplementedError("only the PixArt-alpha Transformer2DModel variant of the examples is built")
+        if norm_type != "ada_norm_single" or activation_fn not in ("gelu-approximate", "geglu") or patch_size != 2:
+            raise NotImplementedError("built: Transformer2DModel with norm_type='ada_norm_single', patch_size 2 and a "
+                                      "'gelu-approximate' (PixArt-alpha) or 'geglu' feed-forward")
         D = num_attention_heads * attention_head_dim
+        if time_embed_dim != D:
+            raise ValueError(f"time_embed_dim ({time_embed_dim}) must equal the inner dimension ({D}): the adaLN-single "
+                             "table is added to 6 * inner_dim modulation rows")
         self.patch_size, self.out_channels, self.in_channels, self.norm_eps = patch_size, out_channels, in_channels, norm_eps
         self.inner_dim, self.sample_size = D, sample_size
         self.pos_embed = PatchEmbed(sample_size, patch_size, in_channels, D)
         self.adaln_single = AdaLayerNormSingle(time_embed_dim, timesteps_embedding_num_channels,
                                                projection_class_embeddings_input_dim, use_concat_vector_conditioning,
                                                num_vector_conditionings)
-        self.caption_projection = TextProjection(caption_channels, D)
+        if caption_channels is not None:      # PixArt; without it the text states feed attn2.to_k / to_v directly
+            self.caption_projection = TextProjection(caption_channels, D)
+        else:
+            self.caption_projection = None
         self.transformer_blocks = nn.ModuleList(
-            [AdaBlock(D, num_attention_heads, attention_head_dim, cross_attention_dim, attention_bias)
+            [AdaBlock(D, num_attention_heads, attention_head_dim, cross_attention_dim, attention_bias,
+                      affine=bool(norm_elementwise_affine), eps=norm_eps, geglu=activation_fn == "geglu",
+                      double_self_attention=double_self_attention)
              for _ in range(num_layers)])
         self.scale_shift_table = nn.Parameter(torch.randn(2, D) / D ** 0.5)
         self.proj_out = nn.Linear(D, patch_size * patch_size * out_channels)
@@ -266,13 +289,18 @@ class DiffusersTransformer2DWrapper(nn.Module):
         t6, emb = self._adaln(timestep, vector, B, dev)
         # caption projection (gelu-tanh in the epilogue of linear_1)
         cp = self.caption_projection
-        T = crossattn.shape[1]
-        c0 = raw.cast_scale(crossattn.detach().float().contiguous().view(B * T, -1), 1.0)
-        c1 = ops.linear(c0, self._pack("cp1", lambda: LinearPack(cp.linear_1)), act=1)
-        ctx = ops.linear(c1, self._pack("cp2", lambda: LinearPack(cp.linear_2)))
-        kv_len = None
-        if mask is not None:      # T5 padding mask (ones then zeros): per-sample number of valid keys
-            kv_len = mask.to(device=dev).reshape(B, T).sum(dim=1).to(torch.int32).contiguous()
+        ctx = kv_len = None
+        needs_ctx = any(b.attn2 is not None and b.attn2.is_cross for b in self.transformer_blocks)
+        if needs_ctx:
+            if crossattn is None:
+                raise ValueError("this configuration has cross-attention layers: conditioning['cond']['crossattn'] is required")
+            T = crossattn.shape[1]
+            ctx = raw.cast_scale(crossattn.detach().float().contiguous().view(B * T, -1), 1.0)
+            if cp is not None:
+                c1 = ops.linear(ctx, self._pack("cp1", lambda: LinearPack(cp.linear_1)), act=1)
+                ctx = ops.linear(c1, self._pack("cp2", lambda: LinearPack(cp.linear_2)))
+            if mask is not None:      # T5 padding mask (ones then zeros): per-sample number of valid keys
+                kv_len = mask.to(device=dev).reshape(B, T).sum(dim=1).to(torch.int32).contiguous()
         # patch embedding: 2x2 stride-2 conv == 4-tap implicit GEMM over the space-to-depth image (+ position table)
         cpad = (Cin + 7) // 8 * 8
         pe = self.pos_embed
@@ -293,18 +321,32 @@ class DiffusersTransformer2DWrapper(nn.Module):
                                                            for b in self.transformer_blocks]))
         mods = (tables[:, None] + t6.view(1, B, 6, D)).contiguous()
         eps = self.norm_eps
+        def affine_mod(norm, scale, shift):
+            """(LN(x) * gamma + beta) * (1 + scale) + shift == LN(x) * (1 + scale') + shift' with
+            scale' = gamma * (1 + scale) - 1, shift' = beta * (1 + scale) + shift  ([B, D] rows, host-side)"""
+            if norm is None:
+                return scale, shift
+            g, b = norm.weight.detach().float(), norm.bias.detach().float()
+            return (g * (1 + scale) - 1).contiguous(), (b * (1 + scale) + shift).contiguous()
+
         for li, blk in enumerate(self.transformer_blocks):
             m = mods[li]                                              # [B, 6, D]: shift/scale/gate msa, mlp
-            n1 = ops.modulate(h, m[:, 1], m[:, 0], N, eps)
+            sc, sh = affine_mod(getattr(blk, "norm1", None), m[:, 1], m[:, 0])
+            n1 = ops.modulate(h, sc, sh, N, eps)
             h = self._attention(blk.attn1, n1, None, B, None, residual=h, gate=m[:, 2], rows=N)
-            h = self._attention(blk.attn2, h, ctx, B, kv_len, residual=h)
-            n2 = ops.modulate(h, m[:, 4], m[:, 3], N, eps)
-            f = ops.linear(n2, self._pack(("ff1", id(blk)), lambda: LinearPack(blk.ff.net[0].proj)), act=1)
+            if blk.attn2 is not None:     # ada_norm_single feeds attn2 the un-normalised states (UPSTREAM forward)
+                h = self._attention(blk.attn2, h, ctx if blk.attn2.is_cross else None, B, kv_len, residual=h)
+            sc, sh = affine_mod(getattr(blk, "norm2", None), m[:, 4], m[:, 3])
+            n2 = ops.modulate(h, sc, sh, N, eps)
+            if blk.ff.geglu:
+                f = ops.geglu(n2, self._pack(("ff1", id(blk)), lambda: LinearPack(blk.ff.net[0].proj, geglu=True)))
+            else:
+                f = ops.linear(n2, self._pack(("ff1", id(blk)), lambda: LinearPack(blk.ff.net[0].proj)), act=1)
             h = ops.gated_linear(f, self._pack(("ff2", id(blk)), lambda: LinearPack(blk.ff.net[2])), m[:, 5], h, N)
         fin = (self.scale_shift_table.detach().float()[None] + emb[:, None]).contiguous()     # [B, 2, D]
-        nf = ops.modulate(h, fin[:, 1], fin[:, 0], N, eps)
+        nf = ops.modulate(h, fin[:, 1], fin[:, 0], N, 1e-6)           # norm_out: LayerNorm(eps=1e-6, no affine), UPSTREAM
         out = ops.linear(nf, self._pack("proj_out", lambda: LinearPack(self.proj_out)), out_fp32=True)
-        return ops.unpatchify(out, B, hh, ww, p, self.out_channels, c_keep)
+        return ops.unpatchify(out, B, hh, ww, p, self.out_channels, min(c_keep, self.out_channels))
 
 
 def patch_lora_pack(proj, Cin, dev):

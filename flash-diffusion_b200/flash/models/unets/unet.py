@@ -278,7 +278,7 @@ class DiffusersUNet2DCondWrapper(nn.Module):
             c1 = self._pack("ce1", lambda: LinearPack(ce.linear_1))
             c2 = self._pack("ce2", lambda: LinearPack(ce.linear_2))
             q1, q2 = c1.pack(), c2.pack()
-            v = raw.cast_scale(class_labels.detach().float().contiguous(), 1.0)
+            v = c1.pad_k(raw.cast_scale(class_labels.detach().float().contiguous(), 1.0))   # odd widths: zero columns
             hc = raw.silu_f32_to_bf16(raw.gemm(v, q1["w"], bias=q1["b"], out_fp32=True))
             # emb = time_embedding(t) + class_embedding(vector): both second Linears in ONE GEMM (two K segments)
             bsum = self._pack("emb_bias", lambda: (p2["b"] + q2["b"]).contiguous())
@@ -349,7 +349,7 @@ class DiffusersUNet2DCondWrapper(nn.Module):
                     if buf is None:
                         buf = store[key] = torch.empty((ctx.shape[0], 2 * inner), device=ctx.device,
                                                        dtype=torch.bfloat16)
-                    kv = ops._linear_fwd_raw(ctx, kvp, None, out=buf)[0]
+                    kv = ops._linear_fwd_raw(kvp.pad_k(ctx), kvp, None, out=buf)[0]
             else:
                 kv = ops.linear(ctx, kvp)
             o = ops.attention_cross(proj.view(B, -1, inner), kv.view(B, -1, 2 * inner), H, head_dim=dp,

@@ -134,10 +134,23 @@ class GELUProj(nn.Module):
         return F.gelu(self.proj(x), approximate="tanh")
 
 
-class FeedForward(nn.Module):
-    def __init__(self, dim, mult=4):
+class GEGLUProj(nn.Module):
+    """diffusers `GEGLU`: value, gate = proj(x).chunk(2, -1); value * gelu(gate)  (exact erf GELU)"""
+
+    def __init__(self, dim_in, dim_out):
         super().__init__()
-        self.net = nn.ModuleList([GELUProj(dim, dim * mult), nn.Dropout(0.0), nn.Linear(dim * mult, dim)])
+        self.proj = nn.Linear(dim_in, 2 * dim_out)
+
+    def forward(self, x):
+        v, g = self.proj(x).chunk(2, dim=-1)
+        return v * F.gelu(g)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim, mult=4, geglu=False):
+        super().__init__()
+        first = GEGLUProj(dim, dim * mult) if geglu else GELUProj(dim, dim * mult)
+        self.net = nn.ModuleList([first, nn.Dropout(0.0), nn.Linear(dim * mult, dim)])
 
     def forward(self, x):
         for m in self.net:
@@ -148,21 +161,33 @@ class FeedForward(nn.Module):
 class AdaBlock(nn.Module):
     """BasicTransformerBlock(norm_type="ada_norm_single")"""
 
-    def __init__(self, dim, heads, dim_head, cross_dim, bias, eps):
+    def __init__(self, dim, heads, dim_head, cross_dim, bias, eps, affine=False, geglu=False,
+                 double_self_attention=False):
         super().__init__()
         self.scale_shift_table = nn.Parameter(torch.randn(6, dim) / dim ** 0.5)
         self.eps = eps
+        # UPSTREAM: norm1 / norm2 are nn.LayerNorm(dim, elementwise_affine=norm_elementwise_affine); attn2 exists when
+        # there is a cross_attention_dim or `double_self_attention` (then it attends to the hidden states themselves)
+        self.norm1 = nn.LayerNorm(dim, eps=eps, elementwise_affine=True) if affine else None
         self.attn1 = Attention(dim, None, heads, dim_head, bias)
-        self.attn2 = Attention(dim, cross_dim, heads, dim_head, bias)
-        self.ff = FeedForward(dim)
+        self.has_attn2 = cross_dim is not None or double_self_attention
+        self.attn2 = Attention(dim, None if double_self_attention else cross_dim, heads, dim_head, bias) \
+            if self.has_attn2 else None
+        self.double_self = double_self_attention
+        self.norm2 = nn.LayerNorm(dim, eps=eps, elementwise_affine=True) if affine else None
+        self.ff = FeedForward(dim, geglu=geglu)
+
+    def _norm(self, norm, h):
+        return norm(h) if norm is not None else F.layer_norm(h, (h.shape[-1],), eps=self.eps)
 
     def forward(self, h, ctx, mask, t6):
         B, _, D = h.shape
         sh_a, sc_a, g_a, sh_m, sc_m, g_m = (self.scale_shift_table[None] + t6.reshape(B, 6, -1)).chunk(6, dim=1)
-        n = F.layer_norm(h, (D,), eps=self.eps) * (1 + sc_a) + sh_a
+        n = self._norm(self.norm1, h) * (1 + sc_a) + sh_a
         h = g_a * self.attn1(n) + h
-        h = self.attn2(h, ctx, mask) + h
-        n = F.layer_norm(h, (D,), eps=self.eps) * (1 + sc_m) + sh_m
+        if self.attn2 is not None:               # ada_norm_single: attn2 sees the un-normalised hidden states
+            h = (self.attn2(h) if self.double_self else self.attn2(h, ctx, mask)) + h
+        n = self._norm(self.norm2, h) * (1 + sc_m) + sh_m
         return g_m * self.ff(n) + h
 
 
@@ -174,18 +199,20 @@ class PixArtTransformerOracle(nn.Module):
                  attention_head_dim=72, in_channels=4, out_channels=8, patch_size=2, attention_bias=True,
                  num_attention_heads=16, cross_attention_dim=1152, activation_fn="gelu-approximate",
                  norm_type="ada_norm_single", norm_elementwise_affine=False, norm_eps=1e-6, caption_channels=4096,
-                 **unused):
+                 double_self_attention=False, **unused):
         super().__init__()
-        assert norm_type == "ada_norm_single" and activation_fn == "gelu-approximate" and not norm_elementwise_affine
+        assert norm_type == "ada_norm_single" and activation_fn in ("gelu-approximate", "geglu")
         D = num_attention_heads * attention_head_dim
         self.p, self.out_channels, self.eps = patch_size, out_channels, norm_eps
         self.pos_embed = PatchEmbed(sample_size, patch_size, in_channels, D)
         self.adaln_single = AdaLayerNormSingle(time_embed_dim, timesteps_embedding_num_channels,
                                                projection_class_embeddings_input_dim, use_concat_vector_conditioning,
                                                num_vector_conditionings)
-        self.caption_projection = TextProjection(caption_channels, D)
+        self.caption_projection = TextProjection(caption_channels, D) if caption_channels is not None else None
         self.transformer_blocks = nn.ModuleList(
-            [AdaBlock(D, num_attention_heads, attention_head_dim, cross_attention_dim, attention_bias, norm_eps)
+            [AdaBlock(D, num_attention_heads, attention_head_dim, cross_attention_dim, attention_bias, norm_eps,
+                      affine=bool(norm_elementwise_affine), geglu=activation_fn == "geglu",
+                      double_self_attention=double_self_attention)
              for _ in range(num_layers)])
         self.scale_shift_table = nn.Parameter(torch.randn(2, D) / D ** 0.5)
         self.proj_out = nn.Linear(D, patch_size * patch_size * out_channels)
@@ -203,16 +230,17 @@ class PixArtTransformerOracle(nn.Module):
         timestep = timestep.reshape(-1).float().expand(B) if timestep.numel() == 1 else timestep.float()
         h = self.pos_embed(sample)
         t6, emb = self.adaln_single(timestep, vector)
-        ctx = self.caption_projection(ctx)
+        if self.caption_projection is not None:
+            ctx = self.caption_projection(ctx)
         for blk in self.transformer_blocks:
             h = blk(h, ctx, mask, t6)
         shift, scale = (self.scale_shift_table[None] + emb[:, None]).chunk(2, dim=1)
-        h = F.layer_norm(h, (h.shape[-1],), eps=self.eps) * (1 + scale) + shift
+        h = F.layer_norm(h, (h.shape[-1],), eps=1e-6) * (1 + scale) + shift     # UPSTREAM norm_out: eps 1e-6, no affine
         h = self.proj_out(h)
         hh, ww, p, c = H // self.p, W // self.p, self.p, self.out_channels
         h = h.reshape(B, hh, ww, p, p, c)
         h = torch.einsum("nhwpqc->nchpwq", h).reshape(B, c, hh * p, ww * p)
-        return h[:, :c_in]
+        return h[:, :c_in]                       # reference wrapper: `.sample[:, :sample_channels]`
 
     def freeze(self):
         self.eval()

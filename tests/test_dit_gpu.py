@@ -86,6 +86,44 @@ def test_small_pixart_forward(masked):
     assert _rel(out, ref) < 2e-2, _rel(out, ref)
 
 
+# Transformer2DModel(norm_type="ada_norm_single") as the reference's own wrapper test builds it
+# (tests/test_transformers/test_transformers_wrappers.py:72-85): diffusers DEFAULTS elsewhere — GEGLU feed-forward, affine
+# LayerNorms, no attention bias, norm_eps 1e-5, no caption projection — odd conditioning widths, optional second
+# self-attention instead of the cross-attention
+REF_TEST = dict(attention_head_dim=64, num_attention_heads=8, num_layers=3, out_channels=3, patch_size=2, sample_size=32,
+                time_embed_dim=512, norm_type="ada_norm_single", activation_fn="geglu", norm_elementwise_affine=True,
+                attention_bias=False, norm_eps=1e-5, caption_channels=None)
+
+
+@pytest.mark.parametrize("crossattn,vector,concat", [(True, True, True), (True, False, False), (False, True, False),
+                                                     (False, False, True)])
+def test_reference_test_transformer_variant(crossattn, vector, concat):
+    kw = dict(REF_TEST, in_channels=8 if concat else 6, cross_attention_dim=123 if crossattn else None,
+              projection_class_embeddings_input_dim=12 if vector else None, double_self_attention=not crossattn)
+    prod, ora = _pair(kw, seed=21)
+    with torch.no_grad():
+        for n, p in ora.named_parameters():              # non-trivial affine norms
+            if ".norm" in n:
+                p.add_(0.2 * torch.randn_like(p))
+    prod.load_state_dict(ora.state_dict())
+    prod.freeze(); ora.freeze()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.rand(2, 6, 32, 32, device="cuda", generator=g)
+    t = torch.randint(0, 1000, (2,), device="cuda", generator=g).float()
+    cond = {}
+    if crossattn:
+        cond["crossattn"] = torch.randn(2, 12, 123, device="cuda", generator=g)
+    if vector:
+        cond["vector"] = torch.randint(0, 256, (2, 12), device="cuda", generator=g).float()
+    if concat:
+        cond["concat"] = torch.randn(2, 2, 32, 32, device="cuda", generator=g)
+    with torch.no_grad():
+        ref = ora(x, t, {"cond": cond})
+        out = prod(x, t, {"cond": cond})
+    assert out.shape == ref.shape == (2, 3, 32, 32)
+    assert _rel(out, ref) < 2e-2, _rel(out, ref)
+
+
 def test_small_pixart_lora_student_forward():
     from flash.models.lora import LoraConfig
     from oracle.unet import LoraConfig as OLoraConfig

@@ -192,3 +192,28 @@ def test_groupnorm_statistics_from_producer_epilogue(monkeypatch):
         ref = ora(x, t, cond)
         assert _rel(fused, plain) < 2e-2, _rel(fused, plain)
         assert _rel(fused, ref) < 2e-2 and _rel(fused, ref) < 1.25 * _rel(plain, ref) + 2e-3, (_rel(fused, ref), _rel(plain, ref))
+
+
+def test_odd_context_and_vector_widths():
+    """Input widths that are not multiples of 8 bf16 (the reference's own wrapper test conditions on a 123-wide context,
+    tests/test_unet/test_unets_wrappers.py:58): the packs' K columns and the activations are zero-padded to a TMA-legal
+    row pitch — forward, and the LoRA / input gradients through a padded cross-attention."""
+    kw = dict(SMALL, cross_attention_dim=123, projection_class_embeddings_input_dim=12)
+    prod, ora = _pair(kw, lora=True, seed=5)
+    x, t, cond = _inputs(2, 32, 32, 123, 12, T=12)
+    with torch.no_grad():
+        assert _rel(prod(x, t, cond), ora(x, t, cond)) < 2e-2
+    xp, xo = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    g = torch.randn(2, 4, 32, 32, device="cuda")
+    (prod(xp, t, cond) * g).sum().backward()
+    (ora(xo, t, cond) * g).sum().backward()
+    cos = lambda a, b: (torch.dot(a.float().reshape(-1), b.float().reshape(-1)) / (a.float().norm() * b.float().norm() + 1e-30)).item()
+    assert cos(xp.grad, xo.grad) > 0.999
+    po = dict(ora.named_parameters())
+    checked = 0
+    for n, p_ in prod.named_parameters():
+        if "attn2.to_k.lora_A" in n or "attn2.to_v.lora_A" in n:          # [r, 123]: gradient of the un-padded columns
+            assert p_.grad.shape == po[n].grad.shape == (64, 123)
+            assert cos(p_.grad, po[n].grad) > 0.99, (n, cos(p_.grad, po[n].grad))
+            checked += 1
+    assert checked >= 4
