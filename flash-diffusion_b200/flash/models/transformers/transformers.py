@@ -153,12 +153,17 @@ class DiffusersTransformer2DWrapper(nn.Module):
     def __init__(self, time_embed_dim: int = 256, timesteps_embedding_num_channels: int = 256,
                  projection_class_embeddings_input_dim: Optional[int] = None,
                  use_concat_vector_conditioning: bool = False, num_vector_conditionings: Optional[int] = None,
-                 sample_size=128, num_layers=28, attention_head_dim=72, in_channels=4, out_channels=8, patch_size=2,
-                 attention_bias=True, num_attention_heads=16, cross_attention_dim=1152,
-                 activation_fn="gelu-approximate", norm_type="ada_norm_single", norm_elementwise_affine=False,
-                 norm_eps=1e-6, caption_channels=4096, double_self_attention=False, **unused):
+                 sample_size=None, num_layers=1, attention_head_dim=88, in_channels=None, out_channels=None,
+                 patch_size=None, attention_bias=False, num_attention_heads=16, cross_attention_dim=None,
+                 activation_fn="geglu", norm_type="layer_norm", norm_elementwise_affine=True,
+                 norm_eps=1e-5, caption_channels=None, double_self_attention=False, **unused):
+        """Keyword defaults are diffusers' `Transformer2DModel` defaults (the reference's wrapper subclasses it,
+        transformers/tranformers.py:19-47), so a caller that omits e.g. `caption_channels` gets what the reference
+        builds; the PixArt-alpha values are spelled out by the example script (examples/train_flash_pixart.py:65-86)."""
         super().__init__()
-        if norm_type != "ada_norm_single" or activation_fn not in ("gelu-approximate", "geglu") or patch_size != 2:
+        out_channels = in_channels if out_channels is None else out_channels
+        if norm_type != "ada_norm_single" or activation_fn not in ("gelu-approximate", "geglu") or patch_size != 2 \
+                or sample_size is None or in_channels is None:
             raise NotImplementedError("built: Transformer2DModel with norm_type='ada_norm_single', patch_size 2 and a "
                                       "'gelu-approximate' (PixArt-alpha) or 'geglu' feed-forward")
         D = num_attention_heads * attention_head_dim

@@ -195,12 +195,14 @@ class PixArtTransformerOracle(nn.Module):
     """Same constructor kwargs / keys / forward contract as the reference `DiffusersTransformer2DWrapper`."""
 
     def __init__(self, time_embed_dim=256, timesteps_embedding_num_channels=256, projection_class_embeddings_input_dim=None,
-                 use_concat_vector_conditioning=False, num_vector_conditionings=None, sample_size=128, num_layers=28,
-                 attention_head_dim=72, in_channels=4, out_channels=8, patch_size=2, attention_bias=True,
-                 num_attention_heads=16, cross_attention_dim=1152, activation_fn="gelu-approximate",
-                 norm_type="ada_norm_single", norm_elementwise_affine=False, norm_eps=1e-6, caption_channels=4096,
+                 use_concat_vector_conditioning=False, num_vector_conditionings=None, sample_size=None, num_layers=1,
+                 attention_head_dim=88, in_channels=None, out_channels=None, patch_size=None, attention_bias=False,
+                 num_attention_heads=16, cross_attention_dim=None, activation_fn="geglu",
+                 norm_type="layer_norm", norm_elementwise_affine=True, norm_eps=1e-5, caption_channels=None,
                  double_self_attention=False, **unused):
+        # keyword defaults = diffusers Transformer2DModel's; only the ada_norm_single / patch variants are restated
         super().__init__()
+        out_channels = in_channels if out_channels is None else out_channels
         assert norm_type == "ada_norm_single" and activation_fn in ("gelu-approximate", "geglu")
         D = num_attention_heads * attention_head_dim
         self.p, self.out_channels, self.eps = patch_size, out_channels, norm_eps
