@@ -21,7 +21,10 @@ _CLIP_BIGG = dict(hidden_size=1280, intermediate_size=5120, num_hidden_layers=32
                   projection_dim=1280, vocab_size=49408, max_position_embeddings=77, hidden_act="gelu")
 _T5_XXL = dict(d_model=4096, d_kv=64, d_ff=10240, num_layers=24, num_heads=64, vocab_size=32128,
                feed_forward_proj="gated-gelu", model_max_length=512)
+_T5_V11_BASE = dict(d_model=768, d_kv=64, d_ff=2048, num_layers=12, num_heads=12, vocab_size=32128,
+                    feed_forward_proj="gated-gelu", model_max_length=512)     # the reference's tests/test_embedders/test_t5_embedder.py:22
 OFFLINE_TEXT_CONFIGS = {
+    ("google/t5-v1_1-base", ""): _T5_V11_BASE,
     ("openai/clip-vit-large-patch14", ""): _CLIP_L,
     ("runwayml/stable-diffusion-v1-5", "text_encoder"): _CLIP_L,
     ("stabilityai/stable-diffusion-xl-base-1.0", "text_encoder"): _CLIP_L,

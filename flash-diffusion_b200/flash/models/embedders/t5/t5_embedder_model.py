@@ -28,6 +28,18 @@ class T5TextEmbedderConfig(BaseConditionerConfig):
     tokenizer_return_length: bool = True
     tokenizer_add_special_tokens: bool = True
 
+    def __post_init__(self):
+        """reference t5_embedder_config.py:49-66: a hidden layer needs an index within the 24 encoder blocks; the
+        projection lists default to empty and must pair up (a pydantic ValidationError otherwise)."""
+        super().__post_init__()
+        if self.layer == "hidden":
+            assert self.layer_idx is not None, "Layer index is required for hidden layer"
+            assert 0 <= abs(self.layer_idx) <= 24, "Layer index should be between 0 and 24"
+        self.projection_nn_modules = self.projection_nn_modules or []
+        self.projection_nn_modules_kwargs = self.projection_nn_modules_kwargs or []
+        assert len(self.projection_nn_modules) == len(self.projection_nn_modules_kwargs), \
+            "Number of modules and kwargs should be same"
+
 
 class T5TextEmbedder(BaseConditioner):
     def __init__(self, config: T5TextEmbedderConfig):

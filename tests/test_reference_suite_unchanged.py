@@ -7,7 +7,8 @@ inside the command, tools/reference_tests_cmd.py — the reference tree does not
 repo).  Each group runs in a fresh interpreter whose sys.path ends with the compat directory.
 
 CPU groups: data filters / mappers, timestep + torch.nn embedders (and, with FLASH_REF_TESTS_SLOW=1, the CLIP
-conditioner tests, which build real-size text encoders).  GPU groups (the denoisers / VAE are CUDA-only): denoiser
+conditioner tests and the T5 embedder's config + t5-v1_1-base cases, which build real-size text encoders: 42 + 3 tests,
+15 minutes on the build container).  GPU groups (the denoisers / VAE are CUDA-only): denoiser
 wrappers, VAE, FlashDiffusion forward.  Known, documented deviation: `test_flash_diffusion.py::test_optimizers*` train
 ALL student parameters — the B200 path differentiates the LoRA adapters and the inputs only (BASELINE north_star: "the
 student LoRA backward"), so those two are not collected."""
@@ -28,6 +29,8 @@ CPU_GROUPS = {        # one interpreter start (tens of seconds of imports on a s
 }
 SLOW_CPU_GROUPS = {
     "clip_conditioners": ["test_embedders/test_conditioners_wrapper.py", "test_embedders/test_clip_embedders.py"],
+    # config validation + the google/t5-v1_1-base cases (the other parameter set builds the 4.7 B-parameter T5-XXL)
+    "t5_base": ["test_embedders/test_t5_embedder.py", "-k", "wrong_config or shape0"],
 }
 GPU_GROUPS = {
     "unet_wrapper": ["test_unet/test_unets_wrappers.py::TestDiffusersUNet2DCondWrapper"],
@@ -47,7 +50,7 @@ sys.exit(pytest.main({args!r}))
 
 
 def run_reference_tests(files, timeout=1500):
-    args = [os.path.join(REF_TESTS, f) for f in files] + ["-q", "-p", "no:cacheprovider", "--rootdir", REF_TESTS,
+    args = [os.path.join(REF_TESTS, f) if f.startswith("test_") else f for f in files] + ["-q", "-p", "no:cacheprovider", "--rootdir", REF_TESTS,
                                                           "--tb=short"]
     code = RUNNER.format(pkg=PKG, compat=os.path.join(PKG, "compat"), args=args)
     env = {k: v for k, v in os.environ.items() if k != "PYTHONPATH"}
