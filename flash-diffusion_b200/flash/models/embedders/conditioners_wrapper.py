@@ -20,6 +20,12 @@ class ConditionerWrapper(nn.Module):
         super().__init__()
         self.conditioners = nn.ModuleList(conditioners)
 
+    def conditioner_sanity_check(self):
+        """reference :32-37 — every key of `self.ucg_keys` (an attribute the caller sets; the reference never does)
+        must be the input key of one of the conditioners."""
+        keys = {c.input_key for c in self.conditioners}
+        assert all(k in keys for k in self.ucg_keys)
+
     def forward(self, batch: Dict[str, Any], ucg_keys: List[str] = None, set_ucg_rate_zero=False,
                 *args, **kwargs):
         ucg_keys = ucg_keys or []

@@ -150,6 +150,8 @@ class Trainer:
                 summary["losses"].append({k: float(v) for k, v in outputs.items()
                                           if k.startswith("loss") and (isinstance(v, (int, float)) or
                                                                        (isinstance(v, torch.Tensor) and v.numel() == 1))})
+                if hasattr(model, "on_train_batch_end"):      # the LightningModule's own hook first, then the callbacks
+                    model.on_train_batch_end(outputs, batch, batch_idx)
                 fire("on_train_batch_end", outputs, batch, batch_idx)
                 if self.max_steps > 0 and self.global_step >= self.max_steps:
                     done = True

@@ -298,6 +298,14 @@ class TrainingPipeline(torch.nn.Module):
         if self.global_rank == 0:
             self.timer = time.perf_counter()
 
+    def on_train_batch_end(self, outputs: Dict[str, Any], batch: Any, batch_idx: int) -> None:
+        """reference trainer.py:62-74 — forward the hook to the model, and on rank 0 log the running average wall-clock
+        seconds per batch every 10 batches (the reference's only step timer)."""
+        self.model.on_train_batch_end(batch)
+        if self.global_rank == 0 and batch_idx % 10 == 0 and self.timer is not None:
+            delta = time.perf_counter() - self.timer
+            logging.info(f"Average time per batch {batch_idx} took {delta / (batch_idx + 1)} seconds")
+
     def validation_step(self, val_batch, val_idx=0):
         loss = self.model(val_batch, device=self.device)["loss"]
         return {"loss": loss, "metrics": self.model.compute_metrics(val_batch)}
