@@ -14,7 +14,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # documented deviations (DESIGN.md §9 / INTEGRATION.md)
 ALLOWED_MISSING_METHODS = {
-    "DiffusersUNet2DWrapper.forward", "DiffusersUNet2DWrapper.freeze",      # unconditional UNet2DModel: out of scope
     # the T2I-adapter recipe (out of scope): the names exist and explain themselves when constructed
     "DiffusersT2IAdapterWrapper.forward", "DiffusersT2IAdapterWrapper.freeze",
     "CannyEdgeMapper.__call__", "MidasDepthMapper.__call__",                # controlnet_aux detectors of that recipe
@@ -27,7 +26,7 @@ ALLOWED_PARAM_DIFFS = {
 }
 # the reference's wrappers subclass diffusers models and take (*args, **kwargs); here the diffusers keyword arguments are
 # spelled out
-SPELLED_OUT_CTORS = {"DiffusersUNet2DCondWrapper.__init__", "DiffusersTransformer2DWrapper.__init__",
+SPELLED_OUT_CTORS = {"DiffusersUNet2DCondWrapper.__init__", "DiffusersUNet2DWrapper.__init__", "DiffusersTransformer2DWrapper.__init__",
                      "DiffusersSD3Transformer2DWrapper.__init__"}
 
 

@@ -12,6 +12,7 @@ conditioner tests and the T5 embedder's config + t5-v1_1-base cases, which build
 wrappers, VAE, FlashDiffusion forward.  Known, documented deviation: `test_flash_diffusion.py::test_optimizers*` train
 ALL student parameters — the B200 path differentiates the LoRA adapters and the inputs only (BASELINE north_star: "the
 student LoRA backward"), so those two are not collected."""
+# (the T5 embedder file's T5-XXL cases need a 4.7 B-parameter encoder and are left to FLASH_REF_TESTS_SLOW runs)
 import os
 import subprocess
 import sys
@@ -34,6 +35,7 @@ SLOW_CPU_GROUPS = {
 }
 GPU_GROUPS = {
     "unet_wrapper": ["test_unet/test_unets_wrappers.py::TestDiffusersUNet2DCondWrapper"],
+    "unet2d_wrapper": ["test_unet/test_unets_wrappers.py::TestDiffusersUNet2DWrapper"],
     "transformer_wrapper": ["test_transformers/test_transformers_wrappers.py"],
     "vae": ["test_vaes/test_autoencoderKL.py"],
     "flash_forward": ["test_flash/test_flash_diffusion.py::TestTurbo::test_model_forward"],

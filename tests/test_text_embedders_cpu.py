@@ -125,7 +125,5 @@ def test_compat_shims_expose_the_names_the_examples_import(monkeypatch):
     with pytest.raises(OSError):
         DiffusionPipeline.from_pretrained("somebody/unknown")
     from flash.models.adapters import DiffusersT2IAdapterWrapper
-    from flash.models.unets import DiffusersUNet2DWrapper
-    for cls in (DiffusersT2IAdapterWrapper, DiffusersUNet2DWrapper):
-        with pytest.raises(NotImplementedError):
-            cls()
+    with pytest.raises(NotImplementedError):
+        DiffusersT2IAdapterWrapper()
