@@ -8,7 +8,7 @@ Default workload = BASELINE config 2 (config.workload): SDXL UNet 1024x1024 (lat
 step, batch 4 per GPU, bf16, K=32 trailing DPM-Solver++ teacher, DMD + lsgan, l2 distill, synthetic latents / text
 embeddings, random-init weights (seed 1234).  A "step" is one full `TrainingPipeline.training_step` (both optimizer
 turns, reference src/flash/trainer/trainer.py:169-218).  The teacher-rollout length depends on the sampled start index
-(flash_diffusion_model.py:167,289); the timed steps pin start_idx to the four mixture modes 0, K/4, K/2, 3K/4 in turn
+(flash_diffusion_model.py:167,289); the timed steps pin start_idx to the four mixture modes in turn (order 0, 3K/4, K/4, K/2)
 (uniform weights = stage 3 of flash_sdxl.yaml:27-32, E[n] = 5K/8) so every run does the same work.
 `--config sd15|pixart|sd3` runs BASELINE configs 1 / 3 / 4 the same way (batch = the example yaml's BATCH_SIZE);
 `--config sample` is config 5: latency of `sample(num_steps=4)` at batch 1..32 plus achieved HBM GB/s.
@@ -129,7 +129,7 @@ def _cfg(name):
 def config_dict(name, cfg, n_gpus):
     K = cfg["K"]
     d = {"workload": cfg["workload"], "name": name, "global_batch": cfg["B"] * n_gpus, "batch_per_gpu": cfg["B"], "K": K,
-         "start_idx_schedule": [0, K // 4, K // 2, 3 * K // 4], "expected_teacher_steps": 5 * K // 8,
+         "start_idx_schedule": [0, 3 * K // 4, K // 4, K // 2], "expected_teacher_steps": 5 * K // 8,
          "parallelism": f"dp{n_gpus}", "l2_policy": "inputs and activations larger than L2 (bf16 weights alone are GBs)",
          "weights": "random-init seed 1234", "distill_loss": "l2"}
     d.update(cfg["extra"])
@@ -397,7 +397,9 @@ def run_ours(args):
     lib.fd_launch_count.restype = ctypes.c_longlong
     cfg = _cfg(args.config)
     B, K = cfg["B"], cfg["K"]
-    modes = [0, K // 4, K // 2, 3 * K // 4]
+    # the four mixture modes in an order whose running mean of teacher steps (K - start_idx) is 5K/8 after every EVEN
+    # number of steps, so a --steps count that is not a multiple of 4 still times the expected rollout length
+    modes = [0, 3 * K // 4, K // 4, K // 2]
     model, pipe = cfg["build"](dev)
 
     def host_batch(i):
