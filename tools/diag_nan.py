@@ -1,4 +1,4 @@
-"""Diagnostic: first op of the Transformer2D engine that yields a non-finite value (vector-conditioned variant)."""
+"""Checker-side diagnostic (uses oracle/, like the tests; never imported by the product or bench.py): first op of the Transformer2D engine that yields a non-finite value (vector-conditioned variant)."""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "flash-diffusion_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))

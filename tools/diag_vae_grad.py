@@ -1,4 +1,4 @@
-"""Diagnostic: decoder input-gradient agreement (product vs fp32 oracle) as a function of the latent channel count."""
+"""Checker-side diagnostic (uses oracle/, like the tests; never imported by the product or bench.py): decoder input-gradient agreement (product vs fp32 oracle) as a function of the latent channel count."""
 import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "flash-diffusion_b200"))
