@@ -44,15 +44,24 @@ class DataModuleConfig(BaseConfig):
 
 
 def custom_collation_fn(samples, combine_tensors=True, combine_scalars=True):
-    """reference collation_fn.py:7-41 — dict of lists, tensors stacked, scalars to tensors"""
+    """reference collation_fn.py:7-41 — the keys COMMON to all samples; per key the type of the first value decides:
+    int / float (bools included) -> one numpy array, torch tensors -> `torch.stack`, numpy arrays -> one numpy array,
+    anything else -> the plain list.  A scalar / tensor column whose `combine_*` flag is off is dropped, as upstream."""
+    import numpy as np
     keys = set.intersection(*[set(s.keys()) for s in samples])
     out = {}
     for k in keys:
         vals = [s[k] for s in samples]
-        if combine_tensors and isinstance(vals[0], torch.Tensor):
-            out[k] = torch.stack(vals)
-        elif combine_scalars and isinstance(vals[0], (int, float)) and not isinstance(vals[0], bool):
-            out[k] = torch.tensor(vals)
+        first = vals[0]
+        if isinstance(first, (int, float)):
+            if combine_scalars:
+                out[k] = np.array(vals)
+        elif isinstance(first, torch.Tensor):
+            if combine_tensors:
+                out[k] = torch.stack(vals)
+        elif isinstance(first, np.ndarray):
+            if combine_tensors:
+                out[k] = np.array(vals)
         else:
             out[k] = vals
     return out

@@ -37,3 +37,21 @@ def test_product_mappers_and_filters_match_reference_run():
     assert out["filters"] == GOLD["filters"]
     _same(out["wrapper"], GOLD["wrapper"], "wrapper")
     assert out["filter_wrapper"] == GOLD["filter_wrapper"]
+
+
+def test_product_collation_matches_reference_run():
+    """`custom_collation_fn` (reference data/datasets/collation_fn.py:7-41): common keys only; scalars (bools included)
+    and numpy arrays become numpy arrays, tensors are stacked, everything else stays a list; a column whose combine flag
+    is off is DROPPED.  Record of the reference's own function: tests/golden/reference_collation.pt."""
+    import make_reference_collation_golden as GC
+    from flash.data.datasets import custom_collation_fn
+    gold = torch.load(os.path.join(HERE, "golden", "reference_collation.pt"), weights_only=False)
+    got = GC.run(custom_collation_fn)
+    for case in ("default", "no_tensors", "no_scalars"):
+        assert list(got[case]) == list(gold[case]), (case, list(got[case]), list(gold[case]))
+        for k, (a, b) in ((k, (got[case][k], gold[case][k])) for k in gold[case]):
+            assert a[:-1] == b[:-1], (case, k, a[:-1], b[:-1])
+            if isinstance(b[-1], torch.Tensor):
+                assert torch.equal(a[-1], b[-1]), (case, k)
+            else:
+                assert a[-1] == b[-1], (case, k)
