@@ -6,6 +6,7 @@ part of the contract here too.
 """
 import json
 import os
+import warnings
 from dataclasses import asdict, field
 from typing import Any, Dict, Union
 
@@ -37,22 +38,26 @@ class BaseConfig:
                                 f"Catch Exception {type(e)} with message: {e}") from e
 
     @classmethod
+    def _check_name(cls, d: Dict[str, Any]) -> Dict[str, Any]:
+        """the serialised `name` is required and only WARNED about when it is another class's (reference :70-77, :131-138)"""
+        name = d.pop("name")
+        if name != cls.__name__:
+            warnings.warn(f"You are trying to load a `{cls.__name__}` while a `{name}` is given.")
+        return d
+
+    @classmethod
     def from_json(cls, json_path: str) -> "BaseConfig":
-        d = cls._dict_from_json(json_path)
-        name = d.pop("name", None)
-        if name is not None and name != cls.__name__:
-            raise ValueError(f"You are trying to load a `{cls.__name__}` while a `{name}` is given.")
-        return cls.from_dict(d)
+        return cls.from_dict(cls._check_name(cls._dict_from_json(json_path)))
 
     @classmethod
     def from_yaml(cls, yaml_path: str) -> "BaseConfig":
         with open(yaml_path, "r") as f:
-            d = yaml.safe_load(f)
-        d = dict(d or {})
-        name = d.pop("name", None)
-        if name is not None and name != cls.__name__:
-            raise ValueError(f"You are trying to load a `{cls.__name__}` while a `{name}` is given.")
-        return cls.from_dict(d)
+            try:
+                d = yaml.safe_load(f)
+            except yaml.YAMLError as e:
+                raise yaml.YAMLError(f"File {yaml_path} not loadable. Maybe not yaml ? \n"
+                                     f"Catch Exception {type(e)} with message: {e}") from e
+        return cls.from_dict(cls._check_name(d))
 
     # ---- serialisation
     def to_dict(self) -> dict:
