@@ -147,6 +147,8 @@ class Trainer:
                 batch = self._to_device(batch, device)
                 outputs = model.training_step(batch, batch_idx)
                 self.global_step += 1
+                if hasattr(model, "step_lr_schedulers"):
+                    model.step_lr_schedulers("step", self.global_step)
                 summary["losses"].append({k: float(v) for k, v in outputs.items()
                                           if k.startswith("loss") and (isinstance(v, (int, float)) or
                                                                        (isinstance(v, torch.Tensor) and v.numel() == 1))})
@@ -156,6 +158,8 @@ class Trainer:
                 if self.max_steps > 0 and self.global_step >= self.max_steps:
                     done = True
                     break
+            if hasattr(model, "step_lr_schedulers") and not done:       # only an epoch that ran all its batches counts
+                model.step_lr_schedulers("epoch", epoch + 1)
         fire("on_train_end")
         summary["steps"] = self.global_step
         if self.default_root_dir and self.global_rank == 0:

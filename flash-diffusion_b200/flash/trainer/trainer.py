@@ -210,7 +210,20 @@ class TrainingPipeline(torch.nn.Module):
         self.optims, self._buckets = optimizers, buckets
         self.lr_schedulers = self.configure_lr_schedulers()
         self.sync_replicas()
-        return optimizers
+        if self.lr_schedulers is None:
+            return optimizers
+        return optimizers, list(self.lr_schedulers)          # Lightning's (optimizers, lr_scheduler configs) form
+
+    def step_lr_schedulers(self, interval: str, count: int):
+        """What Lightning does with the configs returned above under AUTOMATIC optimisation (one optimizer): a scheduler
+        whose `interval` is "step" / "epoch" advances every `frequency` optimizer steps / epochs.  With several
+        optimizers the reference runs manual optimisation and never calls `scheduler.step()` itself
+        (trainer.py:169-218), so — like under Lightning — its schedulers stay where they started."""
+        if not self.automatic_optimization or not self.lr_schedulers:
+            return
+        for cfg in self.lr_schedulers:
+            if cfg is not None and cfg["interval"] == interval and count % max(int(cfg["frequency"]), 1) == 0:
+                cfg["scheduler"].step()
 
     def sync_replicas(self):
         """What Lightning's DDP wrap does at construction: every rank starts from rank 0's parameters and buffers
