@@ -6,7 +6,7 @@ from here).
 """
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int32, c_int64, c_void_p
+from ctypes import Structure, c_char_p, c_float, c_int32, c_int64, c_void_p
 
 import torch
 

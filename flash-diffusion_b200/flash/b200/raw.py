@@ -3,8 +3,7 @@
 Every function launches hand-written sm_100a kernels from libflashb200.so on the current CUDA
 stream.  Tensors must be CUDA tensors; bf16 activations are channels-last ([rows, C] / NHWC).
 """
-import ctypes
-from ctypes import byref, c_float, c_int32, c_int64, c_void_p
+from ctypes import byref, c_float, c_int32, c_int64
 
 import torch
 

@@ -10,7 +10,6 @@ a directory path) the real `from_pretrained` is used.
 """
 import hashlib
 import re
-from types import SimpleNamespace
 
 import torch
 

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from ...b200 import ops, raw
-from ...b200.ops import ConvPack, LinearPack
+from ...b200.ops import LinearPack
 from .unet import (DiffusersUNet2DCondWrapper, Downsample2D, ResnetBlock2D, TimestepEmbedding, Upsample2D, _Container)
 
 DOWN_TYPES = ("DownBlock2D", "AttnDownBlock2D")

@@ -12,7 +12,6 @@ integer timestep (off-schedule DMD / GAN timesteps included).
 """
 import math
 from types import SimpleNamespace
-from typing import List, Optional, Union
 
 import numpy as np
 import torch

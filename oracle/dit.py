@@ -11,8 +11,7 @@ published diffusers implementation; state-dict keys follow the names the referen
 (examples/train_flash_pixart.py:90-172: `adaln_single.timestep_embedder.linear_{1,2}`,
 `adaln_single.add_embedding.<i>.linear_{1,2}`).
 """
-import math
-from typing import Dict, Optional
+from typing import Dict
 
 import numpy as np
 import torch

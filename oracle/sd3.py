@@ -8,7 +8,6 @@ examples/train_flash_sd3.py:65-77.  PARITY UNPINNED (see oracle/unet.py); pinned
 """
 from typing import Dict
 
-import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F

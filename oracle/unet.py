@@ -15,7 +15,7 @@ examples/train_flash_sdxl.py:123-134, examples/train_flash_sd.py:119-152) and pa
 (SURVEY.md Appendix B.6).
 """
 import math
-from typing import Dict, List, Optional, Union
+from typing import Dict, List, Union
 
 import torch
 import torch.nn as nn
