@@ -9,7 +9,10 @@ relu2_2, relu3_3, relu4_3, relu5_3 (64, 128, 256, 512, 512 channels), unit-norma
 (x / (||x||_2 + 1e-10)), squared difference, per-layer non-negative 1x1 "lin" weights, spatial mean, sum over layers.
 State-dict keys as in the lpips package (`net.slice1.0.weight`, `lin0.model.1.weight`, ...) so real weights would load.
 
-PARITY UNPINNED: neither the lpips package nor the VGG16 / lin weights are available offline; random weights.
+PARITY: the VGG16 feature stack (13 convolutions, pooling, the five taps) is pinned to torchvision's own
+`vgg16().features` — the module the lpips package wraps — in tests/test_lpips_vgg_torchvision_cpu.py.  UNPINNED: the
+lpips-specific glue (scaling layer, unit normalisation, lin layers, reduction), restated from the paper / package source;
+neither the lpips package nor the trained VGG16 / lin weights are available offline (random weights throughout).
 """
 import torch
 import torch.nn as nn
