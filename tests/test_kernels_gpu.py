@@ -191,3 +191,42 @@ def test_attention_generic_head_dims_and_mask(raw, B, H, Nq, Nkv, d, masked):
     ref = (torch.softmax(s, dim=-1) @ vf).transpose(1, 2).reshape(B, Nq, H * d)
     assert _rel(o, ref) < 1e-2, _rel(o, ref)
     assert _rel(lse, torch.logsumexp(s, dim=-1)) < 1e-4
+
+
+@pytest.mark.parametrize("kind,K,start", [("dpm", 32, 0), ("dpm", 32, 24), ("dpm", 4, 1), ("flow", 28, 0)])
+def test_fused_cfg_solver_kernel_is_exact_for_a_point_mass(kind, K, start):
+    """Size-independent property of the fused CFG + solver kernel (fd_step_cfg_dpm) at the BASELINE latent size
+    [4, 4, 128, 128]: with the exact denoiser of a point mass at c — eps = (x - alpha_t c) / sigma_t on both CFG branches,
+    any guidance weight — DPM-Solver++ (1st order and 2M) and the rectified-flow Euler step are exact, so a rollout of
+    any length from any start index stays on the ray x_t = alpha_t c + sigma_t n and ends at c
+    (tests/test_scheduler_properties_cpu.py is the host-side twin)."""
+    from flash.schedulers import DPMSolverMultistepScheduler, FlowMatchEulerDiscreteScheduler
+    g = torch.Generator(device="cuda").manual_seed(K + start)
+    shape = (4, 16 if kind == "flow" else 4, 128, 128)
+    c = torch.randn(shape, device="cuda", generator=g)
+    n = torch.randn(shape, device="cuda", generator=g)
+    w = 7.5
+    if kind == "dpm":
+        s = DPMSolverMultistepScheduler.from_pretrained("stabilityai/stable-diffusion-xl-base-1.0", subfolder="scheduler",
+                                                        timestep_spacing="trailing")
+        s.set_timesteps(K)
+        ac = s.alphas_cumprod.double()
+        ts = s.timesteps[start:]
+        a0 = float(ac[int(ts[0])])
+        x = (a0 ** 0.5 * c + (1 - a0) ** 0.5 * n).float().contiguous()
+        scratch = torch.zeros_like(x)
+        for t in ts:
+            a = float(ac[int(t)])
+            eps = ((x - a ** 0.5 * c) / (1 - a) ** 0.5).contiguous()
+            assert torch.allclose(eps, n, atol=5e-3)
+            s.fused_cfg_step(eps, eps.clone(), w, t, x, scratch)           # w e + (1 - w) e = e
+    else:
+        s = FlowMatchEulerDiscreteScheduler.from_pretrained("stabilityai/stable-diffusion-3-medium", subfolder="scheduler")
+        s.set_timesteps(K)
+        sig0 = float(s.sigmas[0])
+        x = ((1 - sig0) * c + sig0 * n).float().contiguous()
+        scratch = torch.zeros_like(x)
+        v = (n - c).contiguous()
+        for t in s.timesteps:
+            s.fused_cfg_step(v, v.clone(), w, t, x, scratch)
+    assert torch.allclose(x, c, atol=2e-3), float((x - c).abs().max())
