@@ -458,9 +458,15 @@ class FlashDiffusion(BaseModel):
     def log_samples(self, batch: Dict[str, Any], input_shape=None, guidance_scale: float = 1.0,
                     teacher_guidance_scale: float = 5.0, max_samples: int = 8, num_steps=20, device="cpu",
                     log_teacher_samples=False, conditioner_inputs: Dict = None, conditioner_uncond_inputs: Dict = None,
-                    **sample_kwargs):
+                    adapter_conditioning_scale: float = 1.0, **sample_kwargs):
         """{"samples_{n}_steps/{SamplerClass}_{cfg}_cfg/student": tensor, ".../teacher": tensor} for every n in
         `num_steps`; the number of samples is capped by `max_samples` and by the shortest conditioning entry."""
+        return self._log_samples(batch, input_shape, guidance_scale, teacher_guidance_scale, max_samples, num_steps,
+                                 device, log_teacher_samples, conditioner_inputs, conditioner_uncond_inputs,
+                                 adapter_conditioning_scale=adapter_conditioning_scale, **sample_kwargs)
+
+    def _log_samples(self, batch, input_shape, guidance_scale, teacher_guidance_scale, max_samples, num_steps, device,
+                     log_teacher_samples, conditioner_inputs, conditioner_uncond_inputs, **sample_kwargs):
         steps = [num_steps] if isinstance(num_steps, int) else list(num_steps)
         logs = {}
         N = max_samples

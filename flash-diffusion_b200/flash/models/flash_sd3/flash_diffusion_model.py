@@ -284,6 +284,15 @@ class FlashDiffusionSD3(FlashDiffusion):
 
     # ------------------------------------------------------------------ few-step sampler (reference :694-838)
     @torch.no_grad()
+    def log_samples(self, batch: Dict[str, Any], input_shape=None, guidance_scale: float = 1.0,
+                    teacher_guidance_scale: float = 5.0, max_samples: int = 8, num_steps=20, device="cpu",
+                    log_teacher_samples=False, conditioner_inputs: Dict = None, conditioner_uncond_inputs: Dict = None,
+                    **sample_kwargs):
+        """reference flash_sd3/flash_diffusion_model.py:845-941 (no adapter argument in the SD3 twin)"""
+        return self._log_samples(batch, input_shape, guidance_scale, teacher_guidance_scale, max_samples, num_steps,
+                                 device, log_teacher_samples, conditioner_inputs, conditioner_uncond_inputs,
+                                 **sample_kwargs)
+
     def sample(self, z, num_steps=20, guidance_scale=1.0, teacher_guidance_scale=5.0, conditioner_inputs=None,
                uncond_conditioner_inputs=None, max_samples=None, verbose=False, log_teacher_samples=False,
                generator=None):

@@ -19,8 +19,6 @@ ALLOWED_MISSING_METHODS = {
     "CannyEdgeMapper.__call__", "MidasDepthMapper.__call__",                # controlnet_aux detectors of that recipe
 }
 ALLOWED_PARAM_DIFFS = {
-    # the reference passes this through to sample(); here it travels in **sample_kwargs
-    "FlashDiffusion.log_samples": {"adapter_conditioning_scale"},
     # rank_zero_only-wrapped callback hook: (*a, **k) forwarding wrapper
     "WandbSampleLogger.log_samples": {"self", "trainer", "pl_module", "outputs", "batch", "batch_idx", "split"},
 }
